@@ -1,0 +1,158 @@
+/*
+ * mrg_fulmov.h -- C ABI of the B200 (sm_100a) replacement for the /fulmov/
+ * particle hot path of @mrg37-080A.f03 (F:n = that file, line n).
+ *
+ * The reference has no FFI: the seam is the Fortran subroutine
+ *   fulmov(x,y,z,vx,vy,vz,qmult,wmult,npr,ipc,ksp,ipar,size)      F:1044
+ * plus the COMMON blocks it reads and writes (F:1061-1120).  Every entry
+ * point below names the reference lines it replaces; the ISO_C_BINDING shim
+ * a maintainer adds on the Fortran side is in INTEGRATION.md and
+ * fortran/mrg_gpu.f03.
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on
+ * failure (mrg_last_error() gives the text); plain pointers and sizes only;
+ * all grids use the reference layout real(C_DOUBLE)(-2:mx+1,-1:my+1,-2:mz+1),
+ * i fastest, mxyzA = (mx+4)(my+3)(mz+4) doubles (param_080A.h:33); particle
+ * counts are int64_t; one context per rank / GPU, driven by one host thread.
+ * There is no CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef MRG_FULMOV_H
+#define MRG_FULMOV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrg_ctx mrg_ctx;
+
+enum {
+  MRG_OK = 0,
+  MRG_ERR_ARG = 1,      /* bad argument                                    */
+  MRG_ERR_CUDA = 2,     /* CUDA runtime error (no device, OOM, launch)      */
+  MRG_ERR_NCCL = 3,     /* NCCL missing or failed                           */
+  MRG_ERR_STATE = 4     /* call order (fields not set, species empty, ...)  */
+};
+
+#define MRG_MAX_SPECIES 4      /* qspec(4), wspec(4): F:1100               */
+#define MRG_UNIQUE_ID_BYTES 128
+
+/* Per-call scalars that fulmov reads from COMMON /parm1/,/parm2/,/profl/.  */
+typedef struct mrg_step_params {
+  double dt, adt, hdt, aimpl;        /* F:1094; adt,hdt are passed, not
+                                        derived: trans zeroes them at it=0
+                                        (F:678-680)                         */
+  double bxc, byc, bzc;              /* F:1097, set at F:8601-8603          */
+  int32_t ifilx, ifily, ifilz;       /* F:1085 (forced to 1 at F:368-370)   */
+  int32_t drive_on;                  /* 0 skips the ipc=0 kick loop entirely
+                                        (for tests); 1 = reference          */
+  double Ez00, zcent, ycent1, ycent2;/* /profl/ F:1109-1110                 */
+} mrg_step_params;
+
+/* Sizes / grid constants.  Derives hx..,hxi..,xmaxe.. exactly as
+ * F:8454-8484 and F:8567-8577.  `device` is the CUDA ordinal; rank/nranks
+ * mirror ipar-1 and size of F:215-219.                                      */
+int mrg_create(mrg_ctx** ctx, int32_t mx, int32_t my, int32_t mz, double xmax,
+               double ymax, double zmax, int32_t nspecies, int32_t rank,
+               int32_t nranks, int32_t device);
+int mrg_destroy(mrg_ctx* ctx);
+const char* mrg_last_error(void);
+/* "sm_100a;<build flags>" -- lets a caller check what was loaded.           */
+const char* mrg_build_info(void);
+
+/* NCCL communicator for the moment sums that replace mpi_allreduce at
+ * F:1312-1315, F:2379-2384 and F:2533.  Rank 0 calls mrg_comm_unique_id and
+ * the host broadcasts the 128 bytes (MPI_Bcast in the Fortran host,
+ * torch.distributed in bench.py); every rank then calls mrg_comm_init.
+ * With nranks == 1 neither call is needed.                                  */
+int mrg_comm_unique_id(unsigned char id[MRG_UNIQUE_ID_BYTES]);
+int mrg_comm_init(mrg_ctx* ctx, const unsigned char id[MRG_UNIQUE_ID_BYTES]);
+
+/* Particles.  The host arrays are the reference's x(np0).. (F:121-122,
+ * F:1056); the rank owns l = first, first+stride, ... <= npr (1-based, as in
+ * `do l= ipar,npr,size`, F:1162) and only those are copied.  Download writes
+ * them back in the original l order whatever the device order is (needed by
+ * restrt, F:9622-9668, and diag1).                                          */
+int mrg_upload_particles(mrg_ctx* ctx, int32_t ksp, const double* x,
+                         const double* y, const double* z, const double* vx,
+                         const double* vy, const double* vz, int64_t npr,
+                         int64_t first, int64_t stride);
+int mrg_download_particles(mrg_ctx* ctx, int32_t ksp, double* x, double* y,
+                           double* z, double* vx, double* vy, double* vz,
+                           int64_t npr, int64_t first, int64_t stride);
+/* Number of particles of species ksp resident on this GPU.                  */
+int64_t mrg_num_local(mrg_ctx* ctx, int32_t ksp);
+
+/* Synthetic two-flux-bundle load generated on the device with the exact
+ * LCG skip-ahead: same values as loadpt, F:8937-9040, for the owned l with
+ * `ppc` particles per cell (the source hard-codes 32, F:8941).  ranfa/ranfb
+ * (COMMON /ranfa/,/ranfb/ after rantbl, F:9255-9256) are advanced as the
+ * serial loader would.                                                      */
+int mrg_loadpt(mrg_ctx* ctx, int32_t ksp, int32_t ppc, double vth, double vdr,
+               double vbeam, int32_t* ranfa, int32_t* ranfb);
+
+/* COMMON /fields/ (F:1066): f12 = ex,ey,ez,bx,by,bz,ex0,ey0,ez0,bx0,by0,bz0,
+ * each mxyzA doubles on the HOST; bit i of mask selects f12[i] (unselected
+ * pointers may be NULL).  Invalidates the cached prepared fields.           */
+int mrg_set_fields(mrg_ctx* ctx, uint32_t mask, const double* const f12[12]);
+/* Same, from DEVICE pointers (resident field solve, bench `value` leg).     */
+int mrg_set_fields_device(mrg_ctx* ctx, uint32_t mask,
+                          const double* const f12_dev[12]);
+
+/* fulmov, F:1044-1390, for this rank's particles of species ksp (1-based):
+ *   section 0 (F:1127-1152)  blend + outmesh3 + filt3e, cached while neither
+ *                            the fields nor aimpl/bxc../ifil* change;
+ *   ipc >= 1  (F:1162-1309, 1375-1386) half-step gather, implicit rotation,
+ *             predicted position/velocity, partbc, srimp1 + srimp2 scatter,
+ *             NCCL sum over ranks, vmesh3/vmesh1 fold;
+ *   ipc == 0  (F:1162-1365) the same gather/rotation, in-place update,
+ *             partbc, E x B drive kick with the rank's ranfp stream.
+ * wkix/wkih receive the rank-summed values of F:1312-1317.  ranfb is the
+ * rank's COMMON /ranfb/ state (in/out; only ipc==0 advances it).            */
+int mrg_fulmov(mrg_ctx* ctx, int32_t ksp, double qmult, double wmult,
+               int32_t ipc, const mrg_step_params* p, int32_t* ranfb,
+               double* wkix, double* wkih);
+
+/* Moments of the last ipc>=1 call for species ksp into the caller's
+ * COMMON /srimp7/ arrays qix|qex, qiy|qey, qiz|qez, qi|qe (F:1067), each
+ * mxyzA doubles on the host.  folded=1: after vmesh3/vmesh1 (what srimp1/2
+ * return); folded=0: the rank-summed arrays before the fold.  NULL pointers
+ * are skipped.                                                              */
+int mrg_get_moments(mrg_ctx* ctx, int32_t ksp, double* qjx, double* qjy,
+                    double* qjz, double* q, int32_t folded);
+/* Device pointers of the same four arrays (folded), valid until the next
+ * mrg_fulmov(ipc>=1) of that species; for a device-resident field solve.    */
+int mrg_get_moments_device(mrg_ctx* ctx, int32_t ksp, const double* dev4[4]);
+
+/* The prepared fields exa,eya,eza,bxa,bya,bza of F:1127-1148 (host, mxyzA
+ * doubles each; NULL skipped).  Runs the preparation if it is stale.        */
+int mrg_get_prepared_fields(mrg_ctx* ctx, const mrg_step_params* p,
+                            double* const a6[6]);
+
+/* Re-order the species' particles in HBM by cell of x + lookahead*v (after
+ * the periodic/wall wrap).  Pure maintenance: results of every other call
+ * are independent of the device order up to fp64 summation order.           */
+int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
+
+/* Kernel selection and tuning knobs (name/value); unknown names fail.
+ *   "deposit"  0 = per-particle global atomics, 1 = warp pre-reduction
+ *              (match_any + shuffle) then global atomics, 2 = cell-run
+ *              register accumulation + warp pre-reduction (default)          */
+int mrg_set_option(mrg_ctx* ctx, const char* name, int64_t value);
+
+/* Counters since the last reset: [0] kernels launched by this library,
+ * [1] bytes copied host->device, [2] bytes copied device->host.             */
+int mrg_get_counters(mrg_ctx* ctx, int64_t out[3], int32_t reset);
+
+/* Device-time of the particle kernel of the last mrg_fulmov call (CUDA
+ * events on the library's stream), in milliseconds.                         */
+int mrg_last_kernel_ms(mrg_ctx* ctx, double* ms);
+
+/* Block the host until all work queued by this context has finished.        */
+int mrg_synchronize(mrg_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRG_FULMOV_H */

@@ -1,0 +1,759 @@
+// mrg_api.cu -- context management and the C ABI of include/mrg_fulmov.h.
+// Host-side orchestration of the /fulmov/ path: field upload + preparation
+// cache, particle residency, the two particle passes, the NCCL moment sum,
+// the fold, the drive kick and the cell sort.  F:n = @mrg37-080A.f03 line n.
+#include "../../include/mrg_fulmov.h"
+#include "mrg_kernels.cuh"
+
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+using namespace mrg;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(MRG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+
+#define CKL(ctx)                                                                          \
+  do {                                                                                    \
+    (ctx)->launches++;                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                  \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(MRG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- NCCL through dlopen: the library loads without NCCL (CPU symbol check,
+// single-GPU runs) and binds to whatever libnccl.so.2 the process already has.
+struct Uid { char internal[MRG_UNIQUE_ID_BYTES]; };   // ncclUniqueId: 128 bytes, passed by value
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Uid, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+int nccl_load() {
+  if (g_nccl.h) return MRG_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names) {
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(MRG_ERR_NCCL, std::string("dlopen libnccl.so.2 failed: ") + dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Uid, int))dlsym(h, "ncclCommInitRank");
+  g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+    return fail(MRG_ERR_NCCL, "libnccl is missing a required symbol");
+  g_nccl.h = h;
+  return MRG_OK;
+}
+std::string nccl_err(int rc) {
+  return g_nccl.GetErrorString ? std::string(g_nccl.GetErrorString(rc)) : ("nccl error " + std::to_string(rc));
+}
+
+struct Species {
+  double* d[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int* id = nullptr;       // nullptr = identity order
+  long long n = 0, cap = 0;
+  double* M4 = nullptr;    // raw moments [ntot][4] + 2 (wkix, wkih)
+  double* out4[4] = {nullptr, nullptr, nullptr, nullptr};  // folded, reference layout
+  bool have_moments = false;
+};
+
+struct PrepKey {
+  double aimpl, bxc, byc, bzc;
+  int ifilx, ifily, ifilz;
+  unsigned long long version;
+  bool operator==(const PrepKey& o) const {
+    return aimpl == o.aimpl && bxc == o.bxc && byc == o.byc && bzc == o.bzc && ifilx == o.ifilx &&
+           ifily == o.ifily && ifilz == o.ifilz && version == o.version;
+  }
+};
+
+}  // namespace
+
+struct mrg_ctx {
+  int device = 0, rank = 0, nranks = 1, nspecies = 2;
+  GP g;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // fields
+  double* f12[12] = {};
+  double* A6[6] = {};
+  double* T1[6] = {};
+  double* T2[6] = {};
+  double* F6 = nullptr;
+  double* tmp6[6] = {};    // unpack scratch for mrg_get_prepared_fields (lazy)
+  unsigned long long field_version = 0;
+  bool fields_set = false, prep_valid = false;
+  PrepKey prep_key{};
+  // species
+  Species sp[MRG_MAX_SPECIES];
+  double* alt[6] = {};     // shared spare particle buffer (sort / download)
+  int* alt_id = nullptr;
+  long long alt_cap = 0;
+  // scratch
+  double* wk_partial = nullptr; long long wk_partial_cap = 0;
+  double* wk2 = nullptr;
+  int* sort_key = nullptr; long long sort_key_cap = 0;
+  int* hist = nullptr; int* cursor = nullptr; long long ncell = 0;
+  int* scan_tiles = nullptr; long long scan_tiles_cap = 0;
+  unsigned* slab_bits = nullptr; int* slab_words = nullptr; long long slab_words_cap = 0;
+  int* slab_list = nullptr; long long slab_list_cap = 0;
+  int* slab_count = nullptr;
+  double* h_pinned = nullptr; size_t h_pinned_bytes = 0;
+  // nccl
+  void* comm = nullptr;
+  // options / counters
+  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2;
+  long long launches = 0, h2d = 0, d2h = 0;
+  double last_kernel_ms = 0.0;
+};
+
+namespace {
+
+int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+int ensure(mrg_ctx* c, void** p, long long* cap, long long need, size_t elem) {
+  if (*cap >= need && *p) return MRG_OK;
+  if (*p) CK(cudaFree(*p));
+  *p = nullptr;
+  long long ncap = std::max<long long>(need, 64);
+  CK(cudaMalloc(p, (size_t)ncap * elem));
+  *cap = ncap;
+  (void)c;
+  return MRG_OK;
+}
+
+int ensure_pinned(mrg_ctx* c, size_t bytes) {
+  if (c->h_pinned_bytes >= bytes) return MRG_OK;
+  if (c->h_pinned) CK(cudaFreeHost(c->h_pinned));
+  c->h_pinned = nullptr;
+  CK(cudaMallocHost((void**)&c->h_pinned, bytes));
+  c->h_pinned_bytes = bytes;
+  return MRG_OK;
+}
+
+int check_species(mrg_ctx* c, int ksp) {
+  if (!c) return fail(MRG_ERR_ARG, "null context");
+  if (ksp < 1 || ksp > c->nspecies) return fail(MRG_ERR_ARG, "ksp out of range (1-based species index)");
+  return MRG_OK;
+}
+
+long long owned_count(long long npr, long long first, long long stride) {
+  if (npr < first) return 0;
+  return (npr - first) / stride + 1;   // l = first, first+stride, ... <= npr
+}
+
+int alloc_species(mrg_ctx* c, Species& s, long long n) {
+  long long cap = ((n + 63) / 64) * 64 + 64;
+  if (s.cap < cap) {
+    for (int k = 0; k < 6; k++) {
+      if (s.d[k]) CK(cudaFree(s.d[k]));
+      s.d[k] = nullptr;
+      CK(cudaMalloc((void**)&s.d[k], (size_t)cap * sizeof(double)));
+    }
+    s.cap = cap;
+  }
+  if (s.id) { CK(cudaFree(s.id)); s.id = nullptr; }
+  s.n = n;
+  if (!s.M4) {
+    CK(cudaMalloc((void**)&s.M4, ((size_t)c->g.ntot * 4 + 2) * sizeof(double)));
+    for (int k = 0; k < 4; k++) CK(cudaMalloc((void**)&s.out4[k], (size_t)c->g.ntot * sizeof(double)));
+  }
+  s.have_moments = false;
+  return MRG_OK;
+}
+
+// spare particle buffer; exact=true keeps its capacity equal to the species'
+// so that buffers (and their id arrays) can be swapped by mrg_sort
+int ensure_alt(mrg_ctx* c, long long cap, bool exact) {
+  if (exact ? (c->alt_cap == cap) : (c->alt_cap >= cap)) return MRG_OK;
+  for (int k = 0; k < 6; k++) {
+    if (c->alt[k]) CK(cudaFree(c->alt[k]));
+    c->alt[k] = nullptr;
+    CK(cudaMalloc((void**)&c->alt[k], (size_t)cap * sizeof(double)));
+  }
+  if (c->alt_id) CK(cudaFree(c->alt_id));
+  c->alt_id = nullptr;
+  CK(cudaMalloc((void**)&c->alt_id, (size_t)cap * sizeof(int)));
+  c->alt_cap = cap;
+  return MRG_OK;
+}
+
+ParticleSoA soa(const Species& s) {
+  ParticleSoA P;
+  P.x = s.d[0]; P.y = s.d[1]; P.z = s.d[2]; P.vx = s.d[3]; P.vy = s.d[4]; P.vz = s.d[5];
+  P.id = s.id; P.n = s.n;
+  return P;
+}
+
+// exclusive scan of n ints (in -> out, may alias), optional grand total (device int)
+int scan_excl(mrg_ctx* c, const int* in, int* out, long long n, int* total_dev) {
+  const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  int rc = ensure(c, (void**)&c->scan_tiles, &c->scan_tiles_cap, ntiles, sizeof(int));
+  if (rc) return rc;
+  k_scan_reduce<<<ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, c->scan_tiles); CKL(c);
+  k_scan_tiles<<<1, SCAN_BLOCK, 0, c->stream>>>(c->scan_tiles, ntiles, total_dev); CKL(c);
+  k_scan_apply<<<ntiles, SCAN_BLOCK, 0, c->stream>>>(in, n, c->scan_tiles, out); CKL(c);
+  return MRG_OK;
+}
+
+// F:1127-1148 on the device, cached on (fields version, aimpl, dc, ifil*)
+int ensure_prep(mrg_ctx* c, const mrg_step_params* p) {
+  if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
+  if (p->ifilx < 0 || p->ifily < 0 || p->ifilz < 0) return fail(MRG_ERR_ARG, "negative filter count");
+  PrepKey key{p->aimpl, p->bxc, p->byc, p->bzc, p->ifilx, p->ifily, p->ifilz, c->field_version};
+  if (c->prep_valid && key == c->prep_key) return MRG_OK;
+  const GP& g = c->g;
+  const long long nin = (long long)g.mx * (g.my + 1) * g.mz;
+  const int B = 256;
+  CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->f12[k];
+  Ptr6 A, T1, T2; for (int k = 0; k < 6; k++) { A.p[k] = c->A6[k]; T1.p[k] = c->T1[k]; T2.p[k] = c->T2[k]; }
+  k_blend<<<grid_for(nin, B), B, 0, c->stream>>>(g, f, A, T1, p->aimpl, 1.0 - p->aimpl, p->bxc, p->byc, p->bzc); CKL(c);
+  Ptr6 src = T1, dst = T2;
+  auto as_const = [](const Ptr6& q) { CPtr6 r; for (int k = 0; k < 6; k++) r.p[k] = q.p[k]; return r; };
+  for (int n = 0; n < p->ifilz; n++) { k_filter<2><<<grid_for(nin, B), B, 0, c->stream>>>(g, as_const(src), dst); CKL(c); std::swap(src, dst); }
+  for (int n = 0; n < p->ifilx; n++) { k_filter<0><<<grid_for(nin, B), B, 0, c->stream>>>(g, as_const(src), dst); CKL(c); std::swap(src, dst); }
+  for (int n = 0; n < p->ifily; n++) { k_filter<1><<<grid_for(nin, B), B, 0, c->stream>>>(g, as_const(src), dst); CKL(c); std::swap(src, dst); }
+  k_finalize<<<grid_for(g.ntot, B), B, 0, c->stream>>>(g, as_const(A), as_const(src), c->F6, p->bxc, p->byc, p->bzc); CKL(c);
+  c->prep_key = key;
+  c->prep_valid = true;
+  return MRG_OK;
+}
+
+// Simpson table fv2 of loadpt, F:8885-8909 (host side of mrg_loadpt)
+void loadpt_table(double vth, double vdr, double fv2[101], double* v2, double* dv2) {
+  const double vrg1 = vdr / vth;
+  double vv = std::max(-3.0, -vrg1);
+  const double dv = (3.0 - vv) / 100.0;
+  *v2 = vv * vth;
+  *dv2 = dv * vth;
+  auto fun2 = [vrg1](double v) { return exp(-(v * v)) * (v + vrg1); };   // F:9195
+  fv2[0] = 0.0;
+  for (int j = 1; j <= 100; j++) {
+    double s = 0.0;
+    const double sdv = dv / 1000.0;
+    for (int k = 1; k <= 500; k++) {
+      vv = vv + 2.0 * sdv;
+      s = s + 4.0 * fun2(vv - sdv) + 2.0 * fun2(vv);
+    }
+    s = (s + 4.0 * fun2(vv + sdv) + fun2(vv + 2.0 * sdv)) * sdv / 3.0;
+    fv2[j] = fv2[j - 1] + s;
+  }
+  const double norm = fv2[100];
+  for (int j = 0; j <= 100; j++) fv2[j] = fv2[j] / norm;
+}
+
+}  // namespace
+
+// ===========================================================================
+extern "C" {
+
+const char* mrg_last_error(void) { return g_err.c_str(); }
+
+const char* mrg_build_info(void) {
+  return "mrg_fulmov sm_100a; nvcc " __DATE__ "; fp64; deposit modes 0/1/2";
+}
+
+int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, double ymax, double zmax,
+               int32_t nspecies, int32_t rank, int32_t nranks, int32_t device) {
+  if (!out) return fail(MRG_ERR_ARG, "null output pointer");
+  *out = nullptr;
+  if (mx < 4 || my < 2 || mz < 4) return fail(MRG_ERR_ARG, "grid too small (need mx,mz >= 4, my >= 2)");
+  if (nspecies < 1 || nspecies > MRG_MAX_SPECIES) return fail(MRG_ERR_ARG, "nspecies out of range");
+  if (nranks < 1 || rank < 0 || rank >= nranks) return fail(MRG_ERR_ARG, "bad rank/nranks");
+  if (!(xmax > 0 && ymax > 0 && zmax > 0)) return fail(MRG_ERR_ARG, "box sizes must be positive");
+  const long long ntot = (long long)(mx + 4) * (my + 3) * (mz + 4);
+  if (ntot * 6 >= (1LL << 31)) return fail(MRG_ERR_ARG, "grid too large for 32-bit node indexing");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(MRG_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (there is no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail(MRG_ERR_ARG, "device ordinal out of range");
+  CK(cudaSetDevice(device));
+  mrg_ctx* c = new mrg_ctx();
+  c->device = device; c->rank = rank; c->nranks = nranks; c->nspecies = nspecies;
+  GP& g = c->g;
+  g.mx = mx; g.my = my; g.mz = mz;
+  g.nx = mx + 4; g.ny = my + 3; g.nz = mz + 4; g.nxy = g.nx * g.ny; g.ntot = ntot;
+  g.xmax = xmax; g.ymax = ymax; g.zmax = zmax;
+  g.hx = xmax / mx; g.hy = ymax / my; g.hz = zmax / mz;                 // F:8454,8467,8484
+  g.hxi = 0.9999999999999 / g.hx; g.hyi = 0.9999999999999 / g.hy; g.hzi = 0.9999999999999 / g.hz;  // F:8567-8569
+  g.xmaxe = 0.9999999999999 * xmax; g.zmaxe = 0.9999999999999 * zmax;    // F:8575,8577
+  g.xlo = -(g.hx / 2); g.xhi = xmax - g.hx / 2;                          // F:1856-1862
+  g.zlo = -(g.hz / 2); g.zhi = zmax - g.hz / 2;
+  g.ymax2 = 2.0 * ymax;
+  c->ncell = (long long)mx * my * mz;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev0));
+  CK(cudaEventCreate(&c->ev1));
+  const size_t gb = (size_t)ntot * sizeof(double);
+  for (int k = 0; k < 12; k++) { CK(cudaMalloc((void**)&c->f12[k], gb)); CK(cudaMemsetAsync(c->f12[k], 0, gb, c->stream)); }
+  for (int k = 0; k < 6; k++) {
+    CK(cudaMalloc((void**)&c->A6[k], gb)); CK(cudaMalloc((void**)&c->T1[k], gb)); CK(cudaMalloc((void**)&c->T2[k], gb));
+    CK(cudaMemsetAsync(c->A6[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T1[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T2[k], 0, gb, c->stream));
+  }
+  CK(cudaMalloc((void**)&c->F6, gb * 6));
+  CK(cudaMalloc((void**)&c->wk2, 2 * sizeof(double)));
+  CK(cudaMalloc((void**)&c->slab_count, sizeof(int)));
+  CK(cudaMalloc((void**)&c->hist, (size_t)(c->ncell + 1) * sizeof(int)));
+  CK(cudaMalloc((void**)&c->cursor, (size_t)(c->ncell + 1) * sizeof(int)));
+  CK(cudaStreamSynchronize(c->stream));
+  *out = c;
+  return MRG_OK;
+}
+
+int mrg_destroy(mrg_ctx* c) {
+  if (!c) return MRG_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  for (int k = 0; k < 12; k++) cudaFree(c->f12[k]);
+  for (int k = 0; k < 6; k++) { cudaFree(c->A6[k]); cudaFree(c->T1[k]); cudaFree(c->T2[k]); cudaFree(c->alt[k]); cudaFree(c->tmp6[k]); }
+  cudaFree(c->F6); cudaFree(c->alt_id);
+  for (auto& s : c->sp) {
+    for (int k = 0; k < 6; k++) cudaFree(s.d[k]);
+    cudaFree(s.id); cudaFree(s.M4);
+    for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
+  }
+  cudaFree(c->wk_partial); cudaFree(c->wk2); cudaFree(c->sort_key); cudaFree(c->hist); cudaFree(c->cursor);
+  cudaFree(c->scan_tiles); cudaFree(c->slab_bits); cudaFree(c->slab_words); cudaFree(c->slab_list); cudaFree(c->slab_count);
+  if (c->h_pinned) cudaFreeHost(c->h_pinned);
+  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return MRG_OK;
+}
+
+int mrg_comm_unique_id(unsigned char id[MRG_UNIQUE_ID_BYTES]) {
+  if (!id) return fail(MRG_ERR_ARG, "null id");
+  int rc = nccl_load();
+  if (rc) return rc;
+  Uid u;
+  int n = g_nccl.GetUniqueId(&u);
+  if (n != 0) return fail(MRG_ERR_NCCL, "ncclGetUniqueId: " + nccl_err(n));
+  memcpy(id, u.internal, MRG_UNIQUE_ID_BYTES);
+  return MRG_OK;
+}
+
+int mrg_comm_init(mrg_ctx* c, const unsigned char id[MRG_UNIQUE_ID_BYTES]) {
+  if (!c || !id) return fail(MRG_ERR_ARG, "null argument");
+  if (c->nranks == 1) return MRG_OK;
+  int rc = nccl_load();
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  Uid u;
+  memcpy(u.internal, id, MRG_UNIQUE_ID_BYTES);
+  int n = g_nccl.CommInitRank(&c->comm, c->nranks, u, c->rank);
+  if (n != 0) return fail(MRG_ERR_NCCL, "ncclCommInitRank: " + nccl_err(n));
+  return MRG_OK;
+}
+
+int64_t mrg_num_local(mrg_ctx* c, int32_t ksp) {
+  if (check_species(c, ksp)) return -1;
+  return c->sp[ksp - 1].n;
+}
+
+int mrg_upload_particles(mrg_ctx* c, int32_t ksp, const double* x, const double* y, const double* z,
+                         const double* vx, const double* vy, const double* vz, int64_t npr, int64_t first,
+                         int64_t stride) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (npr < 0 || first < 1 || stride < 1) return fail(MRG_ERR_ARG, "need npr >= 0, first >= 1 (1-based), stride >= 1");
+  const double* h[6] = {x, y, z, vx, vy, vz};
+  for (int k = 0; k < 6; k++) if (!h[k] && npr > 0) return fail(MRG_ERR_ARG, "null particle array");
+  CK(cudaSetDevice(c->device));
+  const long long n = owned_count(npr, first, stride);
+  if (n >= (1LL << 31) - 64) return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU");
+  Species& s = c->sp[ksp - 1];
+  rc = alloc_species(c, s, n);
+  if (rc) return rc;
+  if (n == 0) return MRG_OK;
+  if (stride == 1) {
+    for (int k = 0; k < 6; k++)
+      CK(cudaMemcpyAsync(s.d[k], h[k] + (first - 1), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  } else {
+    const long long chunk = 1 << 20;
+    rc = ensure_pinned(c, (size_t)chunk * sizeof(double));
+    if (rc) return rc;
+    for (int k = 0; k < 6; k++)
+      for (long long m0 = 0; m0 < n; m0 += chunk) {
+        const long long cnt = std::min(chunk, n - m0);
+        for (long long m = 0; m < cnt; m++) c->h_pinned[m] = h[k][(first - 1) + (m0 + m) * stride];
+        CK(cudaMemcpyAsync(s.d[k] + m0, c->h_pinned, (size_t)cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+      }
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  c->h2d += 6 * n * (long long)sizeof(double);
+  return MRG_OK;
+}
+
+int mrg_download_particles(mrg_ctx* c, int32_t ksp, double* x, double* y, double* z, double* vx, double* vy,
+                           double* vz, int64_t npr, int64_t first, int64_t stride) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (npr < 0 || first < 1 || stride < 1) return fail(MRG_ERR_ARG, "need npr >= 0, first >= 1 (1-based), stride >= 1");
+  Species& s = c->sp[ksp - 1];
+  const long long n = owned_count(npr, first, stride);
+  if (n != s.n) return fail(MRG_ERR_ARG, "npr/first/stride do not match the resident particle count");
+  double* h[6] = {x, y, z, vx, vy, vz};
+  CK(cudaSetDevice(c->device));
+  if (n == 0) return MRG_OK;
+  if (s.id) { rc = ensure_alt(c, s.cap, false); if (rc) return rc; }
+  const long long chunk = 1 << 20;
+  if (stride != 1) { rc = ensure_pinned(c, (size_t)chunk * sizeof(double)); if (rc) return rc; }
+  for (int k = 0; k < 6; k++) {
+    if (!h[k]) continue;
+    const double* src = s.d[k];
+    if (s.id) {   // back to original local order
+      k_unpermute<<<grid_for(n, 256), 256, 0, c->stream>>>(n, s.id, s.d[k], c->alt[0]); CKL(c);
+      src = c->alt[0];
+    }
+    if (stride == 1) {
+      CK(cudaMemcpyAsync(h[k] + (first - 1), src, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    } else {
+      for (long long m0 = 0; m0 < n; m0 += chunk) {
+        const long long cnt = std::min(chunk, n - m0);
+        CK(cudaMemcpyAsync(c->h_pinned, src + m0, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (long long m = 0; m < cnt; m++) h[k][(first - 1) + (m0 + m) * stride] = c->h_pinned[m];
+      }
+    }
+    c->d2h += n * (long long)sizeof(double);
+  }
+  return MRG_OK;
+}
+
+int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, double vbeam, int32_t* ranfa,
+               int32_t* ranfb) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (ppc < 1 || !(vth > 0) || !ranfa || !ranfb) return fail(MRG_ERR_ARG, "bad loadpt arguments");
+  CK(cudaSetDevice(c->device));
+  const GP& g = c->g;
+  const long long npr = (long long)g.mx * g.my * g.mz * ppc;       // F:8937-8957
+  const long long first = c->rank + 1, stride = c->nranks;         // F:219, F:1162
+  const long long n = owned_count(npr, first, stride);
+  if (n >= (1LL << 31) - 64) return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU");
+  Species& s = c->sp[ksp - 1];
+  rc = alloc_species(c, s, n);
+  if (rc) return rc;
+  LoadParams L;
+  loadpt_table(vth, vdr, L.fv2, &L.v2, &L.dv2);
+  L.vdr = vdr; L.vbeam = vbeam;
+  L.half_hx = g.hx / 2; L.half_hz = g.hz / 2;
+  L.zcent = 0.50 * g.zmax; L.dzcent = 0.125 * g.zmax; L.dzsmt = 0.15 * g.zmax;      // F:9001-9003
+  L.ycent1 = 0.30 * g.ymax; L.ycent2 = 0.70 * g.ymax; L.dycent = 0.05 * g.ymax;     // F:9005-9009
+  L.rrz = 0.25 * g.zmax; L.rry = 0.075 * g.ymax;                                    // F:9026-9027
+  L.sa = (unsigned)*ranfa; L.sb = (unsigned)*ranfb;
+  L.first = first; L.stride = stride;
+  if (n > 0) { k_loadpt<<<grid_for(n, 256), 256, 0, c->stream>>>(g, L, soa(s)); CKL(c); }
+  CK(cudaStreamSynchronize(c->stream));
+  // every rank of the reference runs the whole serial loader: 3 ranfp + 4 ranf draws per particle
+  *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, 3ull * (unsigned long long)npr);
+  *ranfa = (int32_t)lcg_skip((unsigned)*ranfa, 4ull * (unsigned long long)npr);
+  return MRG_OK;
+}
+
+static int set_fields_impl(mrg_ctx* c, uint32_t mask, const double* const f12[12], cudaMemcpyKind kind) {
+  if (!c) return fail(MRG_ERR_ARG, "null context");
+  if (mask >> 12) return fail(MRG_ERR_ARG, "mask has bits above 11");
+  CK(cudaSetDevice(c->device));
+  const size_t gb = (size_t)c->g.ntot * sizeof(double);
+  for (int k = 0; k < 12; k++) {
+    if (!((mask >> k) & 1u)) continue;
+    if (!f12 || !f12[k]) return fail(MRG_ERR_ARG, "selected field pointer is null");
+    CK(cudaMemcpyAsync(c->f12[k], f12[k], gb, kind, c->stream));
+    if (kind == cudaMemcpyHostToDevice) c->h2d += (long long)gb;
+  }
+  if (kind == cudaMemcpyHostToDevice) CK(cudaStreamSynchronize(c->stream));
+  c->field_version++;
+  c->fields_set = true;
+  return MRG_OK;
+}
+int mrg_set_fields(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
+  return set_fields_impl(c, mask, f12, cudaMemcpyHostToDevice);
+}
+int mrg_set_fields_device(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
+  return set_fields_impl(c, mask, f12, cudaMemcpyDeviceToDevice);
+}
+
+int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc, const mrg_step_params* p,
+               int32_t* ranfb, double* wkix, double* wkih) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (!p) return fail(MRG_ERR_ARG, "null step parameters");
+  if (ipc < 0) return fail(MRG_ERR_ARG, "ipc must be 0 (update) or >= 1 (predict + deposit)");
+  if (wmult == 0.0) return fail(MRG_ERR_ARG, "wmult must be non-zero");
+  CK(cudaSetDevice(c->device));
+  Species& s = c->sp[ksp - 1];
+  if (!s.M4) { rc = alloc_species(c, s, 0); if (rc) return rc; }
+  rc = ensure_prep(c, p);
+  if (rc) return rc;
+  const GP& g = c->g;
+  PushParams pp;
+  pp.dt = p->dt; pp.adt = p->adt; pp.hdt = p->hdt; pp.aimpl = p->aimpl;
+  pp.hh = p->dt * qmult / wmult;                                   // F:1150-1152
+  pp.ht = 0.5 * pp.hh;
+  pp.ht2 = pp.ht * pp.ht;
+  pp.qmult = qmult;
+  pp.zcent = p->zcent; pp.ycent1 = p->ycent1; pp.ycent2 = p->ycent2;
+  pp.zw = 0.15 * g.zmax; pp.yw = 0.025 * g.ymax;                   // F:1343-1345
+  pp.drive_on = (ipc == 0 && p->drive_on) ? 1 : 0;
+  const ParticleSoA P = soa(s);
+  double wk_host[2] = {0.0, 0.0};
+
+  if (ipc >= 1) {
+    CK(cudaMemsetAsync(s.M4, 0, ((size_t)g.ntot * 4 + 2) * sizeof(double), c->stream));
+    int blocks = 1;
+    const int B = 128;
+    if (s.n > 0) {
+      const int iters = (c->opt_deposit == 2) ? c->opt_iters : 1;
+      const long long per_block = (long long)(B / 32) * 32 * iters;
+      blocks = (int)((s.n + per_block - 1) / per_block);
+      rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * blocks, sizeof(double));
+      if (rc) return rc;
+      CK(cudaEventRecord(c->ev0, c->stream));
+      const int gm = c->opt_group_min * 4;   // option counts particles; a particle is a quad of lanes
+      if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
+      else if (iters == 1) k_predict_run<1><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
+      else if (iters == 4) k_predict_run<4><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
+      else if (iters == 8) k_predict_run<8><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
+      else if (iters == 16) k_predict_run<16><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
+      else if (iters == 32) k_predict_run<32><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
+      else return fail(MRG_ERR_ARG, "option iters must be 4, 8, 16 or 32");
+      CKL(c);
+      CK(cudaEventRecord(c->ev1, c->stream));
+      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, blocks, s.M4 + (size_t)g.ntot * 4); CKL(c);
+    }
+    if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
+      if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
+      int n = g_nccl.AllReduce(s.M4, s.M4, (size_t)g.ntot * 4 + 2, kNcclFloat64, kNcclSum, c->comm, c->stream);
+      if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
+    }
+    Ptr4 o; for (int k = 0; k < 4; k++) o.p[k] = s.out4[k];
+    k_fold_unpack<<<grid_for(g.ntot, 256), 256, 0, c->stream>>>(g, s.M4, o, 1); CKL(c);   // F:2398, 2544
+    CK(cudaMemcpyAsync(wk_host, s.M4 + (size_t)g.ntot * 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    s.have_moments = true;
+  } else {
+    int slab_n = 0;
+    if (pp.drive_on) {
+      if (!ranfb) return fail(MRG_ERR_ARG, "ranfb state pointer is required when the drive kick is on");
+      const long long nwords = (s.n + 31) / 32 + 1;
+      if (c->slab_words_cap < nwords) {
+        if (c->slab_bits) CK(cudaFree(c->slab_bits));
+        if (c->slab_words) CK(cudaFree(c->slab_words));
+        c->slab_bits = nullptr; c->slab_words = nullptr;
+        CK(cudaMalloc((void**)&c->slab_bits, (size_t)nwords * sizeof(unsigned)));
+        CK(cudaMalloc((void**)&c->slab_words, (size_t)nwords * sizeof(int)));
+        c->slab_words_cap = nwords;
+      }
+      rc = ensure(c, (void**)&c->slab_list, &c->slab_list_cap, s.n + 1, sizeof(int));
+      if (rc) return rc;
+      CK(cudaMemsetAsync(c->slab_bits, 0, (size_t)nwords * sizeof(unsigned), c->stream));
+      CK(cudaMemsetAsync(c->slab_count, 0, sizeof(int), c->stream));
+    }
+    CK(cudaMemsetAsync(c->wk2, 0, 2 * sizeof(double), c->stream));
+    if (s.n > 0) {
+      const int B = 256;
+      const int blocks = grid_for(s.n, B);
+      rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * blocks, sizeof(double));
+      if (rc) return rc;
+      CK(cudaEventRecord(c->ev0, c->stream));
+      k_correct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, c->wk_partial, c->slab_bits, c->slab_list, c->slab_count); CKL(c);
+      CK(cudaEventRecord(c->ev1, c->stream));
+      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, blocks, c->wk2); CKL(c);
+    }
+    if (c->nranks > 1) {                                           // F:1312-1315
+      if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
+      int n = g_nccl.AllReduce(c->wk2, c->wk2, 2, kNcclFloat64, kNcclSum, c->comm, c->stream);
+      if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
+    }
+    CK(cudaMemcpyAsync(wk_host, c->wk2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (pp.drive_on && s.n > 0) {
+      CK(cudaMemcpyAsync(&slab_n, c->slab_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      if (slab_n > 0) {
+        const long long nwords = (s.n + 31) / 32 + 1;
+        k_popc<<<grid_for(nwords, 256), 256, 0, c->stream>>>(c->slab_bits, nwords, c->slab_words); CKL(c);
+        rc = scan_excl(c, c->slab_words, c->slab_words, nwords, nullptr);
+        if (rc) return rc;
+        k_kick<<<grid_for(slab_n, 256), 256, 0, c->stream>>>(g, P, c->F6, c->slab_bits, c->slab_words, c->slab_list,
+                                                              c->slab_count, (unsigned)*ranfb, p->Ez00, p->ycent1,
+                                                              p->ycent2, 0.05 * g.ymax); CKL(c);
+        *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)slab_n);
+      }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  if (s.n > 0) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_kernel_ms = ms;
+  } else {
+    c->last_kernel_ms = 0.0;
+  }
+  c->d2h += 2 * (long long)sizeof(double);
+  if (wkix) *wkix = wk_host[0];
+  if (wkih) *wkih = wk_host[1];
+  return MRG_OK;
+}
+
+int mrg_get_moments(mrg_ctx* c, int32_t ksp, double* qjx, double* qjy, double* qjz, double* q, int32_t folded) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  Species& s = c->sp[ksp - 1];
+  if (!s.have_moments) return fail(MRG_ERR_STATE, "no ipc>=1 call has produced moments for this species yet");
+  CK(cudaSetDevice(c->device));
+  double* h[4] = {qjx, qjy, qjz, q};
+  const size_t gb = (size_t)c->g.ntot * sizeof(double);
+  double* const* src = s.out4;
+  if (!folded) {   // unpack the rank-summed raw arrays into T1[0..3] (prep scratch is not live here)
+    Ptr4 o; for (int k = 0; k < 4; k++) o.p[k] = c->T2[k];
+    k_fold_unpack<<<grid_for(c->g.ntot, 256), 256, 0, c->stream>>>(c->g, s.M4, o, 0); CKL(c);
+    src = c->T2;
+  }
+  for (int k = 0; k < 4; k++) {
+    if (!h[k]) continue;
+    CK(cudaMemcpyAsync(h[k], src[k], gb, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h += (long long)gb;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return MRG_OK;
+}
+
+int mrg_get_moments_device(mrg_ctx* c, int32_t ksp, const double* dev4[4]) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  Species& s = c->sp[ksp - 1];
+  if (!s.have_moments) return fail(MRG_ERR_STATE, "no ipc>=1 call has produced moments for this species yet");
+  for (int k = 0; k < 4; k++) dev4[k] = s.out4[k];
+  return MRG_OK;
+}
+
+int mrg_get_prepared_fields(mrg_ctx* c, const mrg_step_params* p, double* const a6[6]) {
+  if (!c || !p || !a6) return fail(MRG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  int rc = ensure_prep(c, p);
+  if (rc) return rc;
+  const size_t gb = (size_t)c->g.ntot * sizeof(double);
+  Ptr6 o;
+  for (int k = 0; k < 6; k++) {
+    if (!c->tmp6[k]) CK(cudaMalloc((void**)&c->tmp6[k], gb));
+    o.p[k] = c->tmp6[k];
+  }
+  k_unpack6<<<grid_for(c->g.ntot, 256), 256, 0, c->stream>>>(c->g, c->F6, o); CKL(c);
+  for (int k = 0; k < 6; k++) {
+    if (!a6[k]) continue;
+    CK(cudaMemcpyAsync(a6[k], c->tmp6[k], gb, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h += (long long)gb;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return MRG_OK;
+}
+
+int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  CK(cudaSetDevice(c->device));
+  Species& s = c->sp[ksp - 1];
+  if (s.n == 0) return MRG_OK;
+  rc = ensure_alt(c, s.cap, true);
+  if (rc) return rc;
+  rc = ensure(c, (void**)&c->sort_key, &c->sort_key_cap, s.n, sizeof(int));
+  if (rc) return rc;
+  const int B = 256;
+  CK(cudaMemsetAsync(c->hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+  k_sort_keys<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, c->sort_key, c->hist); CKL(c);
+  rc = scan_excl(c, c->hist, c->cursor, c->ncell + 1, nullptr);
+  if (rc) return rc;
+  SortArrays A;
+  for (int k = 0; k < 6; k++) { A.src[k] = s.d[k]; A.dst[k] = c->alt[k]; }
+  A.id_src = s.id; A.id_dst = c->alt_id;
+  k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, c->sort_key, c->cursor, A); CKL(c);
+  CK(cudaStreamSynchronize(c->stream));
+  // the spare buffer becomes the species' storage and vice versa
+  for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
+  int* old_id = s.id;
+  s.id = c->alt_id;
+  const long long old_cap = s.cap;
+  s.cap = c->alt_cap;
+  c->alt_cap = old_cap;
+  if (old_id) {
+    c->alt_id = old_id;
+  } else {
+    c->alt_id = nullptr;
+    CK(cudaMalloc((void**)&c->alt_id, (size_t)c->alt_cap * sizeof(int)));
+  }
+  return MRG_OK;
+}
+
+int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
+  if (!c || !name) return fail(MRG_ERR_ARG, "null argument");
+  const std::string n(name);
+  if (n == "deposit") {
+    if (value < 0 || value > 2) return fail(MRG_ERR_ARG, "deposit must be 0, 1 or 2");
+    c->opt_deposit = (int)value;
+  } else if (n == "iters") {
+    if (value != 4 && value != 8 && value != 16 && value != 32) return fail(MRG_ERR_ARG, "iters must be 4, 8, 16 or 32");
+    c->opt_iters = (int)value;
+  } else if (n == "group_min") {
+    if (value < 1 || value > 9) return fail(MRG_ERR_ARG, "group_min must be in 1..9 (particles per sub-iteration group)");
+    c->opt_group_min = (int)value;
+  } else {
+    return fail(MRG_ERR_ARG, "unknown option: " + n);
+  }
+  return MRG_OK;
+}
+
+int mrg_get_counters(mrg_ctx* c, int64_t out[3], int32_t reset) {
+  if (!c || !out) return fail(MRG_ERR_ARG, "null argument");
+  out[0] = c->launches; out[1] = c->h2d; out[2] = c->d2h;
+  if (reset) { c->launches = 0; c->h2d = 0; c->d2h = 0; }
+  return MRG_OK;
+}
+
+int mrg_last_kernel_ms(mrg_ctx* c, double* ms) {
+  if (!c || !ms) return fail(MRG_ERR_ARG, "null argument");
+  *ms = c->last_kernel_ms;
+  return MRG_OK;
+}
+
+int mrg_synchronize(mrg_ctx* c) {
+  if (!c) return fail(MRG_ERR_ARG, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return MRG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,184 @@
+// mrg_device.cuh -- device-side building blocks of the /fulmov/ path.
+//
+// F:n = /root/reference/@mrg37-080A.f03 line n (what each piece reproduces).
+// Lines that decide an integer cell index or a branch use the _rn/_rd
+// intrinsics so that no FMA contraction can change the decision; everything
+// else is free to contract.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mrg {
+
+// Grid constants (COMMON /parm2/,/ptable/ subset), passed by value to kernels.
+struct GP {
+  int mx, my, mz;
+  int nx, ny, nz;          // extended sizes mx+4, my+3, mz+4        (F:1061)
+  int nxy;                 // nx*ny
+  long long ntot;          // mxyzA                                  (P:33)
+  double xmax, ymax, zmax;
+  double hx, hy, hz;       // F:8454,8467,8484
+  double hxi, hyi, hzi;    // F:8567-8569
+  double xmaxe, zmaxe;     // F:8575,8577
+  double xlo, xhi;         // -hx/2, xmax-hx/2   (F:1856-1862)
+  double zlo, zhi;
+  double ymax2;            // 2*ymax             (F:1867)
+};
+
+// node index of (i,j,k) in the (-2:mx+1,-1:my+1,-2:mz+1) layout
+__host__ __device__ __forceinline__ int node_of(const GP& g, int i, int j, int k) {
+  return (i + 2) + g.nx * ((j + 1) + g.ny * (k + 2));
+}
+
+#define MRG_TWO52 4503599627370496.0
+
+// floor(s) for 0 <= s < 2^31 without F2I/I2F: adding 2^52 in round-down mode
+// leaves floor(s) in the low mantissa bits.  Returns the integer and its
+// exact double value.  (The reference truncates with int(), F:1175-1177; its
+// arguments are >= 0 after partbc/partbcEST.)
+__device__ __forceinline__ int floor_pos(double s, double& as_double) {
+  double u = __dadd_rd(s, MRG_TWO52);
+  as_double = __dsub_rn(u, MRG_TWO52);
+  return __double2loint(u);
+}
+
+// partbc (F:1856-1879) / partbcEST (F:1928-1949): applied once, no loop.
+// Returns true when the y wall reflected the particle (partbc then flips vy).
+__device__ __forceinline__ bool wrap_pos(const GP& g, double& x, double& y, double& z) {
+  if (x >= g.xhi) x = __dsub_rn(x, g.xmaxe);
+  else if (x <= g.xlo) x = __dadd_rn(x, g.xmaxe);
+  bool flip = false;
+  if (y >= g.ymax) { y = __dsub_rn(g.ymax2, y); flip = true; }
+  else if (y <= 0.0) { y = -y; flip = true; }
+  if (z >= g.zhi) z = __dsub_rn(z, g.zmaxe);
+  else if (z <= g.zlo) z = __dadd_rn(z, g.zmaxe);
+  return flip;
+}
+
+// Cell index + weights.  GATHER=true: F:1175-1215, GATHER=false: F:2274-2308
+// (the scatter does not override fyl/fyr in the jp>=my branch).
+//   n0 = node of (il,jl,kl); the 18 nodes are n0 + ix + jy*nx + kz*nxy.
+//   fx = (fxl,fxc,fxr), fz = (fzl,fzc,fzr), fy[0]=fyl (row jl), fy[1]=fyr.
+struct Stencil {
+  int n0;
+  int ip, jp, kp;
+  double fx[3], fy[2], fz[3];
+};
+
+template <bool GATHER>
+__device__ __forceinline__ void make_stencil(const GP& g, double rx, double ry, double rz, Stencil& s) {
+  const double tx = __dmul_rn(g.hxi, rx);
+  const double ty = __dmul_rn(g.hyi, ry);
+  const double tz = __dmul_rn(g.hzi, rz);
+  double ipd, jpd, kpd;
+  int ip = floor_pos(__dadd_rn(tx, 0.500000001), ipd);
+  int jp = floor_pos(__dadd_rn(ty, 0.000000001), jpd);
+  int kp = floor_pos(__dadd_rn(tz, 0.500000001), kpd);
+  // Memory safety only: valid (wrapped) positions already satisfy these.
+  ip = min(max(ip, 0), g.mx);
+  jp = min(max(jp, 0), g.my);
+  kp = min(max(kp, 0), g.mz);
+  s.ip = ip; s.jp = jp; s.kp = kp;
+  s.n0 = (ip + 1) + g.nx * ((jp + 1) + g.ny * (kp + 1));
+  double fyl = __dsub_rn(ty, jpd);
+  double fyr = __dsub_rn(1.0, fyl);
+  if (GATHER && jp >= g.my) { fyr = 0.0; fyl = 1.0; }   // F:1191-1195
+  s.fy[0] = fyl; s.fy[1] = fyr;
+  const double xx = __dsub_rn(tx, ipd);
+  const double xm = 0.5 - xx, xp = 0.5 + xx;
+  s.fx[0] = (0.5 * xm) * xm;
+  s.fx[1] = fma(-xx, xx, 0.75);
+  s.fx[2] = (0.5 * xp) * xp;
+  const double zz = __dsub_rn(tz, kpd);
+  const double zm = 0.5 - zz, zp = 0.5 + zz;
+  s.fz[0] = (0.5 * zm) * zm;
+  s.fz[1] = fma(-zz, zz, 0.75);
+  s.fz[2] = (0.5 * zp) * zp;
+}
+
+// Nearest-node indices only (drive kick, F:1347-1349; sort key).
+__device__ __forceinline__ void cell_of(const GP& g, double x, double y, double z, int& ip, int& jp, int& kp) {
+  double d;
+  ip = floor_pos(__dadd_rn(__dmul_rn(g.hxi, x), 0.500000001), d);
+  jp = floor_pos(__dadd_rn(__dmul_rn(g.hyi, y), 0.000000001), d);
+  kp = floor_pos(__dadd_rn(__dmul_rn(g.hzi, z), 0.500000001), d);
+  ip = min(max(ip, 0), g.mx);
+  jp = min(max(jp, 0), g.my);
+  kp = min(max(kp, 0), g.mz);
+}
+
+// Gather of the six prepared fields (F:1217-1270) from the packed array
+// F6[node][6] = (exa,eya,eza,bxa,bya,bza): 9 x 128-bit loads per stencil row.
+// The 18 weights are formed as fx*(fy*fz); the sum order differs from the
+// Fortran nesting by rounding only.
+__device__ __forceinline__ void gather6(const double* __restrict__ F6, const GP& g, const Stencil& s, double f[6]) {
+#pragma unroll
+  for (int c = 0; c < 6; c++) f[c] = 0.0;
+  const double2* base = reinterpret_cast<const double2*>(F6) + (size_t)s.n0 * 3;
+  const int sy = g.nx * 3;
+  const size_t sz = (size_t)g.nxy * 3;
+#pragma unroll
+  for (int kz = 0; kz < 3; kz++) {
+#pragma unroll
+    for (int jy = 0; jy < 2; jy++) {
+      const double2* r = base + jy * sy + kz * sz;
+      const double wyz = s.fy[jy] * s.fz[kz];
+      double2 v[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) v[q] = __ldg(r + q);
+#pragma unroll
+      for (int ix = 0; ix < 3; ix++) {
+        const double w = s.fx[ix] * wyz;
+        f[0] = fma(w, v[3 * ix + 0].x, f[0]);
+        f[1] = fma(w, v[3 * ix + 0].y, f[1]);
+        f[2] = fma(w, v[3 * ix + 1].x, f[2]);
+        f[3] = fma(w, v[3 * ix + 1].y, f[3]);
+        f[4] = fma(w, v[3 * ix + 2].x, f[4]);
+        f[5] = fma(w, v[3 * ix + 2].y, f[5]);
+      }
+    }
+  }
+}
+
+// Closed-form implicit rotation, F:1272-1283.  One reciprocal instead of the
+// three divisions of the source.
+struct Kick {
+  double dvx, dvy, dvz, wx, wh;
+};
+__device__ __forceinline__ Kick rotate(const double f[6], double vx, double vy, double vz, double ht, double ht2) {
+  const double exi = f[0], eyi = f[1], ezi = f[2], bxi = f[3], byi = f[4], bzi = f[5];
+  const double bsqi = fma(bxi, bxi, fma(byi, byi, bzi * bzi));
+  const double acx = exi + (vy * bzi - vz * byi);
+  const double acy = eyi + (vz * bxi - vx * bzi);
+  const double acz = ezi + (vx * byi - vy * bxi);
+  const double ach = fma(exi, bxi, fma(eyi, byi, ezi * bzi));
+  const double rden = 1.0 / fma(ht2, bsqi, 1.0);
+  const double t = ht2 * ach;
+  Kick k;
+  k.dvx = (acx + fma(t, bxi, ht * (acy * bzi - acz * byi))) * rden;
+  k.dvy = (acy + fma(t, byi, ht * (acz * bxi - acx * bzi))) * rden;
+  k.dvz = (acz + fma(t, bzi, ht * (acx * byi - acy * bxi))) * rden;
+  k.wx = 0.5 * fma(acx, acx, fma(acy, acy, acz * acz));
+  k.wh = 0.5 * (ach * ach);
+  return k;
+}
+
+// 31-bit multiplicative LCG of ranf/ranfp (F:9263-9305): state*lambda^n.
+__host__ __device__ __forceinline__ uint32_t lcg_skip(uint32_t state, unsigned long long n) {
+  uint32_t base = 48828125u, acc = 1u;
+  while (n) {
+    if (n & 1ull) acc *= base;
+    base *= base;
+    n >>= 1;
+  }
+  return (acc * state) & 0x7fffffffu;
+}
+__host__ __device__ __forceinline__ uint32_t lcg_next(uint32_t s) { return (48828125u * s) & 0x7fffffffu; }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace mrg

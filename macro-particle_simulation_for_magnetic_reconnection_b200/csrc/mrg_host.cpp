@@ -1,0 +1,140 @@
+// mrg_host.cpp -- see mrg_host.h.  Host mirror of subroutine fulmov (F:1044)
+// that keeps particles resident on the GPU and feeds COMMON /srimp7/,
+// /wkinel/ and edec exactly where the reference writes them.
+#include "mrg_host.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/mrg_fulmov.h"
+
+namespace {
+
+struct HostState {
+  mrg_common_view v{};
+  bool bound = false;
+  int device = 0;
+  mrg_ctx* ctx = nullptr;
+  bool resident[MRG_MAX_SPECIES] = {false, false, false, false};
+  int corrector_calls[MRG_MAX_SPECIES] = {0, 0, 0, 0};
+  bool fields_dirty = true, auto_fields = true;
+  int sort_interval = 1;
+  bool exit_on_error = true;
+  int status = 0;
+  bool have_id = false;
+  unsigned char id[MRG_UNIQUE_ID_BYTES];
+} H;
+
+void die(const char* where, int rc) {
+  H.status = rc;
+  std::fprintf(stderr, "fulmov(gpu): %s failed (%d): %s\n", where, rc, mrg_last_error());
+  if (H.exit_on_error) std::exit(1);   // the reference has no status argument: stop
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrg_host_bind(const mrg_common_view* view, int32_t device) {
+  if (!view) return MRG_ERR_ARG;
+  mrg_host_unbind();
+  H.v = *view;
+  H.device = device;
+  H.bound = true;
+  H.status = 0;
+  return MRG_OK;
+}
+
+void mrg_host_unbind(void) {
+  if (H.ctx) mrg_destroy(H.ctx);
+  H = HostState();
+}
+
+void mrg_host_fields_changed(void) { H.fields_dirty = true; }
+void mrg_host_set_auto_fields(int32_t on) { H.auto_fields = on != 0; }
+void mrg_host_set_sort_interval(int32_t n) { H.sort_interval = n < 0 ? 0 : n; }
+void mrg_host_set_exit_on_error(int32_t on) { H.exit_on_error = on != 0; }
+int mrg_host_status(void) { return H.status; }
+void* mrg_host_context(void) { return H.ctx; }
+void mrg_host_particles_changed(int32_t ksp) {
+  if (ksp >= 1 && ksp <= MRG_MAX_SPECIES) H.resident[ksp - 1] = false;
+}
+
+int mrg_host_unique_id(unsigned char id[128]) { return mrg_comm_unique_id(id); }
+int mrg_host_set_unique_id(const unsigned char id[128]) {
+  std::memcpy(H.id, id, MRG_UNIQUE_ID_BYTES);
+  H.have_id = true;
+  return MRG_OK;
+}
+
+void fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz, double* qmult, double* wmult,
+            int32_t* npr, int32_t* ipc, int32_t* ksp, int32_t* ipar, int32_t* size) {
+  H.status = 0;
+  if (!H.bound) { std::fprintf(stderr, "fulmov(gpu): mrg_host_bind was not called\n"); H.status = MRG_ERR_STATE; if (H.exit_on_error) std::exit(1); return; }
+  const mrg_common_view& v = H.v;
+  const int k = *ksp;
+  if (k < 1 || k > 2) {   // the reference handles exactly two species (F:1321-1327, 1377-1386)
+    std::fprintf(stderr, "fulmov(gpu): ksp must be 1 or 2\n");
+    H.status = MRG_ERR_ARG;
+    if (H.exit_on_error) std::exit(1);
+    return;
+  }
+  int rc;
+  if (!H.ctx) {
+    rc = mrg_create(&H.ctx, v.mx, v.my, v.mz, *v.xmax, *v.ymax, *v.zmax, 2, *ipar - 1, *size, H.device);
+    if (rc) return die("mrg_create", rc);
+    if (*size > 1) {
+      if (!H.have_id) { std::fprintf(stderr, "fulmov(gpu): size > 1 needs mrg_host_set_unique_id\n"); H.status = MRG_ERR_STATE; if (H.exit_on_error) std::exit(1); return; }
+      rc = mrg_comm_init(H.ctx, H.id);
+      if (rc) return die("mrg_comm_init", rc);
+    }
+  }
+  if (!H.resident[k - 1]) {   // first call (or after restrt): take the owned subset, l = ipar, ipar+size, ...
+    rc = mrg_upload_particles(H.ctx, k, x, y, z, vx, vy, vz, *npr, *ipar, *size);
+    if (rc) return die("mrg_upload_particles", rc);
+    H.resident[k - 1] = true;
+  }
+  if (H.fields_dirty || (H.auto_fields && k == 1)) {
+    const double* f12[12] = {v.ex, v.ey, v.ez, v.bx, v.by, v.bz, v.ex0, v.ey0, v.ez0, v.bx0, v.by0, v.bz0};
+    rc = mrg_set_fields(H.ctx, 0xFFFu, f12);
+    if (rc) return die("mrg_set_fields", rc);
+    H.fields_dirty = false;
+  }
+  mrg_step_params p;
+  p.dt = *v.dt; p.adt = *v.adt; p.hdt = *v.hdt; p.aimpl = *v.aimpl;
+  p.bxc = *v.bxc; p.byc = *v.byc; p.bzc = *v.bzc;
+  p.ifilx = *v.ifilx; p.ifily = *v.ifily; p.ifilz = *v.ifilz;
+  p.drive_on = 1;
+  p.Ez00 = *v.Ez00; p.zcent = *v.zcent; p.ycent1 = *v.ycent1; p.ycent2 = *v.ycent2;
+  double wkix = 0.0, wkih = 0.0;
+  rc = mrg_fulmov(H.ctx, k, *qmult, *wmult, *ipc, &p, v.ranfb, &wkix, &wkih);
+  if (rc) return die("mrg_fulmov", rc);
+  *v.wkix = wkix;                                         // F:1316-1317
+  *v.wkih = wkih;
+  if ((*v.it % *v.nha) == 0 && *v.io_pe == 1) {           // F:1320-1328
+    const long row = *v.ldec - 1;
+    const int col = (k == 1) ? 5 : 7;
+    v.edec[row + 3000L * (col - 1)] = wkix;
+    v.edec[row + 3000L * col] = wkih;
+  }
+  if (*ipc >= 1) {                                        // F:1377-1386
+    rc = (k == 1) ? mrg_get_moments(H.ctx, 1, v.qix, v.qiy, v.qiz, v.qi, 1)
+                  : mrg_get_moments(H.ctx, 2, v.qex, v.qey, v.qez, v.qe, 1);
+    if (rc) return die("mrg_get_moments", rc);
+  } else {
+    H.corrector_calls[k - 1]++;
+    if (H.sort_interval > 0 && H.corrector_calls[k - 1] % H.sort_interval == 0) {
+      rc = mrg_sort(H.ctx, k, *v.adt);
+      if (rc) return die("mrg_sort", rc);
+    }
+  }
+}
+
+int mrg_host_pull_particles(int32_t ksp, double* x, double* y, double* z, double* vx, double* vy, double* vz,
+                            int32_t npr, int32_t ipar, int32_t size) {
+  if (!H.ctx || ksp < 1 || ksp > MRG_MAX_SPECIES || !H.resident[ksp - 1]) return MRG_ERR_STATE;
+  return mrg_download_particles(H.ctx, ksp, x, y, z, vx, vy, vz, npr, ipar, size);
+}
+
+}  // extern "C"

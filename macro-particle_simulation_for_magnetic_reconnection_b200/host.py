@@ -1,0 +1,218 @@
+"""Host-side Python mirror of the reference's fulmov interface.
+
+`Fulmov` keeps the call shape of `subroutine fulmov(x,y,z,vx,vy,vz,qmult,
+wmult,npr,ipc,ksp,ipar,size)` (F:1044 of @mrg37-080A.f03) and of the COMMON
+values it reads (a `Common` object stands for /fields/, /srimp7/, /parm1/,
+/parm2/, /wkinel/, /profl/, /ranfb/), and drives the CUDA library through the
+C ABI.  Particles stay resident in HBM between calls.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import StepParams, as_dp, check
+
+FIELD_NAMES = ("ex", "ey", "ez", "bx", "by", "bz", "ex0", "ey0", "ez0", "bx0", "by0", "bz0")
+
+
+def mxyzA(mx, my, mz):
+    """param_080A.h:33"""
+    return (mx + 4) * (my + 3) * (mz + 4)
+
+
+class Common:
+    """The COMMON-block values fulmov reads/writes (F:1066-1110), as numpy."""
+
+    def __init__(self, mx, my, mz, xmax, ymax, zmax, dt=1.2, aimpl=0.6, wce_by_wpe=0.2,
+                 Ez00=0.25e-2, nha=5):
+        self.mx, self.my, self.mz = mx, my, mz
+        self.xmax, self.ymax, self.zmax = float(xmax), float(ymax), float(zmax)
+        n = mxyzA(mx, my, mz)
+        for name in FIELD_NAMES:                                   # common/fields/
+            setattr(self, name, np.zeros(n))
+        for name in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe"):   # common/srimp7/
+            setattr(self, name, np.zeros(n))
+        self.it, self.ldec, self.nha = 0, 1, nha                   # common/parm1/
+        self.ifilx = self.ifily = self.ifilz = 1                   # F:368-370
+        self.dt, self.aimpl = float(dt), float(aimpl)              # common/parm2/
+        self.adt, self.hdt = aimpl * dt, 0.5 * dt                  # F:8579-8580
+        self.bxc, self.byc, self.bzc = float(wce_by_wpe), 0.0, 0.0  # F:8601-8603
+        self.edec = np.zeros((12, 3000))                           # edec(3000,12) column-major
+        self.wkix = self.wkih = 0.0                                # common/wkinel/
+        self.Ez00 = float(Ez00)                                    # common/profl/, F:9001-9006
+        self.zcent, self.ycent1, self.ycent2 = 0.5 * zmax, 0.30 * ymax, 0.70 * ymax
+        self.ranfb = 7331                                          # common/ranfb/, F:553
+        self.io_pe = 1
+
+    def step_params(self, drive_on=True):
+        return StepParams(self.dt, self.adt, self.hdt, self.aimpl, self.bxc, self.byc, self.bzc,
+                          self.ifilx, self.ifily, self.ifilz, 1 if drive_on else 0,
+                          self.Ez00, self.zcent, self.ycent1, self.ycent2)
+
+    def fields(self):
+        return [getattr(self, n) for n in FIELD_NAMES]
+
+
+class MrgContext:
+    """Thin object wrapper over mrg_ctx (one per rank / GPU)."""
+
+    def __init__(self, mx, my, mz, xmax, ymax, zmax, nspecies=2, rank=0, nranks=1, device=0):
+        self.lib = capi.load()
+        self.h = C.c_void_p()
+        check(self.lib.mrg_create(C.byref(self.h), mx, my, mz, xmax, ymax, zmax, nspecies, rank, nranks, device))
+        self.mx, self.my, self.mz = mx, my, mz
+        self.n_grid = mxyzA(mx, my, mz)
+        self.rank, self.nranks = rank, nranks
+
+    def close(self):
+        if self.h:
+            self.lib.mrg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- communicator ------------------------------------------------------
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(capi.UNIQUE_ID_BYTES)
+        check(capi.load().mrg_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, uid):
+        check(self.lib.mrg_comm_init(self.h, uid))
+
+    # -- particles ---------------------------------------------------------
+    def upload(self, ksp, x, y, z, vx, vy, vz, first=1, stride=1):
+        check(self.lib.mrg_upload_particles(self.h, ksp, *[as_dp(a) for a in (x, y, z, vx, vy, vz)],
+                                            len(x), first, stride))
+
+    def download(self, ksp, npr, first=1, stride=1, out=None):
+        arrs = out if out is not None else [np.zeros(npr) for _ in range(6)]
+        check(self.lib.mrg_download_particles(self.h, ksp, *[as_dp(a) for a in arrs], npr, first, stride))
+        return arrs
+
+    def num_local(self, ksp):
+        return self.lib.mrg_num_local(self.h, ksp)
+
+    def loadpt(self, ksp, ppc, vth, vdr, vbeam, ranfa=3021, ranfb=7331):
+        a, b = C.c_int32(ranfa), C.c_int32(ranfb)
+        check(self.lib.mrg_loadpt(self.h, ksp, ppc, vth, vdr, vbeam, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # -- fields ------------------------------------------------------------
+    def set_fields(self, f12, mask=0xFFF):
+        arr = (capi.dp * 12)(*[as_dp(a) for a in f12])
+        check(self.lib.mrg_set_fields(self.h, mask, arr))
+
+    def set_fields_device(self, ptrs, mask=0xFFF):
+        arr = (C.c_void_p * 12)(*ptrs)
+        check(self.lib.mrg_set_fields_device(self.h, mask, arr))
+
+    def prepared_fields(self, params):
+        out = [np.zeros(self.n_grid) for _ in range(6)]
+        arr = (capi.dp * 6)(*[as_dp(a) for a in out])
+        check(self.lib.mrg_get_prepared_fields(self.h, C.byref(params), arr))
+        return out
+
+    # -- the hot path --------------------------------------------------------
+    def fulmov(self, ksp, qmult, wmult, ipc, params, ranfb=7331):
+        st = C.c_int32(ranfb)
+        wkix, wkih = C.c_double(), C.c_double()
+        check(self.lib.mrg_fulmov(self.h, ksp, qmult, wmult, ipc, C.byref(params), C.byref(st),
+                                  C.byref(wkix), C.byref(wkih)))
+        return wkix.value, wkih.value, st.value
+
+    def moments(self, ksp, folded=True, out=None):
+        arrs = out if out is not None else [np.zeros(self.n_grid) for _ in range(4)]
+        check(self.lib.mrg_get_moments(self.h, ksp, *[as_dp(a) for a in arrs], 1 if folded else 0))
+        return arrs
+
+    def moments_device(self, ksp):
+        arr = (C.c_void_p * 4)()
+        check(self.lib.mrg_get_moments_device(self.h, ksp, arr))
+        return list(arr)
+
+    def sort(self, ksp, lookahead=0.0):
+        check(self.lib.mrg_sort(self.h, ksp, lookahead))
+
+    def set_option(self, name, value):
+        check(self.lib.mrg_set_option(self.h, name.encode(), int(value)))
+
+    def counters(self, reset=False):
+        out = (C.c_int64 * 3)()
+        check(self.lib.mrg_get_counters(self.h, out, 1 if reset else 0))
+        return {"launches": out[0], "h2d_bytes": out[1], "d2h_bytes": out[2]}
+
+    def last_kernel_ms(self):
+        ms = C.c_double()
+        check(self.lib.mrg_last_kernel_ms(self.h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(self.lib.mrg_synchronize(self.h))
+
+
+class Fulmov:
+    """Drop-in for the reference's `fulmov` on one rank.
+
+    fm = Fulmov(common, ipar, size); then, as in trans (F:761-787):
+        fm(xi,yi,zi,vxi,vyi,vzi, qspec1, wspec1, npr, ipc, 1)
+        fm(xe,ye,ze,vxe,vye,vze, qspec2, wspec2, npr, ipc, 2)
+    Side effects mirror the subroutine: qix..qi / qex..qe in `common` after
+    ipc>=1 (F:1377-1386), wkix/wkih (F:1316-1317), edec(ldec,5..8) when
+    mod(it,nha)==0 on io_pe==1 (F:1320-1328), ranfb advanced by the kick.
+    The host particle arrays are only read on the first call per species (or
+    after particles_changed); use pull() before host code looks at them.
+    """
+
+    def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1):
+        self.c = common
+        self.ipar, self.size = ipar, size
+        self.ctx = MrgContext(common.mx, common.my, common.mz, common.xmax, common.ymax, common.zmax,
+                              nspecies=2, rank=ipar - 1, nranks=size, device=device)
+        if size > 1:
+            if uid is None:
+                raise ValueError("size > 1 needs the NCCL unique id broadcast from rank 0")
+            self.ctx.comm_init(uid)
+        self.resident = {}
+        self.fields_dirty = True
+        self.sort_interval = sort_interval
+        self.ncorr = {1: 0, 2: 0}
+
+    def fields_changed(self):
+        self.fields_dirty = True
+
+    def particles_changed(self, ksp):
+        self.resident.pop(ksp, None)
+
+    def __call__(self, x, y, z, vx, vy, vz, qmult, wmult, npr, ipc, ksp):
+        c = self.c
+        if ksp not in (1, 2):
+            raise ValueError("ksp must be 1 or 2 (F:1321-1327)")
+        if not self.resident.get(ksp):
+            self.ctx.upload(ksp, x[:npr], y[:npr], z[:npr], vx[:npr], vy[:npr], vz[:npr], self.ipar, self.size)
+            self.resident[ksp] = npr
+        if self.fields_dirty or ksp == 1:
+            self.ctx.set_fields(c.fields())
+            self.fields_dirty = False
+        wkix, wkih, c.ranfb = self.ctx.fulmov(ksp, qmult, wmult, ipc, c.step_params(), c.ranfb)
+        c.wkix, c.wkih = wkix, wkih
+        if c.it % c.nha == 0 and c.io_pe == 1:
+            col = 5 if ksp == 1 else 7
+            c.edec[col - 1, c.ldec - 1] = wkix
+            c.edec[col, c.ldec - 1] = wkih
+        if ipc >= 1:
+            out = [c.qix, c.qiy, c.qiz, c.qi] if ksp == 1 else [c.qex, c.qey, c.qez, c.qe]
+            self.ctx.moments(ksp, folded=True, out=out)
+        else:
+            self.ncorr[ksp] += 1
+            if self.sort_interval and self.ncorr[ksp] % self.sort_interval == 0:
+                self.ctx.sort(ksp, c.adt)
+
+    def pull(self, ksp, x, y, z, vx, vy, vz, npr):
+        self.ctx.download(ksp, npr, self.ipar, self.size, out=[x, y, z, vx, vy, vz])
