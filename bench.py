@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Benchmark of the /fulmov/ particle hot path (BASELINE.json metric:
+particle-pushes/sec incl. J/chi deposition, % of the HBM roofline).
+
+One "step" = one time step of the particle path for BOTH species of the
+synthetic two-flux-bundle load, in the call order of trans (F:761-787):
+  predictor  fulmov(ions, ipc=1), fulmov(electrons, ipc=1)   gather+push+deposit, NCCL sum, fold
+  [fields change: emfild]                                     field prep runs again
+  corrector  fulmov(ions, ipc=0), fulmov(electrons, ipc=0)   gather+push+partbc+drive kick
+  cell sort of both species every --sort-every steps (maintenance, inside the timed region)
+particle-pushes/s = particles of all species x steps / time  (one push = predictor + corrector pass).
+
+  python bench.py [--gpus N --steps K --warmup W]            CUDA path (this repository)
+  python bench.py --impl reference ...                        the reference's CPU path (C restatement,
+                                                              all host threads, bounded sample)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+HX, HY, HZ = 300.0 / 40, 600.0 / 72, 300.0 / 40        # rec_3d80A:4 with param_080A.h:14
+QSPEC, WSPEC = {1: 1.0, 2: -1.0}, {1: 100.0, 2: 1.0}   # rec_3d80A:5-6
+VBEAM = {1: 0.35e-2, 2: -0.35e-2}
+VETH, DT, AIMPL, WCE, EZ00 = 0.2, 1.2, 0.6, 0.2, 0.25e-2
+# weak scaling: 268 M particles (both species) per GPU, 64 ppc; N=1 is BASELINE configs[1], N=8 is configs[2]
+GRIDS = {1: (128, 128, 128), 2: (256, 128, 128), 4: (256, 256, 128), 8: (256, 256, 256)}
+METRIC = "particle-pushes/sec incl. J/chi deposition"
+UNIT = "particle-pushes/s"
+
+
+def vth(ksp):
+    return VETH / np.sqrt(1.0 * WSPEC[1]) if ksp == 1 else VETH       # F:8589-8594
+
+
+def synth_fields(xp, mx, my, mz, seed, **kw):
+    """12 smooth flux-bundle-like field arrays (ex..bz, ex0..bz0) in the reference layout
+    (E ~ 1e-2, B ~ 3e-2 on top of bxc = 0.2, the magnitudes of EMfields.pdf).  xp = numpy or torch."""
+    rs = np.random.RandomState(seed)
+    i = xp.arange(-2, mx + 2, **kw).reshape(1, 1, -1)
+    j = xp.arange(-1, my + 2, **kw).reshape(1, -1, 1)
+    k = xp.arange(-2, mz + 2, **kw).reshape(-1, 1, 1)
+    X, Y, Z = 2 * np.pi * i / mx, np.pi * j / my, 2 * np.pi * k / mz
+    out = []
+    for c in range(12):
+        amp = 1e-2 if (c % 6) < 3 else 3e-2
+        a = rs.normal(size=4)
+        ph = rs.uniform(0, 2 * np.pi, size=3)
+        f = amp * (a[0] * xp.sin(X + ph[0]) * xp.cos(Y) + a[1] * xp.cos(2 * Z + ph[1]) * xp.sin(Y)
+                   + a[2] * xp.sin(X + Z + ph[2]) * xp.cos(2 * Y) + 0.3 * a[3] * xp.cos(3 * X) * xp.sin(Z) * xp.cos(Y))
+        out.append(f.reshape(-1))
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc = device, None
+        self.path = tempfile.mktemp(prefix="mrg_clocks_", suffix=".csv")
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            parts = [t.strip() for t in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_reference_rate(steps, warmup, nthreads=None, grid=(32, 32, 32), ppc=64):
+    """The reference's CPU path (C restatement oracle/fulmov_oracle.c, one OpenMP thread per simulated
+    MPI rank with private particle arrays) on a bounded sample of the same workload.
+    Returns (particle-pushes/s, per-step seconds list, description)."""
+    from oracle import pyoracle as O
+    nthreads = nthreads or min(O.num_threads(), 64)
+    mx, my, mz = grid
+    p = O.make_parm(mx, my, mz, HX * mx, HY * my, HZ * mz, DT, AIMPL, WCE, EZ00)
+    sp = {}
+    for ksp in (1, 2):
+        sp[ksp], _, _ = O.loadpt(p, ppc, vth(ksp), 0.0, VBEAM[ksp])
+    for c in range(3):
+        sp[2][c][:] = sp[1][c]
+    fa = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 1, dtype=np.float64)]
+    fb = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 2, dtype=np.float64)]
+    times = []
+    npart = 2 * len(sp[1][0])
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        a6p = O.field_prep(p, fa)            # F:1127-1148, once per phase (the reference redoes it per call)
+        a6c = O.field_prep(p, fb)
+        tprep = time.perf_counter() - t0
+        tt = tprep
+        for ksp in (1, 2):
+            t, _, _ = O.time_step(p, a6p, a6c, sp[ksp], QSPEC[ksp], WSPEC[ksp], nthreads)
+            tt += t
+        if s >= warmup:
+            times.append(tt)
+    rate = npart * len(times) / sum(times)
+    desc = "%dx%dx%d grid, %d ppc, 2 species = %d particles, %d steps, %d threads (C restatement of the reference CPU path)" % (
+        mx, my, mz, ppc, npart, len(times), nthreads)
+    return rate, times, nthreads, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    rate, times, nthreads, desc = cpu_reference_rate(args.steps, args.warmup)
+    mx, my, mz = GRIDS.get(args.gpus, GRIDS[1])
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(times)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus, args),
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": desc},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(n, args):
+    mx, my, mz = GRIDS[n] if not args.grid else tuple(args.grid)
+    return {"workload": "two-flux-bundle equilibrium (rec_3d80A / param_080A.h), %dx%dx%d grid, %d ppc/species, "
+                        "ions+electrons mi/me=100, dt=1.2, aimpl=0.6 (BASELINE configs[%s])"
+                        % (mx, my, mz, args.ppc, "1" if n == 1 else ("2" if n == 8 else "1 scaled")),
+            "grid": [mx, my, mz], "ppc": args.ppc, "species": 2, "particles_per_gpu": 2 * mx * my * mz * args.ppc // n,
+            "sharding": "round-robin particle ownership l = rank+1 (mod N), replicated grids, NCCL fp64 allreduce of J/chi",
+            "sort_every": args.sort_every, "deposit": args.deposit, "iters": args.iters,
+            "l2": "inputs larger than L2 (12.9 GB of particle arrays per GPU vs 126 MB)"}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import mrg_b200 as mrg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists); use --impl reference for the CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mx, my, mz = GRIDS[args.gpus] if not args.grid else tuple(args.grid)
+    ppc = args.ppc
+    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, rank=rank, nranks=world, device=local)
+    if world > 1:
+        uid = mrg.broadcast_unique_id(rank, device=dev)
+        ctx.comm_init(uid)
+    ctx.set_option("deposit", args.deposit)
+    ctx.set_option("iters", args.iters)
+    ctx.set_option("group_min", args.group_min)
+    # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
+    ranfb = 7331
+    for ksp in (1, 2):
+        _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
+    nloc = ctx.num_local(1) + ctx.num_local(2)
+    ntot_particles = 2 * mx * my * mz * ppc
+    n_grid = ctx.n_grid
+    c = mrg.Common(4, 4, 4, 1.0, 1.0, 1.0, dt=DT, aimpl=AIMPL, wce_by_wpe=WCE, Ez00=EZ00)   # scalars only
+    c.mx, c.my, c.mz, c.xmax, c.ymax, c.zmax = mx, my, mz, HX * mx, HY * my, HZ * mz
+    c.zcent, c.ycent1, c.ycent2 = 0.5 * c.zmax, 0.30 * c.ymax, 0.70 * c.ymax
+    params = c.step_params()
+    # two field sets resident in HBM: "before emfild" and "after emfild"
+    fsets = []
+    for seed in (1, 2):
+        f = synth_fields(torch, mx, my, mz, seed, dtype=torch.float64, device=dev)
+        fsets.append([t.contiguous() for t in f])
+    torch.cuda.synchronize()
+    for ksp in (1, 2):
+        ctx.sort(ksp, c.adt)
+
+    state = {"ranfb": ranfb, "step": 0, "tp": [], "tc": []}
+
+    def step_resident():
+        ctx.set_fields_device([t.data_ptr() for t in fsets[0]])
+        for ksp in (1, 2):
+            ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"])
+            state["tp"].append(ctx.last_kernel_ms())
+        ctx.set_fields_device([t.data_ptr() for t in fsets[1]])
+        for ksp in (1, 2):
+            _, _, state["ranfb"] = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, params, state["ranfb"])
+            state["tc"].append(ctx.last_kernel_ms())
+        state["step"] += 1
+        if args.sort_every and state["step"] % args.sort_every == 0:
+            for ksp in (1, 2):
+                ctx.sort(ksp, c.adt)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        step_resident()
+    state["tp"], state["tc"] = [], []
+    ctx.counters(reset=True)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ctx.event_record(0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    barrier()
+    cnt = ctx.counters(reset=True)
+    tms = torch.tensor([ms, float(cnt["launches"])], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx_t = tms.clone(); dist.all_reduce(mx_t, op=dist.ReduceOp.MAX)
+        sm_t = tms.clone(); dist.all_reduce(sm_t, op=dist.ReduceOp.SUM)
+        ms, launches = float(mx_t[0]), int(sm_t[1])
+    else:
+        launches = int(cnt["launches"])
+    value = ntot_particles * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (per launch, algorithmic bytes) --------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)"
+    n_sp = nloc / 2.0                                     # particles per launch (one species on this GPU)
+    bytes_pred = 48.0 * n_sp + (6 + 2 * 4) * 8.0 * n_grid
+    bytes_corr = 96.0 * n_sp + 6 * 8.0 * n_grid
+    tp, tc = float(np.mean(state["tp"])), float(np.mean(state["tc"]))
+    gb_pred, gb_corr = bytes_pred / (tp * 1e-3) / 1e9, bytes_corr / (tc * 1e-3) / 1e9
+    dominant = "k_predict_run" if tp >= tc else "k_correct"
+    ach = gb_pred if tp >= tc else gb_corr
+    step_bytes = 2 * (bytes_pred + bytes_corr)
+    roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "predictor": {"ms_per_launch": tp, "algorithmic_bytes": bytes_pred, "gbs": gb_pred, "frac": gb_pred / peak},
+                "corrector": {"ms_per_launch": tc, "algorithmic_bytes": bytes_corr, "gbs": gb_corr, "frac": gb_corr / peak},
+                "whole_step": {"algorithmic_bytes": step_bytes, "gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 if world == 1 else None,
+                               "frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak if world == 1 else None}}
+
+    # ---- end to end through the reference-facing call with HOST buffers ------------------------------
+    e2e = None
+    if not args.no_e2e:
+        def pinned(n):
+            return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+        hsets = []
+        for fs in fsets:
+            hs = []
+            for t in fs:
+                a = pinned(n_grid)
+                a[:] = t.cpu().numpy()
+                hs.append(a)
+            hsets.append(hs)
+        for name in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe"):
+            setattr(c, name, pinned(n_grid))
+        c.ranfb = state["ranfb"]
+        fm = mrg.Fulmov(c, ipar=rank + 1, size=world, device=local, sort_interval=args.sort_every, ctx=ctx)
+        dummy = [np.zeros(1)] * 6
+        npr = ntot_particles // 2
+
+        def step_e2e():
+            for name, arr in zip(mrg.host.FIELD_NAMES, hsets[0]):
+                setattr(c, name, arr)
+            fm.fields_changed()
+            for ksp in (1, 2):
+                fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 1, ksp)
+            for name, arr in zip(mrg.host.FIELD_NAMES, hsets[1]):
+                setattr(c, name, arr)
+            fm.fields_changed()
+            for ksp in (1, 2):
+                fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 0, ksp)
+
+        ne = max(2, min(args.steps, 5))
+        step_e2e()
+        ctx.counters(reset=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(ne):
+            step_e2e()
+        ctx.synchronize()
+        te = time.perf_counter() - t0
+        cnt_e = ctx.counters(reset=True)
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt[0])
+        e2e = {"value": ntot_particles * ne / te, "unit": UNIT, "h2d_bytes_per_step": cnt_e["h2d_bytes"] // ne,
+               "d2h_bytes_per_step": cnt_e["d2h_bytes"] // ne, "steps": ne, "ms_per_step": 1e3 * te / ne,
+               "note": "host fields in pinned memory -> mrg_set_fields (H2D), moments -> COMMON /srimp7/ arrays (D2H) every "
+                       "step through the Fulmov mirror of the reference call; particles stay resident in HBM by design"}
+        barrier()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            rate, times, nthreads, desc = cpu_reference_rate(args.cpu_steps, 1)
+            cpu = {"value": rate, "unit": UNIT, "cores": nthreads, "kind": "port", "sample": desc}
+        except Exception as ex:                             # the oracle is a reported baseline only
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        cfg = workload_config(args.gpus, args)
+        cfg["parallelism"] = "particle-sharded x%d" % world
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+                "wall_ms_per_step": 1e3 * wall / args.steps,
+                "pct_hbm_roofline_whole_step": None if world > 1 else 100.0 * roofline["whole_step"]["frac"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, nargs=3, default=None, help="override the grid (mx my mz)")
+    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--sort-every", type=int, default=1)
+    ap.add_argument("--deposit", type=int, default=2)
+    ap.add_argument("--iters", type=int, default=8)
+    ap.add_argument("--group-min", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.gpus not in GRIDS and not args.grid:
+        raise SystemExit("--gpus must be 1, 2, 4 or 8 (or give --grid)")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,6 +149,12 @@ int mrg_get_counters(mrg_ctx* ctx, int64_t out[3], int32_t reset);
  * events on the library's stream), in milliseconds.                         */
 int mrg_last_kernel_ms(mrg_ctx* ctx, double* ms);
 
+/* Device-side stopwatch on the library's stream (where every kernel of this
+ * context is launched): record marks slot 0..7, elapsed gives the CUDA-event
+ * time between two recorded slots in milliseconds (synchronises on b).       */
+int mrg_event_record(mrg_ctx* ctx, int32_t slot);
+int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
+
 /* Block the host until all work queued by this context has finished.        */
 int mrg_synchronize(mrg_ctx* ctx);
 

@@ -20,7 +20,8 @@ SYMBOLS = [
     "mrg_comm_init", "mrg_upload_particles", "mrg_download_particles", "mrg_num_local",
     "mrg_loadpt", "mrg_set_fields", "mrg_set_fields_device", "mrg_fulmov", "mrg_get_moments",
     "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_sort", "mrg_set_option",
-    "mrg_get_counters", "mrg_last_kernel_ms", "mrg_synchronize",
+    "mrg_get_counters", "mrg_last_kernel_ms", "mrg_event_record", "mrg_event_elapsed_ms",
+    "mrg_synchronize",
 ]
 
 
@@ -83,6 +84,8 @@ def load(build_if_missing=True):
     L.mrg_get_counters.argtypes = [vp, C.POINTER(i64), i32]
     L.mrg_last_kernel_ms.argtypes = [vp, dp]
     L.mrg_synchronize.argtypes = [vp]
+    L.mrg_event_record.argtypes = [vp, i32]
+    L.mrg_event_elapsed_ms.argtypes = [vp, i32, i32, dp]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("mrg_last_error", "mrg_build_info", "mrg_num_local"):

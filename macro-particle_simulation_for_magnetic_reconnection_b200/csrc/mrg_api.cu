@@ -103,6 +103,7 @@ struct mrg_ctx {
   GP g;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t user_ev[8] = {};
   // fields
   double* f12[12] = {};
   double* A6[6] = {};
@@ -314,6 +315,7 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
+  for (int k = 0; k < 8; k++) CK(cudaEventCreate(&c->user_ev[k]));
   const size_t gb = (size_t)ntot * sizeof(double);
   for (int k = 0; k < 12; k++) { CK(cudaMalloc((void**)&c->f12[k], gb)); CK(cudaMemsetAsync(c->f12[k], 0, gb, c->stream)); }
   for (int k = 0; k < 6; k++) {
@@ -347,6 +349,7 @@ int mrg_destroy(mrg_ctx* c) {
   cudaFree(c->scan_tiles); cudaFree(c->slab_bits); cudaFree(c->slab_words); cudaFree(c->slab_list); cudaFree(c->slab_count);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  for (int k = 0; k < 8; k++) cudaEventDestroy(c->user_ev[k]);
   cudaStreamDestroy(c->stream);
   delete c;
   return MRG_OK;
@@ -746,6 +749,23 @@ int mrg_get_counters(mrg_ctx* c, int64_t out[3], int32_t reset) {
 int mrg_last_kernel_ms(mrg_ctx* c, double* ms) {
   if (!c || !ms) return fail(MRG_ERR_ARG, "null argument");
   *ms = c->last_kernel_ms;
+  return MRG_OK;
+}
+
+int mrg_event_record(mrg_ctx* c, int32_t slot) {
+  if (!c || slot < 0 || slot >= 8) return fail(MRG_ERR_ARG, "bad event slot");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventRecord(c->user_ev[slot], c->stream));
+  return MRG_OK;
+}
+
+int mrg_event_elapsed_ms(mrg_ctx* c, int32_t a, int32_t b, double* ms) {
+  if (!c || !ms || a < 0 || a >= 8 || b < 0 || b >= 8) return fail(MRG_ERR_ARG, "bad event slot");
+  CK(cudaSetDevice(c->device));
+  CK(cudaEventSynchronize(c->user_ev[b]));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, c->user_ev[a], c->user_ev[b]));
+  *ms = f;
   return MRG_OK;
 }
 

@@ -21,6 +21,30 @@ def mxyzA(mx, my, mz):
     return (mx + 4) * (my + 3) * (mz + 4)
 
 
+def owned_count(npr, ipar, size):
+    """Number of l in `do l= ipar,npr,size` (F:1162); ipar = rank+1 (F:219)."""
+    return 0 if npr < ipar else (npr - ipar) // size + 1
+
+
+def owned_slice(ipar, size):
+    """0-based numpy slice of the particles rank ipar-1 owns."""
+    return slice(ipar - 1, None, size)
+
+
+def broadcast_unique_id(rank, make_id=None, device=None):
+    """Rank 0 creates the NCCL unique id, torch.distributed carries the 128
+    bytes to every rank (the Fortran host would MPI_Bcast them).  Works on any
+    initialised backend (gloo: CPU tensor, nccl: pass the cuda device)."""
+    import torch
+    import torch.distributed as dist
+    buf = torch.zeros(capi.UNIQUE_ID_BYTES, dtype=torch.uint8, device=device if device is not None else "cpu")
+    if rank == 0:
+        raw = (make_id or MrgContext.unique_id)()
+        buf.copy_(torch.frombuffer(bytearray(raw), dtype=torch.uint8))
+    dist.broadcast(buf, src=0)
+    return bytes(buf.cpu().numpy().tobytes())
+
+
 class Common:
     """The COMMON-block values fulmov reads/writes (F:1066-1110), as numpy."""
 
@@ -156,6 +180,14 @@ class MrgContext:
     def synchronize(self):
         check(self.lib.mrg_synchronize(self.h))
 
+    def event_record(self, slot):
+        check(self.lib.mrg_event_record(self.h, slot))
+
+    def event_elapsed_ms(self, a, b):
+        ms = C.c_double()
+        check(self.lib.mrg_event_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
+
 
 class Fulmov:
     """Drop-in for the reference's `fulmov` on one rank.
@@ -170,16 +202,20 @@ class Fulmov:
     after particles_changed); use pull() before host code looks at them.
     """
 
-    def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1):
+    def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1, ctx=None):
         self.c = common
         self.ipar, self.size = ipar, size
-        self.ctx = MrgContext(common.mx, common.my, common.mz, common.xmax, common.ymax, common.zmax,
-                              nspecies=2, rank=ipar - 1, nranks=size, device=device)
-        if size > 1:
-            if uid is None:
-                raise ValueError("size > 1 needs the NCCL unique id broadcast from rank 0")
-            self.ctx.comm_init(uid)
         self.resident = {}
+        if ctx is not None:      # adopt a context whose particles are already resident (device loader)
+            self.ctx = ctx
+            self.resident = {k: ctx.num_local(k) for k in (1, 2) if ctx.num_local(k) > 0}
+        else:
+            self.ctx = MrgContext(common.mx, common.my, common.mz, common.xmax, common.ymax, common.zmax,
+                                  nspecies=2, rank=ipar - 1, nranks=size, device=device)
+            if size > 1:
+                if uid is None:
+                    raise ValueError("size > 1 needs the NCCL unique id broadcast from rank 0")
+                self.ctx.comm_init(uid)
         self.fields_dirty = True
         self.sort_interval = sort_interval
         self.ncorr = {1: 0, 2: 0}

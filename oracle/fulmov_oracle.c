@@ -567,3 +567,71 @@ int64_t orc_loadpt(const orc_parm* p, int ppc, double vth, double vdr,
   }
   return npr;
 }
+
+/* ------------------------------------------------------------------------ */
+/* CPU-baseline timer: one full particle step (ipc=1 then ipc=0, F:761-787)
+ * of one species executed the way the reference's MPI job does it: every
+ * "rank" (an OpenMP thread here) holds its OWN full-size copy of the particle
+ * arrays and temporaries (F:121-122, 1057) and walks them with stride nranks.
+ * Copies are made before the clock starts.  Returns the wall-clock seconds of
+ * the two passes including the rank-ordered moment sums and the folds; the
+ * field preparation (a6p for the predictor, a6c for the corrector) is timed
+ * separately by the caller.  x..vz are left untouched. */
+double orc_time_step(const orc_parm* p, const double* const a6p[6], const double* const a6c[6],
+                     const double* x, const double* y, const double* z, const double* vx,
+                     const double* vy, const double* vz, double qmult, double wmult, int64_t npr,
+                     int nranks, double* t_pred, double* t_corr) {
+  const int64_t n = orc_mxyzA(p);
+  const size_t np = (size_t)(npr > 0 ? npr : 1);
+  double** priv = (double**)malloc((size_t)nranks * 12 * sizeof(double*));
+  const double* src[6] = {x, y, z, vx, vy, vz};
+  for (int r = 0; r < nranks; r++)
+    for (int c = 0; c < 12; c++) {
+      priv[r * 12 + c] = (double*)malloc(np * sizeof(double));
+      if (c < 6) memcpy(priv[r * 12 + c], src[c], np * sizeof(double));
+      else memset(priv[r * 12 + c], 0, np * sizeof(double));
+    }
+  double* part = (double*)calloc((size_t)nranks * 4 * (size_t)n, sizeof(double));
+  double* mom = (double*)calloc((size_t)4 * (size_t)n, sizeof(double));
+  double* wkr = (double*)calloc((size_t)nranks * 2, sizeof(double));
+  int32_t* st = (int32_t*)malloc((size_t)nranks * sizeof(int32_t));
+  for (int r = 0; r < nranks; r++) st[r] = 7331;
+  double t0 = 0, t1 = 0, t2 = 0;
+#ifdef _OPENMP
+  t0 = omp_get_wtime();
+#pragma omp parallel for schedule(static, 1)
+#endif
+  for (int r = 0; r < nranks; r++) {
+    double** q = priv + r * 12;
+    double* rr[4];
+    for (int c = 0; c < 4; c++) rr[c] = part + ((size_t)r * 4 + c) * (size_t)n;
+    fulmov_rank(p, a6p, q[0], q[1], q[2], q[3], q[4], q[5], qmult, wmult, npr, 1, r + 1, nranks,
+                &st[r], rr, &wkr[2 * r], q[6], q[7], q[8], q[9], q[10], q[11]);
+  }
+  for (int c = 0; c < 4; c++)
+    for (int64_t m = 0; m < n; m++) {
+      double s = 0.0;
+      for (int r = 0; r < nranks; r++) s = s + part[((size_t)r * 4 + c) * (size_t)n + m];
+      mom[(size_t)c * (size_t)n + m] = s;
+    }
+  orc_vmesh3(p, mom, mom + n, mom + 2 * n);
+  orc_vmesh1(p, mom + 3 * n);
+#ifdef _OPENMP
+  t1 = omp_get_wtime();
+#pragma omp parallel for schedule(static, 1)
+#endif
+  for (int r = 0; r < nranks; r++) {
+    double** q = priv + r * 12;
+    double* rr[4] = {NULL, NULL, NULL, NULL};
+    fulmov_rank(p, a6c, q[0], q[1], q[2], q[3], q[4], q[5], qmult, wmult, npr, 0, r + 1, nranks,
+                &st[r], rr, &wkr[2 * r], q[6], q[7], q[8], q[9], q[10], q[11]);
+  }
+#ifdef _OPENMP
+  t2 = omp_get_wtime();
+#endif
+  if (t_pred) *t_pred = t1 - t0;
+  if (t_corr) *t_corr = t2 - t1;
+  for (int r = 0; r < nranks * 12; r++) free(priv[r]);
+  free(priv); free(part); free(mom); free(wkr); free(st);
+  return t2 - t0;
+}

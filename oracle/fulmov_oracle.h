@@ -114,6 +114,13 @@ int64_t orc_loadpt(const orc_parm* p, int ppc, double vth, double vdr,
 void orc_loadpt_fv2(double vth, double vdr, double fv2[101], double* v2,
                     double* dv2);
 
+/* CPU-baseline timer (one species, ipc=1 then ipc=0) with per-rank private
+ * particle arrays as in the reference's MPI job; returns seconds.            */
+double orc_time_step(const orc_parm* p, const double* const a6p[6], const double* const a6c[6],
+                     const double* x, const double* y, const double* z, const double* vx,
+                     const double* vy, const double* vz, double qmult, double wmult, int64_t npr,
+                     int nranks, double* t_pred, double* t_corr);
+
 int orc_num_threads(void);
 
 #ifdef __cplusplus

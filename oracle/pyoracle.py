@@ -78,6 +78,8 @@ def lib():
         L.orc_loadpt.argtypes = [P, C.c_int, C.c_double, C.c_double, C.c_double] + [dp] * 6 + [i32p, i32p]
         L.orc_loadpt_fv2.argtypes = [C.c_double, C.c_double, dp, dp, dp]
         L.orc_num_threads.restype = C.c_int
+        L.orc_time_step.restype = C.c_double
+        L.orc_time_step.argtypes = [P, C.POINTER(dp), C.POINTER(dp)] + [dp] * 6 + [C.c_double, C.c_double, i64, C.c_int, dp, dp]
         _lib = L
     return _lib
 
@@ -196,3 +198,12 @@ def ranfp_stream(state, n):
 
 def num_threads():
     return lib().orc_num_threads()
+
+
+def time_step(p, a6p, a6c, arrs, qmult, wmult, nranks):
+    """Seconds for one species' predictor + corrector pass by `nranks` threads
+    (each with private particle arrays, like the reference's MPI ranks)."""
+    tp, tc = C.c_double(), C.c_double()
+    t = lib().orc_time_step(C.byref(p), _parr(a6p), _parr(a6c), *[_p(a) for a in arrs], qmult, wmult,
+                            len(arrs[0]), nranks, C.byref(tp), C.byref(tc))
+    return t, tp.value, tc.value

@@ -1,0 +1,150 @@
+"""The host-side mirrors of `subroutine fulmov` (F:1044): the Python `Fulmov`
+and the C++ `fulmov` of csrc/mrg_host.cpp (what the ISO_C_BINDING shim calls)
+reproduce the subroutine's side effects on COMMON-like storage."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+MTOL, PTOL = 1e-10, 1e-12
+
+
+def _oracle_step(p, f_pred, f_corr, sp, ranfb):
+    ref = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.array([ranfb], dtype=np.int32)
+    mom, wk = {}, {}
+    a6 = O.field_prep(p, f_pred)
+    for k in (1, 2):
+        r = O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 1, nranks=1, ranfb=st)
+        mom[k] = r["mom"]
+    a6 = O.field_prep(p, f_corr)
+    for k in (1, 2):
+        r = O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 0, nranks=1, ranfb=st)
+        wk[k] = (r["wkix"], r["wkih"])
+    return ref, mom, wk, int(st[0])
+
+
+@pytest.fixture(scope="module")
+def case():
+    p = U.make_parm(12, 10, 12)
+    sp, ranfb = U.load_species(p, 12)
+    return p, sp, ranfb, U.smooth_fields(p, seed=21), U.smooth_fields(p, seed=22)
+
+
+def test_python_fulmov_mirror(case):
+    import mrg_b200 as mrg
+    p, sp, ranfb, f_pred, f_corr = case
+    ref, mom, wk, st_ref = _oracle_step(p, f_pred, f_corr, sp, ranfb)
+    c = mrg.Common(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, dt=p.dt, aimpl=p.aimpl, wce_by_wpe=p.bxc, Ez00=p.Ez00)
+    c.ranfb = ranfb
+    c.it, c.nha, c.ldec = 5, 5, 2                      # mod(it,nha)==0 -> edec row ldec is written
+    fm = mrg.Fulmov(c, ipar=1, size=1)
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    npr = len(sp[1][0])
+    for name, arr in zip(mrg.host.FIELD_NAMES, f_pred):
+        getattr(c, name)[:] = arr
+    for k in (1, 2):
+        fm(*host[k], U.QSPEC[k], U.WSPEC[k], npr, 1, k)
+    for cidx, (a, b) in enumerate(zip((c.qix, c.qiy, c.qiz, c.qi), mom[1])):
+        assert U.rel_l2(a, b) < MTOL, cidx
+    for cidx, (a, b) in enumerate(zip((c.qex, c.qey, c.qez, c.qe), mom[2])):
+        assert U.rel_l2(a, b) < MTOL, cidx
+    for name, arr in zip(mrg.host.FIELD_NAMES, f_corr):
+        getattr(c, name)[:] = arr
+    fm.fields_changed()
+    for k in (1, 2):
+        fm(*host[k], U.QSPEC[k], U.WSPEC[k], npr, 0, k)
+        assert abs(c.wkix - wk[k][0]) < MTOL * abs(wk[k][0])
+        col = 5 if k == 1 else 7
+        assert c.edec[col - 1, c.ldec - 1] == c.wkix and c.edec[col, c.ldec - 1] == c.wkih   # F:1320-1328
+    assert c.ranfb == st_ref
+    for k in (1, 2):
+        fm.pull(k, *host[k], npr)
+        assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < PTOL
+
+
+_dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+
+class View(C.Structure):
+    """mirror of mrg_common_view (csrc/mrg_host.h)"""
+    _fields_ = ([("mx", C.c_int32), ("my", C.c_int32), ("mz", C.c_int32)]
+                + [(n, _dp) for n in ("ex", "ey", "ez", "bx", "by", "bz", "ex0", "ey0", "ez0", "bx0", "by0", "bz0")]
+                + [(n, _dp) for n in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe")]
+                + [(n, _ip) for n in ("it", "ldec", "ifilx", "ifily", "ifilz", "nha")]
+                + [(n, _dp) for n in ("xmax", "ymax", "zmax", "dt", "aimpl", "adt", "hdt", "bxc", "byc", "bzc", "edec")]
+                + [(n, _dp) for n in ("wkix", "wkih", "zcent", "ycent1", "ycent2", "Ez00")]
+                + [("ranfb", _ip), ("io_pe", _ip)])
+
+
+def test_cpp_fulmov_mirror(case):
+    """C++ `fulmov` with the Fortran calling convention (everything by reference)."""
+    import mrg_b200 as mrg
+    p, sp, ranfb, f_pred, f_corr = case
+    ref, mom, wk, st_ref = _oracle_step(p, f_pred, f_corr, sp, ranfb)
+    mrg.build.build_host()
+    lib = C.CDLL(mrg.build.HOSTLIB)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.fulmov.argtypes = [dp] * 8 + [ip] * 5
+    lib.fulmov.restype = None
+    lib.mrg_host_pull_particles.argtypes = [C.c_int32] + [dp] * 6 + [C.c_int32] * 3
+    n = O.mxyzA(p)
+    store = {}
+
+    def darr(name, val):
+        store[name] = np.array(val, dtype=np.float64).reshape(-1).copy() if not isinstance(val, np.ndarray) else val
+        return store[name].ctypes.data_as(dp)
+
+    def iarr(name, val):
+        store[name] = np.array([val], dtype=np.int32)
+        return store[name].ctypes.data_as(ip)
+
+    v = View()
+    v.mx, v.my, v.mz = p.mx, p.my, p.mz
+    fnames = ("ex", "ey", "ez", "bx", "by", "bz", "ex0", "ey0", "ez0", "bx0", "by0", "bz0")
+    for name, arr in zip(fnames, f_pred):
+        setattr(v, name, darr(name, arr.copy()))
+    for name in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe"):
+        setattr(v, name, darr(name, np.zeros(n)))
+    for name, val in (("it", 5), ("ldec", 2), ("ifilx", 1), ("ifily", 1), ("ifilz", 1), ("nha", 5), ("ranfb", ranfb), ("io_pe", 1)):
+        setattr(v, name, iarr(name, val))
+    for name, val in (("xmax", p.xmax), ("ymax", p.ymax), ("zmax", p.zmax), ("dt", p.dt), ("aimpl", p.aimpl),
+                      ("adt", p.adt), ("hdt", p.hdt), ("bxc", p.bxc), ("byc", p.byc), ("bzc", p.bzc),
+                      ("wkix", 0.0), ("wkih", 0.0), ("zcent", p.zcent), ("ycent1", p.ycent1), ("ycent2", p.ycent2),
+                      ("Ez00", p.Ez00)):
+        setattr(v, name, darr(name, [val]))
+    v.edec = darr("edec", np.zeros(3000 * 12))
+    assert lib.mrg_host_bind(C.byref(v), 0) == 0
+    lib.mrg_host_set_exit_on_error(0)
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    npr = C.c_int32(len(sp[1][0]))
+    one, size = C.c_int32(1), C.c_int32(1)
+
+    def call(k, ipc):
+        q, w = C.c_double(U.QSPEC[k]), C.c_double(U.WSPEC[k])
+        lib.fulmov(*[a.ctypes.data_as(dp) for a in host[k]], C.byref(q), C.byref(w), C.byref(npr),
+                   C.byref(C.c_int32(ipc)), C.byref(C.c_int32(k)), C.byref(one), C.byref(size))
+        assert lib.mrg_host_status() == 0
+
+    call(1, 1); call(2, 1)
+    for cidx, name in enumerate(("qix", "qiy", "qiz", "qi")):
+        assert U.rel_l2(store[name], mom[1][cidx]) < MTOL, name
+    for cidx, name in enumerate(("qex", "qey", "qez", "qe")):
+        assert U.rel_l2(store[name], mom[2][cidx]) < MTOL, name
+    for name, arr in zip(fnames, f_corr):                 # "emfild" wrote new fields into COMMON /fields/
+        store[name][:] = arr
+    lib.mrg_host_fields_changed()
+    call(1, 0)
+    assert abs(store["wkix"][0] - wk[1][0]) < MTOL * abs(wk[1][0])
+    assert store["edec"][1 + 3000 * 4] == store["wkix"][0] and store["edec"][1 + 3000 * 5] == store["wkih"][0]
+    call(2, 0)
+    assert store["edec"][1 + 3000 * 6] == store["wkix"][0]
+    assert int(store["ranfb"][0]) == st_ref
+    for k in (1, 2):
+        assert lib.mrg_host_pull_particles(k, *[a.ctypes.data_as(dp) for a in host[k]], npr.value, 1, 1) == 0
+        assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < PTOL
+    lib.mrg_host_unbind()

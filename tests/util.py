@@ -38,7 +38,7 @@ def idx(p, i, j, k):
     return (i + 2) + (p.mx + 4) * ((j + 1) + (p.my + 3) * (k + 2))
 
 
-def smooth_fields(p, seed=0, amp_e=1e-2, amp_b=0.1, ghost_nan=True):
+def smooth_fields(p, seed=0, amp_e=1e-2, amp_b=0.03, ghost_nan=True):
     """12 field arrays (ex..bz, ex0..bz0): smooth flux-bundle-like modes on the
     interior points the reference defines (i<mx, j<=my, k<mz).  Ghost elements
     are NaN: fulmov must never read them (F:1127-1139 touches the interior
