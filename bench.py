@@ -169,7 +169,8 @@ def workload_config(n, args):
                         % (mx, my, mz, args.ppc, "1" if n == 1 else ("2" if n == 8 else "1 scaled")),
             "grid": [mx, my, mz], "ppc": args.ppc, "species": 2, "particles_per_gpu": 2 * mx * my * mz * args.ppc // n,
             "sharding": "round-robin particle ownership l = rank+1 (mod N), replicated grids, NCCL fp64 allreduce of J/chi",
-            "sort_every": args.sort_every, "deposit": args.deposit, "iters": args.iters,
+            "sort_every": args.sort_every, "deposit": args.deposit, "iters": args.iters, "tile": args.tile,
+            "fused_keys": args.fused_keys,
             "l2": "inputs larger than L2 (12.9 GB of particle arrays per GPU vs 126 MB)"}
 
 
@@ -199,6 +200,8 @@ def run_ours(args):
     ctx.set_option("deposit", args.deposit)
     ctx.set_option("iters", args.iters)
     ctx.set_option("group_min", args.group_min)
+    ctx.set_option("tile", args.tile)
+    ctx.set_option("fused_keys", args.fused_keys)
     # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
     ranfb = 7331
     for ksp in (1, 2):
@@ -217,7 +220,7 @@ def run_ours(args):
         fsets.append([t.contiguous() for t in f])
     torch.cuda.synchronize()
     for ksp in (1, 2):
-        ctx.sort(ksp, c.adt)
+        ctx.sort(ksp, c.hdt)          # sort key = cell of the gather position x + hdt*v
 
     state = {"ranfb": ranfb, "step": 0, "tp": [], "tc": []}
 
@@ -233,7 +236,7 @@ def run_ours(args):
         state["step"] += 1
         if args.sort_every and state["step"] % args.sort_every == 0:
             for ksp in (1, 2):
-                ctx.sort(ksp, c.adt)
+                ctx.sort(ksp, c.hdt)
 
     def barrier():
         ctx.synchronize()
@@ -280,7 +283,7 @@ def run_ours(args):
     bytes_corr = 96.0 * n_sp + 6 * 8.0 * n_grid
     tp, tc = float(np.mean(state["tp"])), float(np.mean(state["tc"]))
     gb_pred, gb_corr = bytes_pred / (tp * 1e-3) / 1e9, bytes_corr / (tc * 1e-3) / 1e9
-    dominant = "k_predict_run" if tp >= tc else "k_correct"
+    dominant = ("k_predict_tile" if args.tile else "k_predict_run") if tp >= tc else ("k_correct_tile" if args.tile else "k_correct")
     ach = gb_pred if tp >= tc else gb_corr
     step_bytes = 2 * (bytes_pred + bytes_corr)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -377,6 +380,8 @@ def main():
     ap.add_argument("--deposit", type=int, default=2)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--group-min", type=int, default=2)
+    ap.add_argument("--tile", type=int, default=1)
+    ap.add_argument("--fused-keys", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

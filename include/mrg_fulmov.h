@@ -136,9 +136,17 @@ int mrg_get_prepared_fields(mrg_ctx* ctx, const mrg_step_params* p,
 int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
 
 /* Kernel selection and tuning knobs (name/value); unknown names fail.
- *   "deposit"  0 = per-particle global atomics, 1 = warp pre-reduction
- *              (match_any + shuffle) then global atomics, 2 = cell-run
- *              register accumulation + warp pre-reduction (default)          */
+ *   "deposit"    0 = per-particle global atomics, 1 = warp pre-reduction
+ *                (ballot/shuffle) per 32 particles then atomics, 2 = cell-run
+ *                register accumulation + warp pre-reduction (default)
+ *   "tile"       1 (default) = after mrg_sort, particle passes run on
+ *                TMA-staged shared-memory field tiles with shared-memory
+ *                moment accumulators; 0 = gather through L1 only
+ *   "fused_keys" 1 (default) = the tiled corrector also emits the next sort
+ *                keys (cell of x + hdt*v), so mrg_sort(ksp, hdt) skips its
+ *                key pass
+ *   "iters"      particles per warp / 32 of the untiled predictor (4..32)
+ *   "group_min"  smallest stray group (particles) that is pre-reduced        */
 int mrg_set_option(mrg_ctx* ctx, const char* name, int64_t value);
 
 /* Counters since the last reset: [0] kernels launched by this library,

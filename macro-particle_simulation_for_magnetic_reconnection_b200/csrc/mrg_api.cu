@@ -4,6 +4,7 @@
 // the fold, the drive kick and the cell sort.  F:n = @mrg37-080A.f03 line n.
 #include "../../include/mrg_fulmov.h"
 #include "mrg_kernels.cuh"
+#include "mrg_tile.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -84,6 +85,14 @@ struct Species {
   double* M4 = nullptr;    // raw moments [ntot][4] + 2 (wkix, wkih)
   double* out4[4] = {nullptr, nullptr, nullptr, nullptr};  // folded, reference layout
   bool have_moments = false;
+  // cell index of the current slot order (built by mrg_sort): cell_end[c] = end slot of cell c
+  int* cell_end = nullptr;
+  bool index_valid = false;
+  // next-sort keys emitted by the corrector (fused_keys) + their histogram
+  int* key = nullptr; long long key_cap = 0;
+  int* hist = nullptr;
+  bool keys_valid = false;
+  double keys_lookahead = 0.0;
 };
 
 struct PrepKey {
@@ -132,7 +141,7 @@ struct mrg_ctx {
   // nccl
   void* comm = nullptr;
   // options / counters
-  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2;
+  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1;
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -184,6 +193,12 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   }
   if (s.id) { CK(cudaFree(s.id)); s.id = nullptr; }
   s.n = n;
+  s.index_valid = false;
+  s.keys_valid = false;
+  if (!s.cell_end) {
+    CK(cudaMalloc((void**)&s.cell_end, (size_t)(c->ncell + 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&s.hist, (size_t)(c->ncell + 1) * sizeof(int)));
+  }
   if (!s.M4) {
     CK(cudaMalloc((void**)&s.M4, ((size_t)c->g.ntot * 4 + 2) * sizeof(double)));
     for (int k = 0; k < 4; k++) CK(cudaMalloc((void**)&s.out4[k], (size_t)c->g.ntot * sizeof(double)));
@@ -342,7 +357,7 @@ int mrg_destroy(mrg_ctx* c) {
   cudaFree(c->F6); cudaFree(c->alt_id);
   for (auto& s : c->sp) {
     for (int k = 0; k < 6; k++) cudaFree(s.d[k]);
-    cudaFree(s.id); cudaFree(s.M4);
+    cudaFree(s.id); cudaFree(s.M4); cudaFree(s.cell_end); cudaFree(s.key); cudaFree(s.hist);
     for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
   }
   cudaFree(c->wk_partial); cudaFree(c->wk2); cudaFree(c->sort_key); cudaFree(c->hist); cudaFree(c->cursor);
@@ -541,13 +556,16 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     const int B = 128;
     if (s.n > 0) {
       const int iters = (c->opt_deposit == 2) ? c->opt_iters : 1;
+      const bool tiled = c->opt_tile && c->opt_deposit == 2 && s.index_valid;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
+      if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz;
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * blocks, sizeof(double));
       if (rc) return rc;
       CK(cudaEventRecord(c->ev0, c->stream));
       const int gm = c->opt_group_min * 4;   // option counts particles; a particle is a quad of lanes
-      if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
+      if (tiled) k_predict_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm);
+      else if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
       else if (iters == 1) k_predict_run<1><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
       else if (iters == 4) k_predict_run<4><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
       else if (iters == 8) k_predict_run<8><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
@@ -587,14 +605,30 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CK(cudaMemsetAsync(c->slab_count, 0, sizeof(int), c->stream));
     }
     CK(cudaMemsetAsync(c->wk2, 0, 2 * sizeof(double), c->stream));
+    s.keys_valid = false;
     if (s.n > 0) {
-      const int B = 256;
-      const int blocks = grid_for(s.n, B);
+      const bool tiled = c->opt_tile && s.index_valid;
+      const int B = tiled ? 128 : 256;
+      const int blocks = tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz : grid_for(s.n, B);
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * blocks, sizeof(double));
       if (rc) return rc;
+      int* key_out = nullptr;
+      if (tiled && c->opt_fused_keys) {   // emit next step's sort keys (cell of x + hdt*v) and their histogram
+        rc = ensure(c, (void**)&s.key, &s.key_cap, s.n, sizeof(int));
+        if (rc) return rc;
+        CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+        key_out = s.key;
+      }
       CK(cudaEventRecord(c->ev0, c->stream));
-      k_correct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, c->wk_partial, c->slab_bits, c->slab_list, c->slab_count); CKL(c);
+      if (tiled) {
+        k_correct_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, c->slab_bits, c->slab_list,
+                                                    c->slab_count, key_out, s.hist, p->hdt);
+      } else {
+        k_correct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, c->wk_partial, c->slab_bits, c->slab_list, c->slab_count);
+      }
+      CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
+      if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
       k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, blocks, c->wk2); CKL(c);
     }
     if (c->nranks > 1) {                                           // F:1312-1315
@@ -693,18 +727,23 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
   if (s.n == 0) return MRG_OK;
   rc = ensure_alt(c, s.cap, true);
   if (rc) return rc;
-  rc = ensure(c, (void**)&c->sort_key, &c->sort_key_cap, s.n, sizeof(int));
+  rc = ensure(c, (void**)&s.key, &s.key_cap, s.n, sizeof(int));
   if (rc) return rc;
   const int B = 256;
-  CK(cudaMemsetAsync(c->hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
-  k_sort_keys<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, c->sort_key, c->hist); CKL(c);
-  rc = scan_excl(c, c->hist, c->cursor, c->ncell + 1, nullptr);
+  if (!(s.keys_valid && s.keys_lookahead == lookahead)) {   // the corrector may already have emitted keys + histogram
+    CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+    k_sort_keys<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, s.key, s.hist); CKL(c);
+  }
+  s.keys_valid = false;
+  rc = scan_excl(c, s.hist, s.cell_end, c->ncell + 1, nullptr);
   if (rc) return rc;
   SortArrays A;
   for (int k = 0; k < 6; k++) { A.src[k] = s.d[k]; A.dst[k] = c->alt[k]; }
   A.id_src = s.id; A.id_dst = c->alt_id;
-  k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, c->sort_key, c->cursor, A); CKL(c);
+  // the scatter advances cell_end[c] from the start to the end slot of cell c
+  k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.cell_end, A); CKL(c);
   CK(cudaStreamSynchronize(c->stream));
+  s.index_valid = true;
   // the spare buffer becomes the species' storage and vice versa
   for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
   int* old_id = s.id;
@@ -730,6 +769,10 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
   } else if (n == "iters") {
     if (value != 4 && value != 8 && value != 16 && value != 32) return fail(MRG_ERR_ARG, "iters must be 4, 8, 16 or 32");
     c->opt_iters = (int)value;
+  } else if (n == "tile") {
+    c->opt_tile = value != 0;
+  } else if (n == "fused_keys") {
+    c->opt_fused_keys = value != 0;
   } else if (n == "group_min") {
     if (value < 1 || value > 9) return fail(MRG_ERR_ARG, "group_min must be in 1..9 (particles per sub-iteration group)");
     c->opt_group_min = (int)value;

@@ -125,7 +125,7 @@ void fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz,
   } else {
     H.corrector_calls[k - 1]++;
     if (H.sort_interval > 0 && H.corrector_calls[k - 1] % H.sort_interval == 0) {
-      rc = mrg_sort(H.ctx, k, *v.adt);
+      rc = mrg_sort(H.ctx, k, *v.hdt);   // key = cell of the next gather position x + hdt*v
       if (rc) return die("mrg_sort", rc);
     }
   }

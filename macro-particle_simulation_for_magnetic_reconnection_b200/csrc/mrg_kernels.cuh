@@ -335,140 +335,6 @@ k_predict_direct(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------
-// k_predict_run: cell-run deposition with warp-level pre-reduction.
-//
-// A warp owns 32*ITERS consecutive particles (cell-sorted in HBM).  Per
-// iteration:
-//   phase A  each lane gathers, rotates and predicts ONE particle and parks
-//            its 17 scatter factors + stencil key in the warp's shared-memory
-//            slab (9 x 128-bit stores).
-//   phase B  four sub-iterations of 8 particles: a QUAD of lanes serves one
-//            particle, lane q of the quad owning the value rows g9 = 2q, 2q+1
-//            (18 of the 72 stencil x moment values).  Lanes are grouped by
-//            stencil key (ballot/shfl match).  A group that continues the
-//            warp's current cell, is large, or reaches the last lane is
-//            summed in REGISTERS (18 accumulators per lane) across
-//            sub-iterations and iterations; when the warp moves to another
-//            cell the accumulators are reduced with one transposing + two
-//            plain shuffle rounds and flushed with 72 red.global.add.f64 per
-//            WARP (instead of 72 per particle).  Stray small groups fall back
-//            to per-particle atomics, so any particle order is correct; cell
-//            order only makes it fast.
-// ---------------------------------------------------------------------------
-constexpr int PR_WARPS = 4;                 // warps per block
-constexpr int PR_W_STRIDE = 10;             // doubles per particle in the W slab: wxz[9] + key
-
-__device__ __forceinline__ void flush_quad(double* acc, int n0, const GP& g, double* __restrict__ M4) {
-  const int lane = threadIdx.x & 31;
-  const bool hi = (lane & 16) != 0;
-  tr_round<18>(acc, hi, 16);                // acc[0..8]: row g9 = 2q + hi, summed over lane pairs
-#pragma unroll
-  for (int r = 0; r < 9; r++) {
-    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 8);
-    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 4);
-  }
-  const int g9 = 2 * (lane & 3) + (hi ? 1 : 0);
-  const int u = (lane >> 2) & 3;            // the 4 lanes holding the same sums share the 9 atomics
-  const double v0 = sel(u == 0, acc[0], sel(u == 1, acc[1], sel(u == 2, acc[2], acc[3])));
-  const double v1 = sel(u == 0, acc[4], sel(u == 1, acc[5], sel(u == 2, acc[6], acc[7])));
-  atomicAdd(mom_addr(M4, g, n0, g9, u), v0);
-  atomicAdd(mom_addr(M4, g, n0, g9, u + 4), v1);
-  if (u == 0) atomicAdd(mom_addr(M4, g, n0, g9, 8), acc[8]);
-}
-
-template <int ITERS>
-__global__ void __launch_bounds__(PR_WARPS * 32)
-k_predict_run(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
-              double* __restrict__ wk_partial, int group_min) {
-  __shared__ __align__(16) double smW[PR_WARPS][32 * PR_W_STRIDE];   // per particle: wxz[0..8], key
-  __shared__ __align__(16) double smQ[PR_WARPS][4 * 32 * 2];         // [q][particle][2]: qvy[2q], qvy[2q+1]
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int q = lane & 3, pl = lane >> 2;
-  double* W = smW[w];
-  double* Q = smQ[w];
-  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const long long base = warp * (32LL * ITERS);
-  double wx = 0.0, wh = 0.0;
-  double acc[18];
-#pragma unroll
-  for (int n = 0; n < 18; n++) acc[n] = 0.0;
-  int cur = -1;
-#pragma unroll 1
-  for (int it = 0; it < ITERS; it++) {
-    const long long t = base + 32LL * it + lane;
-    if (base + 32LL * it >= P.n) break;                     // warp-uniform
-    // ---- phase A
-    {
-      double qvy[8], wxz[9];
-      int key = -1;
-      if (t < P.n) {
-        const Predicted o = predict_one(g, pp, P, t, F6, wx, wh);
-        key = scatter_factors(g, pp.qmult, o, qvy, wxz);
-      } else {
-#pragma unroll
-        for (int n = 0; n < 8; n++) qvy[n] = 0.0;
-#pragma unroll
-        for (int n = 0; n < 9; n++) wxz[n] = 0.0;
-      }
-      double2* Wp = reinterpret_cast<double2*>(W + lane * PR_W_STRIDE);
-      Wp[0] = make_double2(wxz[0], wxz[1]);
-      Wp[1] = make_double2(wxz[2], wxz[3]);
-      Wp[2] = make_double2(wxz[4], wxz[5]);
-      Wp[3] = make_double2(wxz[6], wxz[7]);
-      Wp[4] = make_double2(wxz[8], __longlong_as_double((long long)key));
-      double2* Qp = reinterpret_cast<double2*>(Q);
-#pragma unroll
-      for (int qq = 0; qq < 4; qq++) Qp[qq * 32 + lane] = make_double2(qvy[2 * qq], qvy[2 * qq + 1]);
-    }
-    __syncwarp();
-    // ---- phase B
-#pragma unroll 1
-    for (int sub = 0; sub < 4; sub++) {
-      const int p = sub * 8 + pl;
-      const double2* Wp = reinterpret_cast<const double2*>(W + p * PR_W_STRIDE);
-      const double2 w01 = Wp[0], w23 = Wp[1], w45 = Wp[2], w67 = Wp[3], w8k = Wp[4];
-      const double2 qv = reinterpret_cast<const double2*>(Q)[q * 32 + p];
-      const int key = (int)__double_as_longlong(w8k.y);
-      const bool valid = key >= 0;
-      const double wxz[9] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w8k.x};
-      unsigned remaining = __ballot_sync(0xffffffffu, valid);
-      while (remaining) {
-        const int leader = __ffs(remaining) - 1;
-        const int kk = __shfl_sync(0xffffffffu, key, leader);
-        const unsigned grp = __ballot_sync(0xffffffffu, valid && key == kk) & remaining;
-        const bool member = (grp >> lane) & 1u;
-        const bool accumulate = (kk == cur) || (__popc(grp) >= group_min) || (grp >> 31);
-        if (accumulate) {
-          if (kk != cur) {
-            if (cur >= 0) flush_quad(acc, cur, g, M4);
-#pragma unroll
-            for (int n = 0; n < 18; n++) acc[n] = 0.0;
-            cur = kk;
-          }
-          if (member) {
-#pragma unroll
-            for (int r = 0; r < 9; r++) {
-              acc[r] = fma(qv.x, wxz[r], acc[r]);
-              acc[9 + r] = fma(qv.y, wxz[r], acc[9 + r]);
-            }
-          }
-        } else if (member) {
-#pragma unroll
-          for (int r = 0; r < 9; r++) {
-            atomicAdd(mom_addr(M4, g, key, 2 * q, r), qv.x * wxz[r]);
-            atomicAdd(mom_addr(M4, g, key, 2 * q + 1, r), qv.y * wxz[r]);
-          }
-        }
-        remaining &= ~grp;
-      }
-    }
-    __syncwarp();
-  }
-  if (cur >= 0) flush_quad(acc, cur, g, M4);
-  block_wk_store(wx, wh, wk_partial);
-}
-
-// ---------------------------------------------------------------------------
 // vmesh3 / vmesh1 (F:3243-3305, 3327-3377) as one gather per output element,
 // fused with the AoS -> reference-layout unpack.  x and z steps ASSIGN, the y
 // step ADDS (kept bug-compatible; needs mx,mz >= 4).  fold=0 only unpacks.

@@ -1,0 +1,462 @@
+// mrg_tile.cuh -- the fast particle passes.
+//
+//   k_predict_run   cell-run deposition with warp-level pre-reduction; fields
+//                   gathered through L1 (works for ANY particle order).
+//   k_predict_tile  same deposition, but a CTA owns a pencil of TILE_CELLS
+//                   cells along x: the 6 stencil rows of the six prepared
+//                   fields are staged in shared memory with 1-D bulk TMA
+//                   (cp.async.bulk + mbarrier), moments are accumulated in a
+//                   shared-memory tile and flushed once per CTA with
+//                   red.global.add.f64.
+//   k_correct_tile  corrector with the same TMA-staged gather; optionally
+//                   emits next step's sort keys + cell histogram.
+//
+// The tiled kernels need the cell index built by mrg_sort (cell_end[]); a
+// particle whose stencil is not inside its CTA's tile takes the L1 / global
+// atomic path, so results never depend on how well the order fits.
+// F:n = /root/reference/@mrg37-080A.f03 line n.
+#pragma once
+#include "mrg_kernels.cuh"
+
+namespace mrg {
+
+// ---------------------------------------------------------------------------
+// Deposit target: global moment array M4[node][4], optionally fronted by a
+// shared-memory accumulator tile sM[row = kz*2+jy][node][4] that covers the
+// stencils of cells (i0 .. i0+ncell-1, j, k); key = stencil base node n0.
+// ---------------------------------------------------------------------------
+constexpr int TILE_CELLS = 32;
+constexpr int TILE_NODES = TILE_CELLS + 2;
+constexpr int TILE_ROW_D = TILE_NODES * 6;   // doubles per staged field row
+constexpr int TILE_ACC_D = TILE_NODES * 4;   // doubles per accumulator row
+
+template <bool TILED>
+struct Target {
+  const GP& g;
+  double* __restrict__ M4;
+  double* sM;
+  int n0_first, ncell;
+  __device__ __forceinline__ void add(int key, int g9, int r, double v) const {
+    if (TILED) {
+      const unsigned d = (unsigned)(key - n0_first);
+      if (d < (unsigned)ncell) {
+        const int jy = g9 >> 2, m = g9 & 3, kz = r / 3, ix = r - 3 * kz;
+        atomicAdd(sM + ((kz * 2 + jy) * TILE_NODES + (int)d + ix) * 4 + m, v);
+        return;
+      }
+    }
+    atomicAdd(mom_addr(M4, g, key, g9, r), v);
+  }
+};
+
+constexpr int PR_WARPS = 4;        // warps per block
+constexpr int PR_W_STRIDE = 10;    // doubles per particle in the W slab: wxz[9] + key
+
+// Sum the quad-distributed accumulators over the warp (one transposing and
+// two plain shuffle rounds) and add the 72 totals of cell `n0` to the target.
+template <bool TILED>
+__device__ __forceinline__ void flush_quad(double* acc, int n0, const Target<TILED>& tg) {
+  const int lane = threadIdx.x & 31;
+  const bool hi = (lane & 16) != 0;
+  tr_round<18>(acc, hi, 16);       // acc[0..8]: row g9 = 2q + hi
+#pragma unroll
+  for (int r = 0; r < 9; r++) {
+    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 8);
+    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 4);
+  }
+  const int g9 = 2 * (lane & 3) + (hi ? 1 : 0);
+  const int u = (lane >> 2) & 3;   // the 4 lanes holding the same sums share the 9 atomics
+  const double v0 = sel(u == 0, acc[0], sel(u == 1, acc[1], sel(u == 2, acc[2], acc[3])));
+  const double v1 = sel(u == 0, acc[4], sel(u == 1, acc[5], sel(u == 2, acc[6], acc[7])));
+  tg.add(n0, g9, u, v0);
+  tg.add(n0, g9, u + 4, v1);
+  if (u == 0) tg.add(n0, g9, 8, acc[8]);
+}
+
+// phase A tail: park the 17 scatter factors + key of this lane's particle
+__device__ __forceinline__ void park_factors(double* W, double* Q, int lane, const double qvy[8], const double wxz[9], int key) {
+  double2* Wp = reinterpret_cast<double2*>(W + lane * PR_W_STRIDE);
+  Wp[0] = make_double2(wxz[0], wxz[1]);
+  Wp[1] = make_double2(wxz[2], wxz[3]);
+  Wp[2] = make_double2(wxz[4], wxz[5]);
+  Wp[3] = make_double2(wxz[6], wxz[7]);
+  Wp[4] = make_double2(wxz[8], __longlong_as_double((long long)key));
+  double2* Qp = reinterpret_cast<double2*>(Q);
+#pragma unroll
+  for (int qq = 0; qq < 4; qq++) Qp[qq * 32 + lane] = make_double2(qvy[2 * qq], qvy[2 * qq + 1]);
+}
+
+// phase B: four sub-iterations of 8 particles; a QUAD of lanes serves one
+// particle, lane q owning value rows g9 = 2q, 2q+1.  Lanes are grouped by key;
+// a group that continues the warp's current cell, is large, or reaches the
+// last lane is summed in registers across (sub-)iterations, other groups go
+// straight to the target.
+template <bool TILED>
+__device__ __forceinline__ void deposit_parked(const double* W, const double* Q, int lane, double* acc, int& cur,
+                                               int group_min, const Target<TILED>& tg) {
+  const int q = lane & 3, pl = lane >> 2;
+#pragma unroll 1
+  for (int sub = 0; sub < 4; sub++) {
+    const int p = sub * 8 + pl;
+    const double2* Wp = reinterpret_cast<const double2*>(W + p * PR_W_STRIDE);
+    const double2 w01 = Wp[0], w23 = Wp[1], w45 = Wp[2], w67 = Wp[3], w8k = Wp[4];
+    const double2 qv = reinterpret_cast<const double2*>(Q)[q * 32 + p];
+    const int key = (int)__double_as_longlong(w8k.y);
+    const bool valid = key >= 0;
+    const double wxz[9] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w8k.x};
+    unsigned remaining = __ballot_sync(0xffffffffu, valid);
+    while (remaining) {
+      const int leader = __ffs(remaining) - 1;
+      const int kk = __shfl_sync(0xffffffffu, key, leader);
+      const unsigned grp = __ballot_sync(0xffffffffu, valid && key == kk) & remaining;
+      const bool member = (grp >> lane) & 1u;
+      const bool accumulate = (kk == cur) || (__popc(grp) >= group_min) || (grp >> 31);
+      if (accumulate) {
+        if (kk != cur) {
+          if (cur >= 0) flush_quad<TILED>(acc, cur, tg);
+#pragma unroll
+          for (int n = 0; n < 18; n++) acc[n] = 0.0;
+          cur = kk;
+        }
+        if (member) {
+#pragma unroll
+          for (int r = 0; r < 9; r++) {
+            acc[r] = fma(qv.x, wxz[r], acc[r]);
+            acc[9 + r] = fma(qv.y, wxz[r], acc[9 + r]);
+          }
+        }
+      } else if (member) {
+#pragma unroll
+        for (int r = 0; r < 9; r++) {
+          tg.add(key, 2 * q, r, qv.x * wxz[r]);
+          tg.add(key, 2 * q + 1, r, qv.y * wxz[r]);
+        }
+      }
+      remaining &= ~grp;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Predictor, any particle order (fields through L1): a warp owns 32*ITERS
+// consecutive particles.  F:1162-1283, 1300-1306, 1375, srimp1+srimp2 scatter.
+// ---------------------------------------------------------------------------
+template <int ITERS>
+__global__ void __launch_bounds__(PR_WARPS * 32)
+k_predict_run(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
+              double* __restrict__ wk_partial, int group_min) {
+  __shared__ __align__(16) double smW[PR_WARPS][32 * PR_W_STRIDE];
+  __shared__ __align__(16) double smQ[PR_WARPS][4 * 32 * 2];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  double* W = smW[w];
+  double* Q = smQ[w];
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long base = warp * (32LL * ITERS);
+  const Target<false> tg{g, M4, nullptr, 0, 0};
+  double wx = 0.0, wh = 0.0;
+  double acc[18];
+#pragma unroll
+  for (int n = 0; n < 18; n++) acc[n] = 0.0;
+  int cur = -1;
+#pragma unroll 1
+  for (int it = 0; it < ITERS; it++) {
+    const long long t = base + 32LL * it + lane;
+    if (base + 32LL * it >= P.n) break;                     // warp-uniform
+    {
+      double qvy[8], wxz[9];
+      int key = -1;
+      if (t < P.n) {
+        const Predicted o = predict_one(g, pp, P, t, F6, wx, wh);
+        key = scatter_factors(g, pp.qmult, o, qvy, wxz);
+      } else {
+#pragma unroll
+        for (int n = 0; n < 8; n++) qvy[n] = 0.0;
+#pragma unroll
+        for (int n = 0; n < 9; n++) wxz[n] = 0.0;
+      }
+      park_factors(W, Q, lane, qvy, wxz, key);
+    }
+    __syncwarp();
+    deposit_parked<false>(W, Q, lane, acc, cur, group_min, tg);
+    __syncwarp();
+  }
+  if (cur >= 0) flush_quad<false>(acc, cur, tg);
+  block_wk_store(wx, wh, wk_partial);
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier + 1-D bulk TMA (global -> shared), sm_90+ PTX.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+  unsigned ok = 0;
+  for (int spin = 0; spin < (1 << 26); spin++) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();   // a lost TMA completion must not hang the GPU
+}
+
+// ---------------------------------------------------------------------------
+// Tile bookkeeping.  Tile t covers cells (i0 .. i0+ncell-1, j, k) of the sort
+// key space (i fastest, F:1175-1177 indices); its particles are the slots
+// [p0,p1) of the cell index built by the last mrg_sort.
+// ---------------------------------------------------------------------------
+struct Tile {
+  int i0, ncell, j, k;
+  int p0, p1;
+  int n0_first;     // stencil base node of cell (i0,j,k) = node (i0-1, j, k-1)
+};
+__device__ __forceinline__ Tile tile_of(const GP& g, const int* __restrict__ cell_end, int tile) {
+  const int ntx = (g.mx + TILE_CELLS - 1) / TILE_CELLS;
+  Tile t;
+  const int tx = tile % ntx, r = tile / ntx;
+  t.j = r % g.my;
+  t.k = r / g.my;
+  t.i0 = tx * TILE_CELLS;
+  t.ncell = min(TILE_CELLS, g.mx - t.i0);
+  const int c0 = t.i0 + g.mx * (t.j + g.my * t.k);
+  t.p0 = (c0 == 0) ? 0 : cell_end[c0 - 1];
+  t.p1 = cell_end[c0 + t.ncell - 1];
+  t.n0_first = node_of(g, t.i0 - 1, t.j, t.k - 1);
+  return t;
+}
+
+// stage the 6 stencil rows (jy = 0,1; kz = 0,1,2) of the packed fields: each
+// row is contiguous in F6, (ncell+2)*48 bytes, 16-byte aligned
+__device__ __forceinline__ void stage_fields(const GP& g, const Tile& t, const double* __restrict__ F6, double* sF,
+                                             unsigned long long* bar) {
+  if (threadIdx.x == 0) {
+    const unsigned row_bytes = (unsigned)(t.ncell + 2) * 48u;
+    mbar_expect_tx(bar, 6u * row_bytes);
+#pragma unroll
+    for (int kz = 0; kz < 3; kz++)
+#pragma unroll
+      for (int jy = 0; jy < 2; jy++) {
+        const size_t node = (size_t)t.n0_first + (size_t)jy * g.nx + (size_t)kz * g.nxy;
+        bulk_g2s(sF + (kz * 2 + jy) * TILE_ROW_D, F6 + node * 6, row_bytes, bar);
+      }
+  }
+}
+
+// gather of the six fields from the staged tile: same arithmetic as gather6,
+// the 54 loads are warp-broadcast LDS.128 when the lanes share a cell
+__device__ __forceinline__ void gather6_tile(const double* sF, int delta, const Stencil& s, double f[6]) {
+#pragma unroll
+  for (int c = 0; c < 6; c++) f[c] = 0.0;
+#pragma unroll
+  for (int kz = 0; kz < 3; kz++) {
+#pragma unroll
+    for (int jy = 0; jy < 2; jy++) {
+      const double2* r = reinterpret_cast<const double2*>(sF + (kz * 2 + jy) * TILE_ROW_D + delta * 6);
+      const double wyz = s.fy[jy] * s.fz[kz];
+      double2 v[9];
+#pragma unroll
+      for (int q = 0; q < 9; q++) v[q] = r[q];
+#pragma unroll
+      for (int ix = 0; ix < 3; ix++) {
+        const double w = s.fx[ix] * wyz;
+        f[0] = fma(w, v[3 * ix + 0].x, f[0]);
+        f[1] = fma(w, v[3 * ix + 0].y, f[1]);
+        f[2] = fma(w, v[3 * ix + 1].x, f[2]);
+        f[3] = fma(w, v[3 * ix + 1].y, f[3]);
+        f[4] = fma(w, v[3 * ix + 2].x, f[4]);
+        f[5] = fma(w, v[3 * ix + 2].y, f[5]);
+      }
+    }
+  }
+}
+
+// half-step position + gather (tile or L1) + rotation for one particle
+__device__ __forceinline__ Kick gather_rotate(const GP& g, const PushParams& pp, const Tile& t, const double* sF,
+                                              const double* __restrict__ F6, double x, double y, double z, double vx,
+                                              double vy, double vz) {
+  double rx = __dadd_rn(x, __dmul_rn(pp.hdt, vx));          // F:1163-1165
+  double ry = __dadd_rn(y, __dmul_rn(pp.hdt, vy));
+  double rz = __dadd_rn(z, __dmul_rn(pp.hdt, vz));
+  wrap_pos(g, rx, ry, rz);                                    // partbcEST, F:1168
+  Stencil s;
+  make_stencil<true>(g, rx, ry, rz, s);
+  double f[6];
+  const unsigned d = (unsigned)(s.n0 - t.n0_first);
+  if (d < (unsigned)t.ncell) gather6_tile(sF, (int)d, s, f);
+  else gather6(F6, g, s, f);
+  return rotate(f, vx, vy, vz, pp.ht, pp.ht2);
+}
+
+// split [p0,p1) into TILE warps' contiguous sub-ranges (multiples of 32)
+__device__ __forceinline__ void warp_range(const Tile& t, int w, int nwarps, int& a, int& b) {
+  const int len = t.p1 - t.p0;
+  const int chunk = ((len + nwarps * 32 - 1) / (nwarps * 32)) * 32;
+  a = min(t.p0 + w * chunk, t.p1);
+  b = min(a + chunk, t.p1);
+}
+
+// ---------------------------------------------------------------------------
+// Predictor on TMA-staged tiles.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PR_WARPS * 32)
+k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
+               const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min) {
+  __shared__ __align__(128) double sF[6 * TILE_ROW_D];
+  __shared__ __align__(16) double sM[6 * TILE_ACC_D];
+  __shared__ __align__(16) double smW[PR_WARPS][32 * PR_W_STRIDE];
+  __shared__ __align__(16) double smQ[PR_WARPS][4 * 32 * 2];
+  __shared__ __align__(8) unsigned long long bar;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const Tile t = tile_of(g, cell_end, blockIdx.x);
+  const bool busy = t.p1 > t.p0;                              // block-uniform
+  double wx = 0.0, wh = 0.0;
+  if (busy) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    for (int e = threadIdx.x; e < 6 * TILE_ACC_D; e += blockDim.x) sM[e] = 0.0;
+    __syncthreads();
+    stage_fields(g, t, F6, sF, &bar);
+    mbar_wait(&bar, 0);
+    double* W = smW[w];
+    double* Q = smQ[w];
+    const Target<true> tg{g, M4, sM, t.n0_first, t.ncell};
+    double acc[18];
+#pragma unroll
+    for (int n = 0; n < 18; n++) acc[n] = 0.0;
+    int cur = -1;
+    int a, b;
+    warp_range(t, w, PR_WARPS, a, b);
+    const double ah = pp.aimpl * pp.hh, hh2 = 0.5 * pp.hh;
+#pragma unroll 1
+    for (int t0 = a; t0 < b; t0 += 32) {
+      const int p = t0 + lane;
+      {
+        double qvy[8], wxz[9];
+        int key = -1;
+        if (p < b) {
+          const double x = __ldcs(P.x + p), y = __ldcs(P.y + p), z = __ldcs(P.z + p);
+          const double vx = __ldcs(P.vx + p), vy = __ldcs(P.vy + p), vz = __ldcs(P.vz + p);
+          const Kick k = gather_rotate(g, pp, t, sF, F6, x, y, z, vx, vy, vz);
+          wx += k.wx; wh += k.wh;
+          Predicted o;
+          o.vxj = fma(ah, k.dvx, vx);                         // F:1300-1302
+          o.vyj = fma(ah, k.dvy, vy);
+          o.vzj = fma(ah, k.dvz, vz);
+          o.rx = fma(pp.adt, fma(hh2, k.dvx, vx), x);         // F:1304-1306
+          o.ry = fma(pp.adt, fma(hh2, k.dvy, vy), y);
+          o.rz = fma(pp.adt, fma(hh2, k.dvz, vz), z);
+          if (wrap_pos(g, o.rx, o.ry, o.rz)) o.vyj = -o.vyj;  // partbc, F:1375
+          key = scatter_factors(g, pp.qmult, o, qvy, wxz);
+        } else {
+#pragma unroll
+          for (int n = 0; n < 8; n++) qvy[n] = 0.0;
+#pragma unroll
+          for (int n = 0; n < 9; n++) wxz[n] = 0.0;
+        }
+        park_factors(W, Q, lane, qvy, wxz, key);
+      }
+      __syncwarp();
+      deposit_parked<true>(W, Q, lane, acc, cur, group_min, tg);
+      __syncwarp();
+    }
+    if (cur >= 0) flush_quad<true>(acc, cur, tg);
+    __syncthreads();
+    // flush the accumulator tile: 4 moments of a node = one 32-byte sector
+    const int nodes = t.ncell + 2;
+    for (int e = threadIdx.x; e < 6 * nodes * 4; e += blockDim.x) {
+      const int row = e / (nodes * 4), rem = e - row * (nodes * 4);
+      const double v = sM[row * TILE_ACC_D + rem];
+      if (v != 0.0) {
+        const int kz = row >> 1, jy = row & 1;
+        atomicAdd(M4 + 4 * ((size_t)t.n0_first + (size_t)jy * g.nx + (size_t)kz * g.nxy) + rem, v);
+      }
+    }
+  }
+  block_wk_store(wx, wh, wk_partial);
+}
+
+// ---------------------------------------------------------------------------
+// Corrector on TMA-staged tiles: F:1162-1295, partbc F:1337, slab test of the
+// drive kick F:1343-1345.  With key_out != nullptr it also writes the cell of
+// wrap(x' + lookahead*v') (next step's sort key) and the cell histogram, which
+// lets mrg_sort skip its key pass.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(PR_WARPS * 32)
+k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, const int* __restrict__ cell_end,
+               double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits, int* __restrict__ slab_list,
+               int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead) {
+  __shared__ __align__(128) double sF[6 * TILE_ROW_D];
+  __shared__ __align__(8) unsigned long long bar;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const Tile t = tile_of(g, cell_end, blockIdx.x);
+  const bool busy = t.p1 > t.p0;
+  double wx = 0.0, wh = 0.0;
+  if (busy) {
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    stage_fields(g, t, F6, sF, &bar);
+    mbar_wait(&bar, 0);
+    int a, b;
+    warp_range(t, w, PR_WARPS, a, b);
+    const double hh2 = 0.5 * pp.hh;
+#pragma unroll 1
+    for (int t0 = a; t0 < b; t0 += 32) {
+      const int p = t0 + lane;
+      const bool valid = p < b;
+      int kcell = -1;
+      if (valid) {
+        double x = __ldcs(P.x + p), y = __ldcs(P.y + p), z = __ldcs(P.z + p);
+        double vx = __ldcs(P.vx + p), vy = __ldcs(P.vy + p), vz = __ldcs(P.vz + p);
+        const Kick k = gather_rotate(g, pp, t, sF, F6, x, y, z, vx, vy, vz);
+        wx += k.wx; wh += k.wh;
+        x = fma(pp.dt, fma(hh2, k.dvx, vx), x);               // F:1289-1291
+        y = fma(pp.dt, fma(hh2, k.dvy, vy), y);
+        z = fma(pp.dt, fma(hh2, k.dvz, vz), z);
+        vx = fma(pp.hh, k.dvx, vx);                           // F:1293-1295
+        vy = fma(pp.hh, k.dvy, vy);
+        vz = fma(pp.hh, k.dvz, vz);
+        if (wrap_pos(g, x, y, z)) vy = -vy;                   // partbc, F:1337
+        __stcs(P.x + p, x); __stcs(P.y + p, y); __stcs(P.z + p, z);
+        __stcs(P.vx + p, vx); __stcs(P.vy + p, vy); __stcs(P.vz + p, vz);
+        if (pp.drive_on) {
+          if ((fabs(z - pp.zcent) < pp.zw) && ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw))) {
+            const int id = P.id ? P.id[p] : p;
+            atomicOr(slab_bits + (id >> 5), 1u << (id & 31));
+            slab_list[atomicAdd(slab_count, 1)] = p;
+          }
+        }
+        if (key_out) {
+          double sx = fma(lookahead, vx, x), sy = fma(lookahead, vy, y), sz = fma(lookahead, vz, z);
+          wrap_pos(g, sx, sy, sz);
+          int ip, jp, kp;
+          cell_of(g, sx, sy, sz, ip, jp, kp);
+          ip = min(ip, g.mx - 1); jp = min(jp, g.my - 1); kp = min(kp, g.mz - 1);
+          kcell = ip + g.mx * (jp + g.my * kp);
+          key_out[p] = kcell;
+        }
+      }
+      if (key_out) {
+        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+          const unsigned m = __match_any_sync(act, kcell);
+          if (lane == __ffs(m) - 1) atomicAdd(hist + kcell, __popc(m));
+        }
+      }
+    }
+  }
+  block_wk_store(wx, wh, wk_partial);
+}
+
+}  // namespace mrg

@@ -248,7 +248,7 @@ class Fulmov:
         else:
             self.ncorr[ksp] += 1
             if self.sort_interval and self.ncorr[ksp] % self.sort_interval == 0:
-                self.ctx.sort(ksp, c.adt)
+                self.ctx.sort(ksp, c.hdt)     # key = cell of the next gather position x + hdt*v
 
     def pull(self, ksp, x, y, z, vx, vy, vz, npr):
         self.ctx.download(ksp, npr, self.ipar, self.size, out=[x, y, z, vx, vy, vz])

@@ -63,18 +63,19 @@ def test_prepared_fields_bit_exact(mrg, case, ifil):
 
 # ---- C1: corrector ------------------------------------------------------------
 @pytest.mark.parametrize("ksp", [1, 2])
-@pytest.mark.parametrize("sort", [False, True])
-def test_corrector_particles(mrg, case, ksp, sort):
+@pytest.mark.parametrize("sort,tile", [(False, 1), (True, 1), (True, 0)])
+def test_corrector_particles(mrg, case, ksp, sort, tile):
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
     ref = [a.copy() for a in sp[ksp]]
     st = np.array([ranfb], dtype=np.int32)
     r = O.fulmov(p, a6, *ref, q, w, 0, nranks=1, ranfb=st)
     ctx = new_ctx(mrg, p)
+    ctx.set_option("tile", tile)
     ctx.set_fields(f12)
     ctx.upload(ksp, *sp[ksp])
     if sort:
-        ctx.sort(ksp, p.adt)
+        ctx.sort(ksp, p.hdt)
     wkix, wkih, st_gpu = ctx.fulmov(ksp, q, w, 0, params_of(mrg, p), ranfb)
     got = ctx.download(ksp, len(ref[0]))
     assert U.particle_err(got, ref, p.hx, U.vth(ksp)) < PTOL
@@ -86,9 +87,13 @@ def test_corrector_particles(mrg, case, ksp, sort):
 
 # ---- C2: predictor + deposit, every deposit mode, sorted and unsorted -----------
 @pytest.mark.parametrize("ksp", [1, 2])
-@pytest.mark.parametrize("deposit,iters,sort", [(0, 8, False), (1, 8, False), (1, 8, True), (2, 4, True),
-                                                (2, 8, True), (2, 8, False), (2, 32, True)])
-def test_predictor_moments(mrg, case, ksp, deposit, iters, sort):
+@pytest.mark.parametrize("deposit,iters,sort,tile", [(0, 8, False, 0), (1, 8, False, 0), (1, 8, True, 0), (2, 4, True, 0),
+                                                     (2, 8, True, 0), (2, 8, False, 0), (2, 32, True, 0),
+                                                     (2, 8, True, 1), (2, 8, "adt", 1), (2, 8, "stale", 1)])
+def test_predictor_moments(mrg, case, ksp, deposit, iters, sort, tile):
+    """sort: False = load order; True = sorted by the gather cell (x + hdt*v); "adt" = sorted by another
+    key (many particles gather outside their tile); "stale" = sorted, then moved by a corrector step
+    without re-sorting.  tile=1 runs the TMA-staged shared-memory kernels."""
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
     orig = [a.copy() for a in sp[ksp]]
@@ -96,10 +101,19 @@ def test_predictor_moments(mrg, case, ksp, deposit, iters, sort):
     ctx = new_ctx(mrg, p)
     ctx.set_option("deposit", deposit)
     ctx.set_option("iters", iters)
+    ctx.set_option("tile", tile)
     ctx.set_fields(f12)
-    ctx.upload(ksp, *orig)
-    if sort:
-        ctx.sort(ksp, p.adt)
+    if sort == "stale":
+        # a sort index that no longer matches the positions: sort, push one step, restore order-independent truth
+        ctx.upload(ksp, *orig)
+        ctx.sort(ksp, p.hdt)
+        ctx.fulmov(ksp, q, w, 0, params_of(mrg, p, drive_on=False))
+        orig = ctx.download(ksp, len(orig[0]))
+        r = O.fulmov(p, a6, *[a.copy() for a in orig], q, w, 1, nranks=1, want_raw=True)
+    else:
+        ctx.upload(ksp, *orig)
+        if sort:
+            ctx.sort(ksp, p.adt * 3 if sort == "adt" else p.hdt)
     wkix, wkih, _ = ctx.fulmov(ksp, q, w, 1, params_of(mrg, p))
     raw = ctx.moments(ksp, folded=False)
     mom = ctx.moments(ksp, folded=True)
@@ -144,7 +158,7 @@ def test_step_sequence(mrg, case):
             else:
                 assert st_gpu == int(st[0])
                 if sort_after:
-                    ctx.sort(k, pp.adt)
+                    ctx.sort(k, pp.hdt)                  # uses the keys the tiled corrector emitted
 
     # it = 0: dt = adt = hdt = 0, moments only
     p0 = U.make_parm(p.mx, p.my, p.mz, dt=0.0)
