@@ -35,23 +35,26 @@ def _stale(target, sources):
 
 
 def cuda_sources():
-    srcs = [os.path.join(CSRC, f) for f in ("mrg_api.cu", "mrg_kernels.cuh", "mrg_device.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("mrg_api.cu", "mrg_kernels.cuh", "mrg_tile.cuh", "mrg_device.cuh")]
     srcs.append(os.path.join(ROOT, "include", "mrg_fulmov.h"))
     return srcs
 
 
-def build_cuda(force=False, verbose=False):
+def build_cuda(force=False, verbose=False, out=None, defines=()):
+    """out/defines build an experimental variant next to the product library
+    (tools/ only; select it at run time with MRG_LIB=<path>)."""
     srcs = cuda_sources()
-    if not force and not _stale(LIB, srcs):
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [
-        "-o", LIB, os.path.join(CSRC, "mrg_api.cu"), "-ldl"]
+    target = out or LIB
+    if not force and not _stale(target, srcs):
+        return target
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + [
+        "-o", target, os.path.join(CSRC, "mrg_api.cu"), "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
-    return LIB
+    return target
 
 
 def build_host(force=False):

@@ -52,15 +52,16 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    if build_if_missing:
+    path = os.environ.get("MRG_LIB") or _build.LIB      # MRG_LIB: an experimental build of the same sources (tools/)
+    if build_if_missing and path == _build.LIB:
         try:
             _build.build_cuda()
         except Exception:
             if not os.path.exists(_build.LIB):
                 raise
-    if not os.path.exists(_build.LIB):
-        raise MrgError("libmrg_fulmov.so is missing: run __graft_entry__.build() (no CPU fallback exists)")
-    L = C.CDLL(_build.LIB)
+    if not os.path.exists(path):
+        raise MrgError("%s is missing: run __graft_entry__.build() (no CPU fallback exists)" % path)
+    L = C.CDLL(path)
     vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
     L.mrg_last_error.restype = C.c_char_p
     L.mrg_build_info.restype = C.c_char_p

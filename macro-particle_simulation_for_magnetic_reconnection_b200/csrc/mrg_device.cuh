@@ -44,14 +44,24 @@ __device__ __forceinline__ int floor_pos(double s, double& as_double) {
 
 // partbc (F:1856-1879) / partbcEST (F:1928-1949): applied once, no loop.
 // Returns true when the y wall reflected the particle (partbc then flips vy).
+// The six comparisons are done on the IEEE bit patterns with integer
+// instructions (the fp64 pipe is the bottleneck of the particle passes): for
+// non-NaN x, `x >= a` with a > 0 is a signed compare of the patterns, `x <= b`
+// with b < 0 an unsigned one, `y <= 0` is "pattern <= 0" (covers -0.0).  The
+// decisions are identical to the floating-point compares of the source.
+__device__ __forceinline__ bool ge_pos(double x, double a) { return __double_as_longlong(x) >= __double_as_longlong(a); }
+__device__ __forceinline__ bool le_neg(double x, double b) {
+  return (unsigned long long)__double_as_longlong(x) >= (unsigned long long)__double_as_longlong(b);
+}
 __device__ __forceinline__ bool wrap_pos(const GP& g, double& x, double& y, double& z) {
-  if (x >= g.xhi) x = __dsub_rn(x, g.xmaxe);
-  else if (x <= g.xlo) x = __dadd_rn(x, g.xmaxe);
-  bool flip = false;
-  if (y >= g.ymax) { y = __dsub_rn(g.ymax2, y); flip = true; }
-  else if (y <= 0.0) { y = -y; flip = true; }
-  if (z >= g.zhi) z = __dsub_rn(z, g.zmaxe);
-  else if (z <= g.zlo) z = __dadd_rn(z, g.zmaxe);
+  const bool xge = ge_pos(x, g.xhi), xle = le_neg(x, g.xlo);
+  x = __dadd_rn(x, xge ? -g.xmaxe : (xle ? g.xmaxe : 0.0));      // x - xmaxe | x + xmaxe | x
+  const bool yge = ge_pos(y, g.ymax), yle = __double_as_longlong(y) <= 0ll;
+  const bool flip = yge || yle;
+  const double yr = __dsub_rn(yge ? g.ymax2 : 0.0, y);            // 2*ymax - y | -y
+  y = flip ? yr : y;
+  const bool zge = ge_pos(z, g.zhi), zle = le_neg(z, g.zlo);
+  z = __dadd_rn(z, zge ? -g.zmaxe : (zle ? g.zmaxe : 0.0));
   return flip;
 }
 
@@ -105,6 +115,20 @@ __device__ __forceinline__ void cell_of(const GP& g, double x, double y, double 
   ip = min(max(ip, 0), g.mx);
   jp = min(max(jp, 0), g.my);
   kp = min(max(kp, 0), g.mz);
+}
+
+// Sort key: linear cell index (i fastest) of an already wrapped position.  A
+// sorting hint only -- every result is independent of the particle order -- so
+// it may contract to FMA (it can differ from the exact F:1175-1177 index only
+// for positions within an ulp of a cell boundary).
+__device__ __forceinline__ int sort_cell(const GP& g, double x, double y, double z) {
+  int ip = __double2loint(__dadd_rd(fma(g.hxi, x, 0.500000001), MRG_TWO52));
+  int jp = __double2loint(__dadd_rd(fma(g.hyi, y, 0.000000001), MRG_TWO52));
+  int kp = __double2loint(__dadd_rd(fma(g.hzi, z, 0.500000001), MRG_TWO52));
+  ip = min(max(ip, 0), g.mx - 1);
+  jp = min(max(jp, 0), g.my - 1);
+  kp = min(max(kp, 0), g.mz - 1);
+  return ip + g.mx * (jp + g.my * kp);
 }
 
 // Gather of the six prepared fields (F:1217-1270) from the packed array

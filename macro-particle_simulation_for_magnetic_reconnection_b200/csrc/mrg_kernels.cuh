@@ -460,10 +460,7 @@ __global__ void k_sort_keys(GP g, ParticleSoA P, double lookahead, int* __restri
     double y = fma(lookahead, P.vy[t], P.y[t]);
     double z = fma(lookahead, P.vz[t], P.z[t]);
     wrap_pos(g, x, y, z);
-    int ip, jp, kp;
-    cell_of(g, x, y, z, ip, jp, kp);
-    ip = min(ip, g.mx - 1); jp = min(jp, g.my - 1); kp = min(kp, g.mz - 1);
-    kcell = ip + g.mx * (jp + g.my * kp);
+    kcell = sort_cell(g, x, y, z);
     key[t] = kcell;
   }
   // warp-aggregated histogram increment

@@ -11,31 +11,65 @@
 //   k_correct_tile  corrector with the same TMA-staged gather; optionally
 //                   emits next step's sort keys + cell histogram.
 //
-// The tiled kernels need the cell index built by mrg_sort (cell_end[]); a
-// particle whose stencil is not inside its CTA's tile takes the L1 / global
-// atomic path, so results never depend on how well the order fits.
-// F:n = /root/reference/@mrg37-080A.f03 line n.
+// Both tiled kernels stream a warp's contiguous slice of the tile's particles
+// with the NEXT 32 particles prefetched into registers while the current 32
+// are pushed (the passes are fp64-issue bound; the HBM latency must not be
+// exposed).  The tiled kernels need the cell index built by mrg_sort
+// (cell_end[]); a particle whose stencil is not inside its CTA's tile takes
+// the L1 / global atomic path, so results never depend on how well the order
+// fits.  F:n = /root/reference/@mrg37-080A.f03 line n.
 #pragma once
 #include "mrg_kernels.cuh"
 
 namespace mrg {
 
-// ---------------------------------------------------------------------------
-// Deposit target: global moment array M4[node][4], optionally fronted by a
-// shared-memory accumulator tile sM[row = kz*2+jy][node][4] that covers the
-// stencils of cells (i0 .. i0+ncell-1, j, k); key = stencil base node n0.
-// ---------------------------------------------------------------------------
 constexpr int TILE_CELLS = 32;
 constexpr int TILE_NODES = TILE_CELLS + 2;
 constexpr int TILE_ROW_D = TILE_NODES * 6;   // doubles per staged field row
 constexpr int TILE_ACC_D = TILE_NODES * 4;   // doubles per accumulator row
+constexpr unsigned FULL = 0xffffffffu;
+// resident CTAs per SM the tiled kernels are compiled for (register budget)
+#ifndef MRG_PRED_MINB
+#define MRG_PRED_MINB 4
+#endif
+#ifndef MRG_CORR_MINB
+#define MRG_CORR_MINB 5
+#endif
 
+// ---------------------------------------------------------------------------
+// Deposit target: global moment array M4[node][4], optionally fronted by a
+// shared-memory accumulator tile sM[row = kz*2+jy][node][4] that covers the
+// stencils of cells (i0 .. i0+ncell-1, j, k); key = stencil base node n0.
+//
+// Lane roles in the pre-reduction (phase B): a QUAD of lanes serves one
+// particle; lane q = lane&3 owns the value rows g9 = 2q, 2q+1 (g9 = jy*4 + m).
+// After the cross-quad reduction of flush_quad a lane holds three totals of
+// row g9 = 2q + hi (hi = lane bit 4): r = r0, r0+1 (r0 = 4*bit3 + 2*bit2) and
+// r = 8; the addresses of those three, relative to the cell, are lane
+// constants kept in the target.
+// ---------------------------------------------------------------------------
 template <bool TILED>
 struct Target {
   const GP& g;
   double* __restrict__ M4;
   double* sM;
   int n0_first, ncell;
+  int so[3];      // shared-memory offsets (doubles) of the lane's three flush values, relative to sM + 4*d
+  int go[3];      // global offsets (doubles) relative to M4 + 4*n0
+  __device__ __forceinline__ Target(const GP& g_, double* M4_, double* sM_, int n0f, int nc, int lane)
+      : g(g_), M4(M4_), sM(sM_), n0_first(n0f), ncell(nc) {
+    const int g9 = 2 * (lane & 3) + ((lane >> 4) & 1);
+    const int jy = g9 >> 2, m = g9 & 3;
+    const int r0 = ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int r = (k == 2) ? 8 : r0 + k;
+      const int kz = r / 3, ix = r - 3 * kz;
+      so[k] = ((kz * 2 + jy) * TILE_NODES + ix) * 4 + m;
+      go[k] = 4 * (ix + jy * g.nx + kz * g.nxy) + m;
+    }
+  }
+  // general (g9, r) element of the cell whose stencil base node is `key`
   __device__ __forceinline__ void add(int key, int g9, int r, double v) const {
     if (TILED) {
       const unsigned d = (unsigned)(key - n0_first);
@@ -47,30 +81,37 @@ struct Target {
     }
     atomicAdd(mom_addr(M4, g, key, g9, r), v);
   }
+  // the lane's k-th flush value of cell `key`
+  __device__ __forceinline__ void add_flush(int key, int k, double v) const {
+    if (TILED) {
+      const unsigned d = (unsigned)(key - n0_first);
+      if (d < (unsigned)ncell) {
+        atomicAdd(sM + 4 * (int)d + so[k], v);
+        return;
+      }
+    }
+    atomicAdd(M4 + 4 * (size_t)key + go[k], v);
+  }
 };
 
 constexpr int PR_WARPS = 4;        // warps per block
 constexpr int PR_W_STRIDE = 10;    // doubles per particle in the W slab: wxz[9] + key
 
-// Sum the quad-distributed accumulators over the warp (one transposing and
-// two plain shuffle rounds) and add the 72 totals of cell `n0` to the target.
+// Sum the quad-distributed accumulators over the warp with a transposing
+// butterfly (18 -> 9 -> 4+1 -> 2+1 values per lane) and add the 72 totals of
+// cell `n0` to the target.
 template <bool TILED>
 __device__ __forceinline__ void flush_quad(double* acc, int n0, const Target<TILED>& tg) {
   const int lane = threadIdx.x & 31;
-  const bool hi = (lane & 16) != 0;
-  tr_round<18>(acc, hi, 16);       // acc[0..8]: row g9 = 2q + hi
-#pragma unroll
-  for (int r = 0; r < 9; r++) {
-    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 8);
-    acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], 4);
-  }
-  const int g9 = 2 * (lane & 3) + (hi ? 1 : 0);
-  const int u = (lane >> 2) & 3;   // the 4 lanes holding the same sums share the 9 atomics
-  const double v0 = sel(u == 0, acc[0], sel(u == 1, acc[1], sel(u == 2, acc[2], acc[3])));
-  const double v1 = sel(u == 0, acc[4], sel(u == 1, acc[5], sel(u == 2, acc[6], acc[7])));
-  tg.add(n0, g9, u, v0);
-  tg.add(n0, g9, u + 4, v1);
-  if (u == 0) tg.add(n0, g9, 8, acc[8]);
+  tr_round<18>(acc, (lane & 16) != 0, 16);     // acc[0..8]: row g9 = 2q + hi, r = 0..8
+  double a8 = acc[8];
+  a8 += __shfl_xor_sync(FULL, a8, 8);
+  a8 += __shfl_xor_sync(FULL, a8, 4);
+  tr_round<8>(acc, (lane & 8) != 0, 8);        // acc[0..3]: r = 4*bit3 + 0..3
+  tr_round<4>(acc, (lane & 4) != 0, 4);        // acc[0..1]: r = 4*bit3 + 2*bit2 + 0..1
+  tg.add_flush(n0, 0, acc[0]);
+  tg.add_flush(n0, 1, acc[1]);
+  if ((lane & 12) == 0) tg.add_flush(n0, 2, a8);
 }
 
 // phase A tail: park the 17 scatter factors + key of this lane's particle
@@ -87,10 +128,12 @@ __device__ __forceinline__ void park_factors(double* W, double* Q, int lane, con
 }
 
 // phase B: four sub-iterations of 8 particles; a QUAD of lanes serves one
-// particle, lane q owning value rows g9 = 2q, 2q+1.  Lanes are grouped by key;
-// a group that continues the warp's current cell, is large, or reaches the
-// last lane is summed in registers across (sub-)iterations, other groups go
-// straight to the target.
+// particle, lane q owning value rows g9 = 2q, 2q+1.  Fast path: all eight
+// particles continue the warp's current cell (key < 0 marks an empty slot
+// whose factors are zero) -> 18 FMAs per lane.  Otherwise lanes are grouped by
+// key; a group that continues the current cell, is large, or reaches the last
+// lane is summed in registers across (sub-)iterations, other groups (strays)
+// go straight to the target.
 template <bool TILED>
 __device__ __forceinline__ void deposit_parked(const double* W, const double* Q, int lane, double* acc, int& cur,
                                                int group_min, const Target<TILED>& tg) {
@@ -102,13 +145,21 @@ __device__ __forceinline__ void deposit_parked(const double* W, const double* Q,
     const double2 w01 = Wp[0], w23 = Wp[1], w45 = Wp[2], w67 = Wp[3], w8k = Wp[4];
     const double2 qv = reinterpret_cast<const double2*>(Q)[q * 32 + p];
     const int key = (int)__double_as_longlong(w8k.y);
-    const bool valid = key >= 0;
     const double wxz[9] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w8k.x};
-    unsigned remaining = __ballot_sync(0xffffffffu, valid);
+    if (__all_sync(FULL, (key == cur) || (key < 0))) {
+#pragma unroll
+      for (int r = 0; r < 9; r++) {
+        acc[r] = fma(qv.x, wxz[r], acc[r]);
+        acc[9 + r] = fma(qv.y, wxz[r], acc[9 + r]);
+      }
+      continue;
+    }
+    const bool valid = key >= 0;
+    unsigned remaining = __ballot_sync(FULL, valid);
     while (remaining) {
       const int leader = __ffs(remaining) - 1;
-      const int kk = __shfl_sync(0xffffffffu, key, leader);
-      const unsigned grp = __ballot_sync(0xffffffffu, valid && key == kk) & remaining;
+      const int kk = __shfl_sync(FULL, key, leader);
+      const unsigned grp = __ballot_sync(FULL, valid && key == kk) & remaining;
       const bool member = (grp >> lane) & 1u;
       const bool accumulate = (kk == cur) || (__popc(grp) >= group_min) || (grp >> 31);
       if (accumulate) {
@@ -152,7 +203,7 @@ k_predict_run(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6,
   double* Q = smQ[w];
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long base = warp * (32LL * ITERS);
-  const Target<false> tg{g, M4, nullptr, 0, 0};
+  const Target<false> tg(g, M4, nullptr, 0, 0, lane);
   double wx = 0.0, wh = 0.0;
   double acc[18];
 #pragma unroll
@@ -202,6 +253,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   unsigned ok = 0;
+#pragma unroll 1
   for (int spin = 0; spin < (1 << 26); spin++) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
@@ -260,11 +312,12 @@ __device__ __forceinline__ void stage_fields(const GP& g, const Tile& t, const d
 __device__ __forceinline__ void gather6_tile(const double* sF, int delta, const Stencil& s, double f[6]) {
 #pragma unroll
   for (int c = 0; c < 6; c++) f[c] = 0.0;
+  const double2* base = reinterpret_cast<const double2*>(sF + delta * 6);
 #pragma unroll
   for (int kz = 0; kz < 3; kz++) {
 #pragma unroll
     for (int jy = 0; jy < 2; jy++) {
-      const double2* r = reinterpret_cast<const double2*>(sF + (kz * 2 + jy) * TILE_ROW_D + delta * 6);
+      const double2* r = base + (kz * 2 + jy) * (TILE_ROW_D / 2);
       const double wyz = s.fy[jy] * s.fz[kz];
       double2 v[9];
 #pragma unroll
@@ -300,7 +353,7 @@ __device__ __forceinline__ Kick gather_rotate(const GP& g, const PushParams& pp,
   return rotate(f, vx, vy, vz, pp.ht, pp.ht2);
 }
 
-// split [p0,p1) into TILE warps' contiguous sub-ranges (multiples of 32)
+// split [p0,p1) into the warps' contiguous sub-ranges (multiples of 32)
 __device__ __forceinline__ void warp_range(const Tile& t, int w, int nwarps, int& a, int& b) {
   const int len = t.p1 - t.p0;
   const int chunk = ((len + nwarps * 32 - 1) / (nwarps * 32)) * 32;
@@ -308,10 +361,17 @@ __device__ __forceinline__ void warp_range(const Tile& t, int w, int nwarps, int
   b = min(a + chunk, t.p1);
 }
 
+// one particle's six phase-space coordinates, streamed (evict-first)
+struct P6 { double x, y, z, vx, vy, vz; };
+__device__ __forceinline__ void load_p6(const ParticleSoA& P, int p, P6& o) {
+  o.x = __ldcs(P.x + p); o.y = __ldcs(P.y + p); o.z = __ldcs(P.z + p);
+  o.vx = __ldcs(P.vx + p); o.vy = __ldcs(P.vy + p); o.vz = __ldcs(P.vz + p);
+}
+
 // ---------------------------------------------------------------------------
 // Predictor on TMA-staged tiles.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(PR_WARPS * 32)
+__global__ void __launch_bounds__(PR_WARPS * 32, MRG_PRED_MINB)
 k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
                const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min) {
   __shared__ __align__(128) double sF[6 * TILE_ROW_D];
@@ -324,6 +384,10 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
   const bool busy = t.p1 > t.p0;                              // block-uniform
   double wx = 0.0, wh = 0.0;
   if (busy) {
+    int a, b;
+    warp_range(t, w, PR_WARPS, a, b);
+    P6 nxt;
+    if (a + lane < b) load_p6(P, a + lane, nxt);              // first 32 particles in flight during the staging
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     for (int e = threadIdx.x; e < 6 * TILE_ACC_D; e += blockDim.x) sM[e] = 0.0;
     __syncthreads();
@@ -331,32 +395,30 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     mbar_wait(&bar, 0);
     double* W = smW[w];
     double* Q = smQ[w];
-    const Target<true> tg{g, M4, sM, t.n0_first, t.ncell};
+    const Target<true> tg(g, M4, sM, t.n0_first, t.ncell, lane);
     double acc[18];
 #pragma unroll
     for (int n = 0; n < 18; n++) acc[n] = 0.0;
     int cur = -1;
-    int a, b;
-    warp_range(t, w, PR_WARPS, a, b);
     const double ah = pp.aimpl * pp.hh, hh2 = 0.5 * pp.hh;
 #pragma unroll 1
     for (int t0 = a; t0 < b; t0 += 32) {
-      const int p = t0 + lane;
+      const bool valid = t0 + lane < b;
+      const P6 c = nxt;
+      if (t0 + 32 + lane < b) load_p6(P, t0 + 32 + lane, nxt);   // prefetch the next 32 particles
       {
         double qvy[8], wxz[9];
         int key = -1;
-        if (p < b) {
-          const double x = __ldcs(P.x + p), y = __ldcs(P.y + p), z = __ldcs(P.z + p);
-          const double vx = __ldcs(P.vx + p), vy = __ldcs(P.vy + p), vz = __ldcs(P.vz + p);
-          const Kick k = gather_rotate(g, pp, t, sF, F6, x, y, z, vx, vy, vz);
+        if (valid) {
+          const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
           wx += k.wx; wh += k.wh;
           Predicted o;
-          o.vxj = fma(ah, k.dvx, vx);                         // F:1300-1302
-          o.vyj = fma(ah, k.dvy, vy);
-          o.vzj = fma(ah, k.dvz, vz);
-          o.rx = fma(pp.adt, fma(hh2, k.dvx, vx), x);         // F:1304-1306
-          o.ry = fma(pp.adt, fma(hh2, k.dvy, vy), y);
-          o.rz = fma(pp.adt, fma(hh2, k.dvz, vz), z);
+          o.vxj = fma(ah, k.dvx, c.vx);                       // F:1300-1302
+          o.vyj = fma(ah, k.dvy, c.vy);
+          o.vzj = fma(ah, k.dvz, c.vz);
+          o.rx = fma(pp.adt, fma(hh2, k.dvx, c.vx), c.x);     // F:1304-1306
+          o.ry = fma(pp.adt, fma(hh2, k.dvy, c.vy), c.y);
+          o.rz = fma(pp.adt, fma(hh2, k.dvz, c.vz), c.z);
           if (wrap_pos(g, o.rx, o.ry, o.rz)) o.vyj = -o.vyj;  // partbc, F:1375
           key = scatter_factors(g, pp.qmult, o, qvy, wxz);
         } else {
@@ -391,9 +453,10 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
 // Corrector on TMA-staged tiles: F:1162-1295, partbc F:1337, slab test of the
 // drive kick F:1343-1345.  With key_out != nullptr it also writes the cell of
 // wrap(x' + lookahead*v') (next step's sort key) and the cell histogram, which
-// lets mrg_sort skip its key pass.
+// lets mrg_sort skip its key pass.  The key is a sorting hint only (any value
+// gives the same results), so it is formed with contracted arithmetic.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(PR_WARPS * 32)
+__global__ void __launch_bounds__(PR_WARPS * 32, MRG_CORR_MINB)
 k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, const int* __restrict__ cell_end,
                double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits, int* __restrict__ slab_list,
                int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead) {
@@ -404,29 +467,31 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
   const bool busy = t.p1 > t.p0;
   double wx = 0.0, wh = 0.0;
   if (busy) {
+    int a, b;
+    warp_range(t, w, PR_WARPS, a, b);
+    P6 nxt;
+    if (a + lane < b) load_p6(P, a + lane, nxt);
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
-    int a, b;
-    warp_range(t, w, PR_WARPS, a, b);
     const double hh2 = 0.5 * pp.hh;
 #pragma unroll 1
     for (int t0 = a; t0 < b; t0 += 32) {
       const int p = t0 + lane;
       const bool valid = p < b;
+      const P6 c = nxt;
+      if (p + 32 < b) load_p6(P, p + 32, nxt);                // prefetch the next 32 particles
       int kcell = -1;
       if (valid) {
-        double x = __ldcs(P.x + p), y = __ldcs(P.y + p), z = __ldcs(P.z + p);
-        double vx = __ldcs(P.vx + p), vy = __ldcs(P.vy + p), vz = __ldcs(P.vz + p);
-        const Kick k = gather_rotate(g, pp, t, sF, F6, x, y, z, vx, vy, vz);
+        const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
         wx += k.wx; wh += k.wh;
-        x = fma(pp.dt, fma(hh2, k.dvx, vx), x);               // F:1289-1291
-        y = fma(pp.dt, fma(hh2, k.dvy, vy), y);
-        z = fma(pp.dt, fma(hh2, k.dvz, vz), z);
-        vx = fma(pp.hh, k.dvx, vx);                           // F:1293-1295
-        vy = fma(pp.hh, k.dvy, vy);
-        vz = fma(pp.hh, k.dvz, vz);
+        double x = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x);    // F:1289-1291
+        double y = fma(pp.dt, fma(hh2, k.dvy, c.vy), c.y);
+        double z = fma(pp.dt, fma(hh2, k.dvz, c.vz), c.z);
+        const double vx = fma(pp.hh, k.dvx, c.vx);            // F:1293-1295
+        double vy = fma(pp.hh, k.dvy, c.vy);
+        const double vz = fma(pp.hh, k.dvz, c.vz);
         if (wrap_pos(g, x, y, z)) vy = -vy;                   // partbc, F:1337
         __stcs(P.x + p, x); __stcs(P.y + p, y); __stcs(P.z + p, z);
         __stcs(P.vx + p, vx); __stcs(P.vy + p, vy); __stcs(P.vz + p, vz);
@@ -440,15 +505,12 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
         if (key_out) {
           double sx = fma(lookahead, vx, x), sy = fma(lookahead, vy, y), sz = fma(lookahead, vz, z);
           wrap_pos(g, sx, sy, sz);
-          int ip, jp, kp;
-          cell_of(g, sx, sy, sz, ip, jp, kp);
-          ip = min(ip, g.mx - 1); jp = min(jp, g.my - 1); kp = min(kp, g.mz - 1);
-          kcell = ip + g.mx * (jp + g.my * kp);
+          kcell = sort_cell(g, sx, sy, sz);
           key_out[p] = kcell;
         }
       }
       if (key_out) {
-        const unsigned act = __ballot_sync(0xffffffffu, valid);
+        const unsigned act = __ballot_sync(FULL, valid);
         if (valid) {
           const unsigned m = __match_any_sync(act, kcell);
           if (lane == __ffs(m) - 1) atomicAdd(hist + kcell, __popc(m));

@@ -1,0 +1,21 @@
+#!/bin/bash
+# parity + bench of the product library and of every variants/libmrg_*.so
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e "$@" > gpurun_out/bench_main.log 2>&1; tail -c 900 gpurun_out/bench_main.log
+for v in variants/libmrg_*.so; do
+  [ -f "$v" ] || continue
+  n=$(basename $v .so)
+  MRG_LIB=$PWD/$v timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu --no-e2e "$@" > gpurun_out/bench_$n.log 2>&1
+done
+python - <<'PY'
+import glob, json
+for f in sorted(glob.glob("gpurun_out/bench_*.log")):
+    l = [x for x in open(f) if x.startswith("{")]
+    if not l:
+        print(f, "NO RESULT"); continue
+    d = json.loads(l[-1]); r = d["roofline"]
+    print("%-40s ms/step %.2f pred %.2f corr %.2f clocks %s" % (f, d["ms_per_step"], r["predictor"]["ms_per_launch"], r["corrector"]["ms_per_launch"], d["clocks"]))
+PY
