@@ -283,7 +283,8 @@ def run_ours(args):
     bytes_corr = 96.0 * n_sp + 6 * 8.0 * n_grid
     tp, tc = float(np.mean(state["tp"])), float(np.mean(state["tc"]))
     gb_pred, gb_corr = bytes_pred / (tp * 1e-3) / 1e9, bytes_corr / (tc * 1e-3) / 1e9
-    dominant = ("k_predict_tile" if args.tile else "k_predict_run") if tp >= tc else ("k_correct_tile" if args.tile else "k_correct")
+    kn = {0: ("k_predict_run", "k_correct"), 1: ("k_predict_tile", "k_correct_tile"), 2: ("k_predict_pair", "k_correct_pair")}[args.tile]
+    dominant = kn[0] if tp >= tc else kn[1]
     ach = gb_pred if tp >= tc else gb_corr
     step_bytes = 2 * (bytes_pred + bytes_corr)
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
@@ -380,7 +381,7 @@ def main():
     ap.add_argument("--deposit", type=int, default=2)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--group-min", type=int, default=2)
-    ap.add_argument("--tile", type=int, default=1)
+    ap.add_argument("--tile", type=int, default=2)
     ap.add_argument("--fused-keys", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")

@@ -5,6 +5,7 @@
 #include "../../include/mrg_fulmov.h"
 #include "mrg_kernels.cuh"
 #include "mrg_tile.cuh"
+#include "mrg_pair.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -55,6 +56,15 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 
+// warps per CTA of the pair kernels (shared-memory budget: see PredSmem / CorrSmem)
+#ifndef MRG_PRED_NW
+#define MRG_PRED_NW 6
+#endif
+#ifndef MRG_CORR_NW
+#define MRG_CORR_NW 4
+#endif
+constexpr int PRED_NW = MRG_PRED_NW, CORR_NW = MRG_CORR_NW;
+
 int nccl_load() {
   if (g_nccl.h) return MRG_OK;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -92,6 +102,7 @@ struct Species {
   int* key = nullptr; long long key_cap = 0;
   int* hist = nullptr;
   bool keys_valid = false;
+  bool hist_valid = false;     // s.hist matches s.key (the pair corrector emits keys only)
   double keys_lookahead = 0.0;
 };
 
@@ -141,7 +152,7 @@ struct mrg_ctx {
   // nccl
   void* comm = nullptr;
   // options / counters
-  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1;
+  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 2, opt_fused_keys = 1;
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -326,7 +337,12 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   g.xlo = -(g.hx / 2); g.xhi = xmax - g.hx / 2;                          // F:1856-1862
   g.zlo = -(g.hz / 2); g.zhi = zmax - g.hz / 2;
   g.ymax2 = 2.0 * ymax;
+  auto hi32 = [](double v) { long long b; memcpy(&b, &v, 8); return (int)(b >> 32); };
+  g.xhi_h = hi32(g.xhi); g.xlo_h = hi32(g.xlo); g.ymax_h = hi32(g.ymax); g.zhi_h = hi32(g.zhi); g.zlo_h = hi32(g.zlo);
   c->ncell = (long long)mx * my * mz;
+  CK(cudaFuncSetAttribute(k_predict_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_predict_pair<PRED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PredSmem<PRED_NW>::bytes));
+  CK(cudaFuncSetAttribute(k_correct_pair<CORR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CorrSmem<CORR_NW>::bytes));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&c->ev0));
   CK(cudaEventCreate(&c->ev1));
@@ -557,14 +573,17 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     if (s.n > 0) {
       const int iters = (c->opt_deposit == 2) ? c->opt_iters : 1;
       const bool tiled = c->opt_tile && c->opt_deposit == 2 && s.index_valid;
+      const bool pair = tiled && c->opt_tile == 2;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
       if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz;
-      rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * blocks, sizeof(double));
+      const int nparts = pair ? blocks * PRED_NW : (tiled ? blocks * PR_WARPS : blocks);   // tiled kernels store one partial per warp
+      rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
       CK(cudaEventRecord(c->ev0, c->stream));
       const int gm = c->opt_group_min * 4;   // option counts particles; a particle is a quad of lanes
-      if (tiled) k_predict_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm);
+      if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
+      else if (tiled) k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm);
       else if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
       else if (iters == 1) k_predict_run<1><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
       else if (iters == 4) k_predict_run<4><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
@@ -574,7 +593,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       else return fail(MRG_ERR_ARG, "option iters must be 4, 8, 16 or 32");
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
-      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, blocks, s.M4 + (size_t)g.ntot * 4); CKL(c);
+      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c);
     }
     if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
@@ -608,28 +627,35 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     s.keys_valid = false;
     if (s.n > 0) {
       const bool tiled = c->opt_tile && s.index_valid;
-      const int B = tiled ? 128 : 256;
+      const bool pair = tiled && c->opt_tile == 2;
+      const int B = pair ? CORR_NW * 32 : (tiled ? 128 : 256);
       const int blocks = tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz : grid_for(s.n, B);
-      rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * blocks, sizeof(double));
+      const int nparts = pair ? blocks * CORR_NW : (tiled ? blocks * PR_WARPS : blocks);
+      rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
       int* key_out = nullptr;
-      if (tiled && c->opt_fused_keys) {   // emit next step's sort keys (cell of x + hdt*v) and their histogram
-        rc = ensure(c, (void**)&s.key, &s.key_cap, s.n, sizeof(int));
+      if (tiled && c->opt_fused_keys) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
+        rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
         if (rc) return rc;
-        CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+        if (!pair) CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
         key_out = s.key;
       }
       CK(cudaEventRecord(c->ev0, c->stream));
-      if (tiled) {
+      if (pair) {
+        Slab sl{c->slab_bits, c->slab_list, c->slab_count};
+        k_correct_pair<CORR_NW><<<blocks, B, CorrSmem<CORR_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, sl, key_out, p->hdt);
+        s.hist_valid = false;
+      } else if (tiled) {
         k_correct_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, c->slab_bits, c->slab_list,
                                                     c->slab_count, key_out, s.hist, p->hdt);
+        s.hist_valid = true;
       } else {
         k_correct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, c->wk_partial, c->slab_bits, c->slab_list, c->slab_count);
       }
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
       if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
-      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, blocks, c->wk2); CKL(c);
+      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c);
     }
     if (c->nranks > 1) {                                           // F:1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
@@ -727,12 +753,15 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
   if (s.n == 0) return MRG_OK;
   rc = ensure_alt(c, s.cap, true);
   if (rc) return rc;
-  rc = ensure(c, (void**)&s.key, &s.key_cap, s.n, sizeof(int));
+  rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
   if (rc) return rc;
   const int B = 256;
-  if (!(s.keys_valid && s.keys_lookahead == lookahead)) {   // the corrector may already have emitted keys + histogram
+  if (!(s.keys_valid && s.keys_lookahead == lookahead)) {   // the corrector may already have emitted the keys
     CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
     k_sort_keys<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, s.key, s.hist); CKL(c);
+  } else if (!s.hist_valid) {
+    CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+    k_key_hist<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.hist); CKL(c);
   }
   s.keys_valid = false;
   rc = scan_excl(c, s.hist, s.cell_end, c->ncell + 1, nullptr);
@@ -770,7 +799,8 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value != 4 && value != 8 && value != 16 && value != 32) return fail(MRG_ERR_ARG, "iters must be 4, 8, 16 or 32");
     c->opt_iters = (int)value;
   } else if (n == "tile") {
-    c->opt_tile = value != 0;
+    if (value < 0 || value > 2) return fail(MRG_ERR_ARG, "tile must be 0, 1 or 2");
+    c->opt_tile = (int)value;
   } else if (n == "fused_keys") {
     c->opt_fused_keys = value != 0;
   } else if (n == "group_min") {

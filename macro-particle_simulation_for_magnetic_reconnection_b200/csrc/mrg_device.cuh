@@ -23,6 +23,7 @@ struct GP {
   double xlo, xhi;         // -hx/2, xmax-hx/2   (F:1856-1862)
   double zlo, zhi;
   double ymax2;            // 2*ymax             (F:1867)
+  int xhi_h, xlo_h, ymax_h, zhi_h, zlo_h;   // high words of the partbc limits (maybe_wrap pre-test)
 };
 
 // node index of (i,j,k) in the (-2:mx+1,-1:my+1,-2:mz+1) layout

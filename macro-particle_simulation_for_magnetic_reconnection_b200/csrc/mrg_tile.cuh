@@ -251,6 +251,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned by
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// same, with an L2 evict-first policy: the particle streams (GBs per pass) must not
+// push the field / moment grids out of L2 (CUTLASS CacheHintSm90::EVICT_FIRST encoding)
+__device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   unsigned ok = 0;
 #pragma unroll 1
@@ -353,48 +362,123 @@ __device__ __forceinline__ Kick gather_rotate(const GP& g, const PushParams& pp,
   return rotate(f, vx, vy, vz, pp.ht, pp.ht2);
 }
 
-// split [p0,p1) into the warps' contiguous sub-ranges (multiples of 32)
-__device__ __forceinline__ void warp_range(const Tile& t, int w, int nwarps, int& a, int& b) {
-  const int len = t.p1 - t.p0;
-  const int chunk = ((len + nwarps * 32 - 1) / (nwarps * 32)) * 32;
-  a = min(t.p0 + w * chunk, t.p1);
-  b = min(a + chunk, t.p1);
+// ---------------------------------------------------------------------------
+// Particle streams.  The NW warps of a CTA split the tile's iterations (32
+// particles each) evenly; every warp pulls its own slice through an NSTAGE-deep
+// ring of shared-memory stages filled by 1-D bulk TMA (six copies per stage,
+// one per SoA array), so the HBM latency is covered by the ring and costs no
+// registers.  A stage holds STAGE_D = 34 doubles per array: bulk copies need
+// 16-byte aligned addresses, so the copy starts at the even index below the
+// slice start (the arrays are allocated with >= 64 elements of slack).
+// ---------------------------------------------------------------------------
+constexpr int NSTAGE = 3;
+constexpr int STAGE_D = 34;
+constexpr int STAGE_BYTES = STAGE_D * 8;
+
+struct Stream {
+  int a, b;         // this warp's particle slots [a, b)
+  int nit;          // iterations
+  int issued;       // iterations whose copies have been issued
+  double* ring;     // [NSTAGE][6][STAGE_D]
+  unsigned long long* bar;   // [NSTAGE]
+};
+
+__device__ __forceinline__ void stream_issue(const ParticleSoA& P, Stream& st, int lane) {
+  if (st.issued < st.nit) {
+    if (lane == 0) {
+      const int slot = st.issued % NSTAGE;
+      const int e = (st.a + 32 * st.issued) & ~1;
+      double* dst = st.ring + slot * 6 * STAGE_D;
+      unsigned long long* bar = st.bar + slot;
+      mbar_expect_tx(bar, 6u * STAGE_BYTES);
+      bulk_g2s_stream(dst + 0 * STAGE_D, P.x + e, STAGE_BYTES, bar);
+      bulk_g2s_stream(dst + 1 * STAGE_D, P.y + e, STAGE_BYTES, bar);
+      bulk_g2s_stream(dst + 2 * STAGE_D, P.z + e, STAGE_BYTES, bar);
+      bulk_g2s_stream(dst + 3 * STAGE_D, P.vx + e, STAGE_BYTES, bar);
+      bulk_g2s_stream(dst + 4 * STAGE_D, P.vy + e, STAGE_BYTES, bar);
+      bulk_g2s_stream(dst + 5 * STAGE_D, P.vz + e, STAGE_BYTES, bar);
+    }
+    st.issued++;
+  }
 }
 
-// one particle's six phase-space coordinates, streamed (evict-first)
+// iterations [w*N/NW, (w+1)*N/NW) of the tile's N = ceil(len/32) go to warp w; starts the ring
+__device__ __forceinline__ void stream_open(const ParticleSoA& P, const Tile& t, int w, int nwarps, int lane, double* ring,
+                                            unsigned long long* bar, Stream& st) {
+  const int N = (t.p1 - t.p0 + 31) >> 5;
+  const int i0 = (w * N) / nwarps, i1 = ((w + 1) * N) / nwarps;
+  st.a = t.p0 + 32 * i0;
+  st.b = min(t.p0 + 32 * i1, t.p1);
+  st.nit = i1 - i0;
+  st.issued = 0;
+  st.ring = ring;
+  st.bar = bar;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; s++) mbar_init(bar + s, 1);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int s = 0; s < NSTAGE - 1; s++) stream_issue(P, st, lane);
+}
+
+// one particle's six phase-space coordinates
 struct P6 { double x, y, z, vx, vy, vz; };
-__device__ __forceinline__ void load_p6(const ParticleSoA& P, int p, P6& o) {
-  o.x = __ldcs(P.x + p); o.y = __ldcs(P.y + p); o.z = __ldcs(P.z + p);
-  o.vx = __ldcs(P.vx + p); o.vy = __ldcs(P.vy + p); o.vz = __ldcs(P.vz + p);
+
+// wait for iteration `it` of the stream, hand lane `lane` its particle, keep the ring full.
+// Must be called by the whole warp, after a __syncwarp() that ends the previous iteration's reads.
+__device__ __forceinline__ void stream_next(const ParticleSoA& P, Stream& st, int it, int lane, P6& o) {
+  stream_issue(P, st, lane);                                   // refill the slot consumed in iteration it-1
+  const int slot = it % NSTAGE;
+  mbar_wait(st.bar + slot, (unsigned)((it / NSTAGE) & 1));
+  const int start = st.a + 32 * it;
+  const double* src = st.ring + slot * 6 * STAGE_D + (start & 1) + lane;
+  o.x = src[0 * STAGE_D]; o.y = src[1 * STAGE_D]; o.z = src[2 * STAGE_D];
+  o.vx = src[3 * STAGE_D]; o.vy = src[4 * STAGE_D]; o.vz = src[5 * STAGE_D];
+}
+
+// per-warp partial sums of wkix/wkih (F:1282-1283) -> wk_partial[2*(block*nwarps + w)]
+__device__ __forceinline__ void warp_wk_store(double wx, double wh, double* __restrict__ partial, int nwarps) {
+  wx = warp_sum(wx);
+  wh = warp_sum(wh);
+  if ((threadIdx.x & 31) == 0) {
+    const size_t e = 2 * ((size_t)blockIdx.x * nwarps + (threadIdx.x >> 5));
+    partial[e + 0] = wx;
+    partial[e + 1] = wh;
+  }
 }
 
 // ---------------------------------------------------------------------------
 // Predictor on TMA-staged tiles.
 // ---------------------------------------------------------------------------
+constexpr int PRED_SMEM_BYTES = (6 * TILE_ROW_D + 6 * TILE_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + 256 + NSTAGE * 6 * STAGE_D)) * 8 +
+                                (PR_WARPS * NSTAGE + 1) * 8;
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_PRED_MINB)
 k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
                const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min) {
-  __shared__ __align__(128) double sF[6 * TILE_ROW_D];
-  __shared__ __align__(16) double sM[6 * TILE_ACC_D];
-  __shared__ __align__(16) double smW[PR_WARPS][32 * PR_W_STRIDE];
-  __shared__ __align__(16) double smQ[PR_WARPS][4 * 32 * 2];
-  __shared__ __align__(8) unsigned long long bar;
+  // dynamic shared memory (PRED_SMEM_BYTES > 48 KB static limit), carved up by hand
+  extern __shared__ __align__(128) double smem_dyn[];
+  double* sF = smem_dyn;                                       // [6][TILE_ROW_D]      staged fields
+  double* sM = sF + 6 * TILE_ROW_D;                            // [6][TILE_ACC_D]      moment accumulators
+  double* smW = sM + 6 * TILE_ACC_D;                           // [warps][32*PR_W_STRIDE]
+  double* smQ = smW + PR_WARPS * 32 * PR_W_STRIDE;             // [warps][256]
+  double* sRing = smQ + PR_WARPS * 256;                        // [warps][NSTAGE*6*STAGE_D]
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sRing + PR_WARPS * NSTAGE * 6 * STAGE_D);   // [warps][NSTAGE] + 1
+  unsigned long long& bar = sBar[PR_WARPS * NSTAGE];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Tile t = tile_of(g, cell_end, blockIdx.x);
   const bool busy = t.p1 > t.p0;                              // block-uniform
   double wx = 0.0, wh = 0.0;
   if (busy) {
-    int a, b;
-    warp_range(t, w, PR_WARPS, a, b);
-    P6 nxt;
-    if (a + lane < b) load_p6(P, a + lane, nxt);              // first 32 particles in flight during the staging
+    Stream st;
+    stream_open(P, t, w, PR_WARPS, lane, sRing + w * (NSTAGE * 6 * STAGE_D), sBar + w * NSTAGE, st);   // particles in flight during the field staging
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     for (int e = threadIdx.x; e < 6 * TILE_ACC_D; e += blockDim.x) sM[e] = 0.0;
     __syncthreads();
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
-    double* W = smW[w];
-    double* Q = smQ[w];
+    double* W = smW + w * (32 * PR_W_STRIDE);
+    double* Q = smQ + w * 256;
     const Target<true> tg(g, M4, sM, t.n0_first, t.ncell, lane);
     double acc[18];
 #pragma unroll
@@ -402,10 +486,10 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     int cur = -1;
     const double ah = pp.aimpl * pp.hh, hh2 = 0.5 * pp.hh;
 #pragma unroll 1
-    for (int t0 = a; t0 < b; t0 += 32) {
-      const bool valid = t0 + lane < b;
-      const P6 c = nxt;
-      if (t0 + 32 + lane < b) load_p6(P, t0 + 32 + lane, nxt);   // prefetch the next 32 particles
+    for (int it = 0; it < st.nit; it++) {
+      P6 c;
+      stream_next(P, st, it, lane, c);
+      const bool valid = st.a + 32 * it + lane < st.b;
       {
         double qvy[8], wxz[9];
         int key = -1;
@@ -446,7 +530,7 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       }
     }
   }
-  block_wk_store(wx, wh, wk_partial);
+  warp_wk_store(wx, wh, wk_partial, PR_WARPS);
 }
 
 // ---------------------------------------------------------------------------
@@ -461,27 +545,27 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
                double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits, int* __restrict__ slab_list,
                int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead) {
   __shared__ __align__(128) double sF[6 * TILE_ROW_D];
+  __shared__ __align__(16) double sRing[PR_WARPS][NSTAGE * 6 * STAGE_D];
+  __shared__ __align__(8) unsigned long long sBar[PR_WARPS][NSTAGE];
   __shared__ __align__(8) unsigned long long bar;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Tile t = tile_of(g, cell_end, blockIdx.x);
   const bool busy = t.p1 > t.p0;
   double wx = 0.0, wh = 0.0;
   if (busy) {
-    int a, b;
-    warp_range(t, w, PR_WARPS, a, b);
-    P6 nxt;
-    if (a + lane < b) load_p6(P, a + lane, nxt);
+    Stream st;
+    stream_open(P, t, w, PR_WARPS, lane, sRing[w], sBar[w], st);
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     const double hh2 = 0.5 * pp.hh;
 #pragma unroll 1
-    for (int t0 = a; t0 < b; t0 += 32) {
-      const int p = t0 + lane;
-      const bool valid = p < b;
-      const P6 c = nxt;
-      if (p + 32 < b) load_p6(P, p + 32, nxt);                // prefetch the next 32 particles
+    for (int it = 0; it < st.nit; it++) {
+      P6 c;
+      stream_next(P, st, it, lane, c);
+      const int p = st.a + 32 * it + lane;
+      const bool valid = p < st.b;
       int kcell = -1;
       if (valid) {
         const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
@@ -516,9 +600,10 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
           if (lane == __ffs(m) - 1) atomicAdd(hist + kcell, __popc(m));
         }
       }
+      __syncwarp();
     }
   }
-  block_wk_store(wx, wh, wk_partial);
+  warp_wk_store(wx, wh, wk_partial, PR_WARPS);
 }
 
 }  // namespace mrg

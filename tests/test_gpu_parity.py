@@ -63,7 +63,7 @@ def test_prepared_fields_bit_exact(mrg, case, ifil):
 
 # ---- C1: corrector ------------------------------------------------------------
 @pytest.mark.parametrize("ksp", [1, 2])
-@pytest.mark.parametrize("sort,tile", [(False, 1), (True, 1), (True, 0)])
+@pytest.mark.parametrize("sort,tile", [(False, 2), (True, 2), (True, 1), (True, 0)])
 def test_corrector_particles(mrg, case, ksp, sort, tile):
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
@@ -89,11 +89,13 @@ def test_corrector_particles(mrg, case, ksp, sort, tile):
 @pytest.mark.parametrize("ksp", [1, 2])
 @pytest.mark.parametrize("deposit,iters,sort,tile", [(0, 8, False, 0), (1, 8, False, 0), (1, 8, True, 0), (2, 4, True, 0),
                                                      (2, 8, True, 0), (2, 8, False, 0), (2, 32, True, 0),
-                                                     (2, 8, True, 1), (2, 8, "adt", 1), (2, 8, "stale", 1)])
+                                                     (2, 8, True, 1), (2, 8, "adt", 1), (2, 8, "stale", 1),
+                                                     (2, 8, True, 2), (2, 8, "adt", 2), (2, 8, "stale", 2)])
 def test_predictor_moments(mrg, case, ksp, deposit, iters, sort, tile):
     """sort: False = load order; True = sorted by the gather cell (x + hdt*v); "adt" = sorted by another
     key (many particles gather outside their tile); "stale" = sorted, then moved by a corrector step
-    without re-sorting.  tile=1 runs the TMA-staged shared-memory kernels."""
+    without re-sorting.  tile=1 runs the TMA-staged shared-memory kernels, tile=2 the two-particles-per-thread
+    kernels (the default)."""
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
     orig = [a.copy() for a in sp[ksp]]
