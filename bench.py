@@ -169,7 +169,7 @@ def workload_config(n, args):
                         % (mx, my, mz, args.ppc, "1" if n == 1 else ("2" if n == 8 else "1 scaled")),
             "grid": [mx, my, mz], "ppc": args.ppc, "species": 2, "particles_per_gpu": 2 * mx * my * mz * args.ppc // n,
             "sharding": "round-robin particle ownership l = rank+1 (mod N), replicated grids, NCCL fp64 allreduce of J/chi",
-            "sort_every": args.sort_every, "deposit": args.deposit, "iters": args.iters, "tile": args.tile,
+            "sort_every": args.sort_every, "sort_every_ions": args.sort_every_ions or args.sort_every, "deposit": args.deposit, "iters": args.iters, "tile": args.tile,
             "fused_keys": args.fused_keys,
             "l2": "inputs larger than L2 (12.9 GB of particle arrays per GPU vs 126 MB)"}
 
@@ -234,8 +234,9 @@ def run_ours(args):
             _, _, state["ranfb"] = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, params, state["ranfb"])
             state["tc"].append(ctx.last_kernel_ms())
         state["step"] += 1
-        if args.sort_every and state["step"] % args.sort_every == 0:
-            for ksp in (1, 2):
+        for ksp in (1, 2):
+            every = args.sort_every_ions if (ksp == 1 and args.sort_every_ions) else args.sort_every
+            if every and state["step"] % every == 0:
                 ctx.sort(ksp, c.hdt)
 
     def barrier():
@@ -283,7 +284,8 @@ def run_ours(args):
     bytes_corr = 96.0 * n_sp + 6 * 8.0 * n_grid
     tp, tc = float(np.mean(state["tp"])), float(np.mean(state["tc"]))
     gb_pred, gb_corr = bytes_pred / (tp * 1e-3) / 1e9, bytes_corr / (tc * 1e-3) / 1e9
-    kn = {0: ("k_predict_run", "k_correct"), 1: ("k_predict_tile", "k_correct_tile"), 2: ("k_predict_pair", "k_correct_pair")}[args.tile]
+    kn = {0: ("k_predict_run", "k_correct"), 1: ("k_predict_tile", "k_correct_tile"), 2: ("k_predict_pair", "k_correct_pair"),
+          3: ("k_lane<1>+k_lane_deposit", "k_lane<0>"), 4: ("k_predict_quad", "k_correct_quad")}[args.tile]
     dominant = kn[0] if tp >= tc else kn[1]
     ach = gb_pred if tp >= tc else gb_corr
     step_bytes = 2 * (bytes_pred + bytes_corr)
@@ -378,10 +380,11 @@ def main():
     ap.add_argument("--grid", type=int, nargs=3, default=None, help="override the grid (mx my mz)")
     ap.add_argument("--ppc", type=int, default=64)
     ap.add_argument("--sort-every", type=int, default=1)
+    ap.add_argument("--sort-every-ions", type=int, default=0, help="ion sort cadence (0 = same as --sort-every)")
     ap.add_argument("--deposit", type=int, default=2)
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--group-min", type=int, default=2)
-    ap.add_argument("--tile", type=int, default=2)
+    ap.add_argument("--tile", type=int, default=1)
     ap.add_argument("--fused-keys", type=int, default=1)
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")

@@ -6,6 +6,8 @@
 #include "mrg_kernels.cuh"
 #include "mrg_tile.cuh"
 #include "mrg_pair.cuh"
+#include "mrg_lane.cuh"
+#include "mrg_quad.cuh"
 
 #include <dlfcn.h>
 #include <math.h>
@@ -98,6 +100,7 @@ struct Species {
   // cell index of the current slot order (built by mrg_sort): cell_end[c] = end slot of cell c
   int* cell_end = nullptr;
   bool index_valid = false;
+  int layout = 0;              // 0 = slots in cell order; 1 = 16-cell tiles stored as 16 interleaved runs (mrg_lane.cuh)
   // next-sort keys emitted by the corrector (fused_keys) + their histogram
   int* key = nullptr; long long key_cap = 0;
   int* hist = nullptr;
@@ -152,7 +155,8 @@ struct mrg_ctx {
   // nccl
   void* comm = nullptr;
   // options / counters
-  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 2, opt_fused_keys = 1;
+  int lane_grid[3] = {148 * 8, 148 * 8, 148 * 8};   // persistent warps of k_lane<0>, k_lane<1>, k_lane_deposit (SMs x resident CTAs)
+  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1;
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -205,6 +209,7 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   if (s.id) { CK(cudaFree(s.id)); s.id = nullptr; }
   s.n = n;
   s.index_valid = false;
+  s.layout = 0;
   s.keys_valid = false;
   if (!s.cell_end) {
     CK(cudaMalloc((void**)&s.cell_end, (size_t)(c->ncell + 1) * sizeof(int)));
@@ -340,7 +345,18 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   auto hi32 = [](double v) { long long b; memcpy(&b, &v, 8); return (int)(b >> 32); };
   g.xhi_h = hi32(g.xhi); g.xlo_h = hi32(g.xlo); g.ymax_h = hi32(g.ymax); g.zhi_h = hi32(g.zhi); g.zlo_h = hi32(g.zlo);
   c->ncell = (long long)mx * my * mz;
+  {
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    int nb[3] = {8, 8, 8};
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[0], k_lane<0>, 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[1], k_lane<1>, 32, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[2], k_lane_deposit, 32, 0));
+    for (int k = 0; k < 3; k++) c->lane_grid[k] = prop.multiProcessorCount * std::max(nb[k], 1);
+  }
   CK(cudaFuncSetAttribute(k_predict_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_predict_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, QPRED_SMEM_BYTES));
+  CK(cudaFuncSetAttribute(k_correct_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, QCORR_SMEM_BYTES));
   CK(cudaFuncSetAttribute(k_predict_pair<PRED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PredSmem<PRED_NW>::bytes));
   CK(cudaFuncSetAttribute(k_correct_pair<CORR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CorrSmem<CORR_NW>::bytes));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -572,17 +588,29 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     const int B = 128;
     if (s.n > 0) {
       const int iters = (c->opt_deposit == 2) ? c->opt_iters : 1;
-      const bool tiled = c->opt_tile && c->opt_deposit == 2 && s.index_valid;
+      const bool lane = c->opt_tile == 3 && s.index_valid && s.layout == 1;
+      const bool quad = c->opt_tile == 4 && s.index_valid && s.layout == 0;
+      const bool tiled = !lane && !quad && c->opt_tile && c->opt_tile < 3 && c->opt_deposit == 2 && s.index_valid && s.layout == 0;
       const bool pair = tiled && c->opt_tile == 2;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
       if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz;
-      const int nparts = pair ? blocks * PRED_NW : (tiled ? blocks * PR_WARPS : blocks);   // tiled kernels store one partial per warp
+      if (lane) blocks = ((g.mx + LT_CELLS - 1) / LT_CELLS) * g.my * g.mz;
+      if (quad) blocks = ((g.mx + QT_CELLS - 1) / QT_CELLS) * g.my * g.mz;
+      const int nparts = pair ? blocks * PRED_NW : (tiled ? 1 : blocks);   // pair kernels: one partial per warp; tiled: two atomic accumulators
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
+      if (tiled && !pair) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
+      if (lane) { rc = ensure_alt(c, s.cap, false); if (rc) return rc; }
       CK(cudaEventRecord(c->ev0, c->stream));
       const int gm = c->opt_group_min * 4;   // option counts particles; a particle is a quad of lanes
-      if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
+      if (quad) k_predict_quad<<<blocks, PR_WARPS * 32, QPRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, s.M4 + (size_t)g.ntot * 4, gm);
+      else if (lane) {   // split predictor: push into the spare SoA set, then deposit from it
+        Six Q; for (int k = 0; k < 6; k++) Q.p[k] = c->alt[k];
+        k_lane<1><<<std::min(blocks, c->lane_grid[1]), 32, 0, c->stream>>>(g, pp, P, Q, c->F6, s.cell_end, s.M4 + (size_t)g.ntot * 4, Slab{nullptr, nullptr, nullptr}, nullptr, 0.0, blocks); CKL(c);
+        k_lane_deposit<<<std::min(blocks, c->lane_grid[2]), 32, 0, c->stream>>>(g, qmult, Q, s.M4, s.cell_end, blocks);
+      }
+      else if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
       else if (tiled) k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm);
       else if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
       else if (iters == 1) k_predict_run<1><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
@@ -593,7 +621,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       else return fail(MRG_ERR_ARG, "option iters must be 4, 8, 16 or 32");
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
-      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c);
+      if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c); }   // k_lane / k_*_quad sum wkix/wkih themselves
     }
     if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
@@ -626,22 +654,35 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     CK(cudaMemsetAsync(c->wk2, 0, 2 * sizeof(double), c->stream));
     s.keys_valid = false;
     if (s.n > 0) {
-      const bool tiled = c->opt_tile && s.index_valid;
+      const bool lane = c->opt_tile == 3 && s.index_valid && s.layout == 1;
+      const bool quad = c->opt_tile == 4 && s.index_valid && s.layout == 0;
+      const bool tiled = !lane && !quad && c->opt_tile && c->opt_tile < 3 && s.index_valid && s.layout == 0;
       const bool pair = tiled && c->opt_tile == 2;
-      const int B = pair ? CORR_NW * 32 : (tiled ? 128 : 256);
-      const int blocks = tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz : grid_for(s.n, B);
-      const int nparts = pair ? blocks * CORR_NW : (tiled ? blocks * PR_WARPS : blocks);
+      const int B = lane ? 32 : (pair ? CORR_NW * 32 : ((tiled || quad) ? 128 : 256));
+      const int blocks = lane ? ((g.mx + LT_CELLS - 1) / LT_CELLS) * g.my * g.mz
+                              : quad ? ((g.mx + QT_CELLS - 1) / QT_CELLS) * g.my * g.mz
+                              : (tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz : grid_for(s.n, B));
+      const int nparts = pair ? blocks * CORR_NW : (tiled ? 1 : blocks);
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
+      if (tiled && !pair) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
       int* key_out = nullptr;
-      if (tiled && c->opt_fused_keys) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
+      if ((tiled || lane || quad) && c->opt_fused_keys) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
         rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
         if (rc) return rc;
-        if (!pair) CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+        if (!pair && !lane && !quad) CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
         key_out = s.key;
       }
       CK(cudaEventRecord(c->ev0, c->stream));
-      if (pair) {
+      if (quad) {
+        Slab sl{c->slab_bits, c->slab_list, c->slab_count};
+        k_correct_quad<<<blocks, B, QCORR_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk2, sl, key_out, p->hdt);
+        s.hist_valid = false;
+      } else if (lane) {
+        Slab sl{c->slab_bits, c->slab_list, c->slab_count};
+        k_lane<0><<<std::min(blocks, c->lane_grid[0]), 32, 0, c->stream>>>(g, pp, P, Six{}, c->F6, s.cell_end, c->wk2, sl, key_out, p->hdt, blocks);
+        s.hist_valid = false;
+      } else if (pair) {
         Slab sl{c->slab_bits, c->slab_list, c->slab_count};
         k_correct_pair<CORR_NW><<<blocks, B, CorrSmem<CORR_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, sl, key_out, p->hdt);
         s.hist_valid = false;
@@ -655,7 +696,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
       if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
-      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c);
+      if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c); }
     }
     if (c->nranks > 1) {                                           // F:1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
@@ -764,15 +805,22 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
     k_key_hist<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.hist); CKL(c);
   }
   s.keys_valid = false;
-  rc = scan_excl(c, s.hist, s.cell_end, c->ncell + 1, nullptr);
+  const bool lane_layout = c->opt_tile == 3;
+  rc = scan_excl(c, s.hist, lane_layout ? c->cursor : s.cell_end, c->ncell + 1, nullptr);
   if (rc) return rc;
   SortArrays A;
   for (int k = 0; k < 6; k++) { A.src[k] = s.d[k]; A.dst[k] = c->alt[k]; }
   A.id_src = s.id; A.id_dst = c->alt_id;
   // the scatter advances cell_end[c] from the start to the end slot of cell c
-  k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.cell_end, A); CKL(c);
+  if (lane_layout) {   // c->cursor keeps the cell starts (tile base / size of the interleaved layout)
+    CK(cudaMemcpyAsync(s.cell_end, c->cursor, (size_t)(c->ncell + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    k_sort_scatter_lane<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, c->g.mx, s.key, c->cursor, s.cell_end, A); CKL(c);
+  } else {
+    k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.cell_end, A); CKL(c);
+  }
   CK(cudaStreamSynchronize(c->stream));
   s.index_valid = true;
+  s.layout = lane_layout ? 1 : 0;
   // the spare buffer becomes the species' storage and vice versa
   for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
   int* old_id = s.id;
@@ -799,7 +847,7 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value != 4 && value != 8 && value != 16 && value != 32) return fail(MRG_ERR_ARG, "iters must be 4, 8, 16 or 32");
     c->opt_iters = (int)value;
   } else if (n == "tile") {
-    if (value < 0 || value > 2) return fail(MRG_ERR_ARG, "tile must be 0, 1 or 2");
+    if (value < 0 || value > 4) return fail(MRG_ERR_ARG, "tile must be 0..4");
     c->opt_tile = (int)value;
   } else if (n == "fused_keys") {
     c->opt_fused_keys = value != 0;

@@ -66,6 +66,17 @@ __device__ __forceinline__ bool wrap_pos(const GP& g, double& x, double& y, doub
   return flip;
 }
 
+// ---------------------------------------------------------------------------
+// Conservative "might need partbc" test on the high words (integer pipe).  True
+// whenever any of the six comparisons of wrap_pos could be true; false
+// positives only for coordinates within 2^-20 (relative) of a limit.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ bool maybe_wrap(const GP& g, double x, double y, double z) {
+  const int xh = __double2hiint(x), yh = __double2hiint(y), zh = __double2hiint(z);
+  return (xh >= g.xhi_h) | ((unsigned)xh >= (unsigned)g.xlo_h) | (yh >= g.ymax_h) | (yh <= 0) | (zh >= g.zhi_h) |
+         ((unsigned)zh >= (unsigned)g.zlo_h);
+}
+
 // Cell index + weights.  GATHER=true: F:1175-1215, GATHER=false: F:2274-2308
 // (the scatter does not override fyl/fyr in the jp>=my branch).
 //   n0 = node of (il,jl,kl); the 18 nodes are n0 + ix + jy*nx + kz*nxy.
@@ -126,6 +137,21 @@ __device__ __forceinline__ int sort_cell(const GP& g, double x, double y, double
   int ip = __double2loint(__dadd_rd(fma(g.hxi, x, 0.500000001), MRG_TWO52));
   int jp = __double2loint(__dadd_rd(fma(g.hyi, y, 0.000000001), MRG_TWO52));
   int kp = __double2loint(__dadd_rd(fma(g.hzi, z, 0.500000001), MRG_TWO52));
+  ip = min(max(ip, 0), g.mx - 1);
+  jp = min(max(jp, 0), g.my - 1);
+  kp = min(max(kp, 0), g.mz - 1);
+  return ip + g.mx * (jp + g.my * kp);
+}
+
+// Sort key of an UNWRAPPED position: periodic / reflecting images are folded in index space (a sorting
+// hint only, like sort_cell).
+__device__ __forceinline__ int sort_cell_folded(const GP& g, double x, double y, double z) {
+  int ip = __double2loint(__dadd_rd(fma(g.hxi, x, 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
+  int jp = __double2loint(__dadd_rd(fma(g.hyi, y, 0.000000001 + 65536.0), MRG_TWO52)) - 65536;
+  int kp = __double2loint(__dadd_rd(fma(g.hzi, z, 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
+  ip = ip < 0 ? ip + g.mx : (ip >= g.mx ? ip - g.mx : ip);
+  kp = kp < 0 ? kp + g.mz : (kp >= g.mz ? kp - g.mz : kp);
+  jp = jp < 0 ? -1 - jp : (jp >= g.my ? 2 * g.my - 1 - jp : jp);
   ip = min(max(ip, 0), g.mx - 1);
   jp = min(max(jp, 0), g.my - 1);
   kp = min(max(kp, 0), g.mz - 1);

@@ -131,17 +131,6 @@ __device__ __forceinline__ void pstream_next(const ParticleSoA& P, PairStream& s
   }
 }
 
-// ---------------------------------------------------------------------------
-// Conservative "might need partbc" test on the high words (integer pipe).  True
-// whenever any of the six comparisons of wrap_pos could be true; false
-// positives only for coordinates within 2^-20 (relative) of a limit.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ bool maybe_wrap(const GP& g, double x, double y, double z) {
-  const int xh = __double2hiint(x), yh = __double2hiint(y), zh = __double2hiint(z);
-  return (xh >= g.xhi_h) | ((unsigned)xh >= (unsigned)g.xlo_h) | (yh >= g.ymax_h) | (yh <= 0) | (zh >= g.zhi_h) |
-         ((unsigned)zh >= (unsigned)g.zlo_h);
-}
-
 // gather weights of one particle (subset of Stencil, F:1175-1215)
 struct GW {
   int d;              // stencil base node relative to the tile's first base node (valid when in-tile)
@@ -245,20 +234,6 @@ struct CorrSmem {
   static constexpr int ring_d = NW * CORR_NST * PRING_D;
   static constexpr int bytes = (6 * TILE_ROW_D + ring_d) * 8 + (NW * CORR_NST + 1) * 8;
 };
-
-// sort key of an unwrapped position (see above)
-__device__ __forceinline__ int sort_cell_folded(const GP& g, double x, double y, double z) {
-  int ip = __double2loint(__dadd_rd(fma(g.hxi, x, 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
-  int jp = __double2loint(__dadd_rd(fma(g.hyi, y, 0.000000001 + 65536.0), MRG_TWO52)) - 65536;
-  int kp = __double2loint(__dadd_rd(fma(g.hzi, z, 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
-  ip = ip < 0 ? ip + g.mx : (ip >= g.mx ? ip - g.mx : ip);
-  kp = kp < 0 ? kp + g.mz : (kp >= g.mz ? kp - g.mz : kp);
-  jp = jp < 0 ? -1 - jp : (jp >= g.my ? 2 * g.my - 1 - jp : jp);
-  ip = min(max(ip, 0), g.mx - 1);
-  jp = min(max(jp, 0), g.my - 1);
-  kp = min(max(kp, 0), g.mz - 1);
-  return ip + g.mx * (jp + g.my * kp);
-}
 
 struct Slab {                 // drive-kick slab of F:1343-1345
   unsigned* bits; int* list; int* count;

@@ -352,7 +352,7 @@ __device__ __forceinline__ Kick gather_rotate(const GP& g, const PushParams& pp,
   double rx = __dadd_rn(x, __dmul_rn(pp.hdt, vx));          // F:1163-1165
   double ry = __dadd_rn(y, __dmul_rn(pp.hdt, vy));
   double rz = __dadd_rn(z, __dmul_rn(pp.hdt, vz));
-  wrap_pos(g, rx, ry, rz);                                    // partbcEST, F:1168
+  if (__any_sync(FULL, maybe_wrap(g, rx, ry, rz))) wrap_pos(g, rx, ry, rz);   // partbcEST, F:1168 (whole warp calls this)
   Stencil s;
   make_stencil<true>(g, rx, ry, rz, s);
   double f[6];
@@ -448,6 +448,13 @@ __device__ __forceinline__ void warp_wk_store(double wx, double wh, double* __re
   }
 }
 
+// wkix/wkih of the warp -> two global accumulators (zeroed by the host before the launch)
+__device__ __forceinline__ void warp_wk_atomic(double wx, double wh, double* __restrict__ acc2) {
+  wx = warp_sum(wx);
+  wh = warp_sum(wh);
+  if ((threadIdx.x & 31) == 0 && (wx != 0.0 || wh != 0.0)) { atomicAdd(acc2, wx); atomicAdd(acc2 + 1, wh); }
+}
+
 // ---------------------------------------------------------------------------
 // Predictor on TMA-staged tiles.
 // ---------------------------------------------------------------------------
@@ -485,6 +492,7 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     for (int n = 0; n < 18; n++) acc[n] = 0.0;
     int cur = -1;
     const double ah = pp.aimpl * pp.hh, hh2 = 0.5 * pp.hh;
+    const P6 safe = {0.0, 0.5 * g.hy, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
@@ -493,24 +501,20 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       {
         double qvy[8], wxz[9];
         int key = -1;
-        if (valid) {
-          const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
-          wx += k.wx; wh += k.wh;
-          Predicted o;
-          o.vxj = fma(ah, k.dvx, c.vx);                       // F:1300-1302
-          o.vyj = fma(ah, k.dvy, c.vy);
-          o.vzj = fma(ah, k.dvz, c.vz);
-          o.rx = fma(pp.adt, fma(hh2, k.dvx, c.vx), c.x);     // F:1304-1306
-          o.ry = fma(pp.adt, fma(hh2, k.dvy, c.vy), c.y);
-          o.rz = fma(pp.adt, fma(hh2, k.dvz, c.vz), c.z);
+        if (!valid) c = safe;                                 // idle lanes push a harmless copy (results masked)
+        const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
+        Predicted o;
+        o.vxj = fma(ah, k.dvx, c.vx);                         // F:1300-1302
+        o.vyj = fma(ah, k.dvy, c.vy);
+        o.vzj = fma(ah, k.dvz, c.vz);
+        o.rx = fma(pp.adt, fma(hh2, k.dvx, c.vx), c.x);       // F:1304-1306
+        o.ry = fma(pp.adt, fma(hh2, k.dvy, c.vy), c.y);
+        o.rz = fma(pp.adt, fma(hh2, k.dvz, c.vz), c.z);
+        if (__any_sync(FULL, maybe_wrap(g, o.rx, o.ry, o.rz))) {
           if (wrap_pos(g, o.rx, o.ry, o.rz)) o.vyj = -o.vyj;  // partbc, F:1375
-          key = scatter_factors(g, pp.qmult, o, qvy, wxz);
-        } else {
-#pragma unroll
-          for (int n = 0; n < 8; n++) qvy[n] = 0.0;
-#pragma unroll
-          for (int n = 0; n < 9; n++) wxz[n] = 0.0;
         }
+        key = scatter_factors(g, valid ? pp.qmult : 0.0, o, qvy, wxz);
+        if (valid) { wx += k.wx; wh += k.wh; } else key = -1;
         park_factors(W, Q, lane, qvy, wxz, key);
       }
       __syncwarp();
@@ -530,7 +534,7 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       }
     }
   }
-  warp_wk_store(wx, wh, wk_partial, PR_WARPS);
+  warp_wk_atomic(wx, wh, wk_partial);
 }
 
 // ---------------------------------------------------------------------------
@@ -560,6 +564,7 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     const double hh2 = 0.5 * pp.hh;
+    const P6 safe = {0.0, 0.5 * g.hy, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
@@ -567,16 +572,19 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       const int p = st.a + 32 * it + lane;
       const bool valid = p < st.b;
       int kcell = -1;
-      if (valid) {
-        const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
-        wx += k.wx; wh += k.wh;
-        double x = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x);    // F:1289-1291
-        double y = fma(pp.dt, fma(hh2, k.dvy, c.vy), c.y);
-        double z = fma(pp.dt, fma(hh2, k.dvz, c.vz), c.z);
-        const double vx = fma(pp.hh, k.dvx, c.vx);            // F:1293-1295
-        double vy = fma(pp.hh, k.dvy, c.vy);
-        const double vz = fma(pp.hh, k.dvz, c.vz);
+      if (!valid) c = safe;                                   // idle lanes push a harmless copy (nothing is stored)
+      const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
+      double x = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x);      // F:1289-1291
+      double y = fma(pp.dt, fma(hh2, k.dvy, c.vy), c.y);
+      double z = fma(pp.dt, fma(hh2, k.dvz, c.vz), c.z);
+      const double vx = fma(pp.hh, k.dvx, c.vx);              // F:1293-1295
+      double vy = fma(pp.hh, k.dvy, c.vy);
+      const double vz = fma(pp.hh, k.dvz, c.vz);
+      if (__any_sync(FULL, maybe_wrap(g, x, y, z))) {
         if (wrap_pos(g, x, y, z)) vy = -vy;                   // partbc, F:1337
+      }
+      if (valid) {
+        wx += k.wx; wh += k.wh;
         __stcs(P.x + p, x); __stcs(P.y + p, y); __stcs(P.z + p, z);
         __stcs(P.vx + p, vx); __stcs(P.vy + p, vy); __stcs(P.vz + p, vz);
         if (pp.drive_on) {
@@ -587,9 +595,7 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
           }
         }
         if (key_out) {
-          double sx = fma(lookahead, vx, x), sy = fma(lookahead, vy, y), sz = fma(lookahead, vz, z);
-          wrap_pos(g, sx, sy, sz);
-          kcell = sort_cell(g, sx, sy, sz);
+          kcell = sort_cell_folded(g, fma(lookahead, vx, x), fma(lookahead, vy, y), fma(lookahead, vz, z));
           key_out[p] = kcell;
         }
       }
@@ -603,7 +609,7 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       __syncwarp();
     }
   }
-  warp_wk_store(wx, wh, wk_partial, PR_WARPS);
+  warp_wk_atomic(wx, wh, wk_partial);
 }
 
 }  // namespace mrg

@@ -8,6 +8,8 @@ at the thermal speed); deposited moments <= 1e-10 relative L2 (atomic
 summation order differs); prepared fields and the synthetic loader are
 bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -33,7 +35,10 @@ def params_of(mrg, p, drive_on=True, ifil=(1, 1, 1)):
 
 
 def new_ctx(mrg, p, **kw):
-    return mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, **kw)
+    ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, **kw)
+    if os.environ.get("MRG_TEST_TILE"):      # run the whole suite on another kernel family
+        ctx.set_option("tile", int(os.environ["MRG_TEST_TILE"]))
+    return ctx
 
 
 @pytest.fixture(scope="module")
@@ -63,7 +68,7 @@ def test_prepared_fields_bit_exact(mrg, case, ifil):
 
 # ---- C1: corrector ------------------------------------------------------------
 @pytest.mark.parametrize("ksp", [1, 2])
-@pytest.mark.parametrize("sort,tile", [(False, 2), (True, 2), (True, 1), (True, 0)])
+@pytest.mark.parametrize("sort,tile", [(False, 2), (True, 2), (True, 1), (True, 0), (True, 3), ("adt", 3), (True, 4), ("adt", 4)])
 def test_corrector_particles(mrg, case, ksp, sort, tile):
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
@@ -75,7 +80,7 @@ def test_corrector_particles(mrg, case, ksp, sort, tile):
     ctx.set_fields(f12)
     ctx.upload(ksp, *sp[ksp])
     if sort:
-        ctx.sort(ksp, p.hdt)
+        ctx.sort(ksp, p.adt * 3 if sort == "adt" else p.hdt)
     wkix, wkih, st_gpu = ctx.fulmov(ksp, q, w, 0, params_of(mrg, p), ranfb)
     got = ctx.download(ksp, len(ref[0]))
     assert U.particle_err(got, ref, p.hx, U.vth(ksp)) < PTOL
@@ -90,12 +95,14 @@ def test_corrector_particles(mrg, case, ksp, sort, tile):
 @pytest.mark.parametrize("deposit,iters,sort,tile", [(0, 8, False, 0), (1, 8, False, 0), (1, 8, True, 0), (2, 4, True, 0),
                                                      (2, 8, True, 0), (2, 8, False, 0), (2, 32, True, 0),
                                                      (2, 8, True, 1), (2, 8, "adt", 1), (2, 8, "stale", 1),
-                                                     (2, 8, True, 2), (2, 8, "adt", 2), (2, 8, "stale", 2)])
+                                                     (2, 8, True, 2), (2, 8, "adt", 2), (2, 8, "stale", 2),
+                                                     (2, 8, True, 3), (2, 8, "adt", 3), (2, 8, "stale", 3),
+                                                     (2, 8, True, 4), (2, 8, "adt", 4), (2, 8, "stale", 4)])
 def test_predictor_moments(mrg, case, ksp, deposit, iters, sort, tile):
     """sort: False = load order; True = sorted by the gather cell (x + hdt*v); "adt" = sorted by another
     key (many particles gather outside their tile); "stale" = sorted, then moved by a corrector step
     without re-sorting.  tile=1 runs the TMA-staged shared-memory kernels, tile=2 the two-particles-per-thread
-    kernels (the default)."""
+    kernels, tile=3 the register-stationary lane-pair kernels on the interleaved tile layout."""
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
     orig = [a.copy() for a in sp[ksp]]
@@ -180,7 +187,9 @@ def test_step_sequence(mrg, case):
 
 
 # ---- C4: seams, walls, cell boundaries ----------------------------------------------
-def test_edge_particles(mrg, case):
+@pytest.mark.parametrize("tile", [None, 1, 3, 4])
+def test_edge_particles(mrg, case, tile):
+    """tile=None: load order (any-order kernels); 1 / 3: sorted, tiled / lane-pair kernels"""
     p, sp, ranfb, f12, a6 = case
     rng = np.random.default_rng(42)
     n = 4096
@@ -208,6 +217,9 @@ def test_edge_particles(mrg, case):
         ctx = new_ctx(mrg, p)
         ctx.set_fields(f12)
         ctx.upload(ksp, *arrs)
+        if tile is not None:
+            ctx.set_option("tile", tile)
+            ctx.sort(ksp, p.hdt)
         ctx.fulmov(ksp, q, w, 1, params_of(mrg, p))
         raw = ctx.moments(ksp, folded=False)
         for c in range(4):
@@ -217,6 +229,46 @@ def test_edge_particles(mrg, case):
         assert U.particle_err(got, ref, p.hx, 0.3) < PTOL
         # wall reflections flipped vy exactly like partbc
         assert np.array_equal(np.sign(got[4][32:40]), np.sign(ref[4][32:40]))
+        ctx.close()
+
+
+# ---- lane-pair kernels on a grid whose x size is not a multiple of the 16-cell tile --------------
+@pytest.mark.parametrize("tile", [3, 4])
+@pytest.mark.parametrize("mx,ppc", [(40, 7), (17, 33), (8, 70)])
+def test_lane_kernels_ragged_tiles(mrg, mx, ppc, tile):
+    p = U.make_parm(mx, 6, 8)
+    sp, ranfb = U.load_species(p, ppc)
+    f12 = U.smooth_fields(p, seed=11)
+    a6 = O.field_prep(p, f12)
+    for ksp in (1, 2):
+        q, w = U.QSPEC[ksp], U.WSPEC[ksp]
+        n = len(sp[ksp][0])
+        ctx = new_ctx(mrg, p)
+        ctx.set_option("tile", tile)
+        ctx.set_fields(f12)
+        ctx.upload(ksp, *sp[ksp])
+        ctx.sort(ksp, p.hdt)
+        r = O.fulmov(p, a6, *[a.copy() for a in sp[ksp]], q, w, 1, nranks=1, want_raw=True)
+        wkix, wkih, _ = ctx.fulmov(ksp, q, w, 1, params_of(mrg, p))
+        raw = ctx.moments(ksp, folded=False)
+        for c in range(4):
+            assert U.rel_l2(raw[c], r["raw"][c]) < MTOL, c
+        assert abs(raw[3].sum() - q * n) < 1e-9 * n
+        assert abs(wkix - r["wkix"]) < MTOL * abs(r["wkix"])
+        ref = [a.copy() for a in sp[ksp]]
+        st = np.array([ranfb], dtype=np.int32)
+        r0 = O.fulmov(p, a6, *ref, q, w, 0, nranks=1, ranfb=st)
+        _, _, st_gpu = ctx.fulmov(ksp, q, w, 0, params_of(mrg, p), ranfb)
+        got = ctx.download(ksp, n)
+        assert U.particle_err(got, ref, p.hx, U.vth(ksp)) < PTOL
+        assert st_gpu == int(r0["ranfb"][0])
+        # the keys the corrector emitted drive the next sort; a second step stays on the oracle
+        ctx.sort(ksp, p.hdt)
+        r = O.fulmov(p, a6, *[a.copy() for a in ref], q, w, 1, nranks=1, want_raw=True)
+        ctx.fulmov(ksp, q, w, 1, params_of(mrg, p))
+        raw = ctx.moments(ksp, folded=False)
+        for c in range(4):
+            assert U.rel_l2(raw[c], r["raw"][c]) < MTOL, (c, "step 2")
         ctx.close()
 
 

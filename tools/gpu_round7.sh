@@ -1,0 +1,18 @@
+#!/bin/bash
+# default (tile=1) kernels after the trims: parity, bench (sort cadence variants)
+mkdir -p gpurun_out
+cd "$(dirname "$0")/.."
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -6 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e "$@" > gpurun_out/bench_main.log 2>&1
+timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e --sort-every-ions 4 "$@" > gpurun_out/bench_ions4.log 2>&1
+timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e --sort-every-ions 8 "$@" > gpurun_out/bench_ions8.log 2>&1
+python - <<'PY'
+import glob, json
+for f in sorted(glob.glob("gpurun_out/bench_*.log")):
+    l = [x for x in open(f) if x.startswith("{")]
+    if not l:
+        print(f, "NO RESULT", open(f).read()[-300:]); continue
+    d = json.loads(l[-1]); r = d["roofline"]
+    print("%-40s ms/step %.2f pred %.2f corr %.2f clocks %s" % (f, d["ms_per_step"], r["predictor"]["ms_per_launch"], r["corrector"]["ms_per_launch"], d["clocks"]["sm_mhz"]))
+PY
