@@ -141,10 +141,17 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                register accumulation + warp pre-reduction (default)
  *   "tile"       1 (default) = after mrg_sort, particle passes run on
  *                TMA-staged shared-memory field tiles with shared-memory
- *                moment accumulators; 0 = gather through L1 only
- *   "fused_keys" 1 (default) = the tiled corrector also emits the next sort
- *                keys (cell of x + hdt*v), so mrg_sort(ksp, hdt) skips its
- *                key pass
+ *                moment accumulators; 0 = gather through L1 only; 2 = two
+ *                particles per thread; 3 = register-stationary lane pairs on
+ *                an interleaved tile layout; 4 = quad-cooperative polynomial
+ *                gather (2-4 are experimental)
+ *   "fused_sort" 1 (default) = the tiled predictor emits the cell keys of the
+ *                next order and the tiled corrector writes the updated
+ *                particles straight into that order, so mrg_sort(ksp, hdt)
+ *                after a predictor+corrector pair returns at once
+ *   "fused_keys" 1 (default) = a tiled corrector that does not scatter emits
+ *                the next sort keys (cell of x + hdt*v), so mrg_sort(ksp, hdt)
+ *                skips its key pass
  *   "iters"      particles per warp / 32 of the untiled predictor (4..32)
  *   "group_min"  smallest stray group (particles) that is pre-reduced        */
 int mrg_set_option(mrg_ctx* ctx, const char* name, int64_t value);

@@ -100,6 +100,11 @@ struct Species {
   // cell index of the current slot order (built by mrg_sort): cell_end[c] = end slot of cell c
   int* cell_end = nullptr;
   bool index_valid = false;
+  // fused sort: keys of the NEXT order written by the tiled predictor (+ their histogram in hist); the tiled
+  // corrector scatters by them into the spare buffers, so the order is fresh without a sort pass
+  bool prekeys_valid = false;
+  bool fresh = false; double fresh_lookahead = 0.0;
+  int* cell_end2 = nullptr;
   int layout = 0;              // 0 = slots in cell order; 1 = 16-cell tiles stored as 16 interleaved runs (mrg_lane.cuh)
   // next-sort keys emitted by the corrector (fused_keys) + their histogram
   int* key = nullptr; long long key_cap = 0;
@@ -156,7 +161,7 @@ struct mrg_ctx {
   void* comm = nullptr;
   // options / counters
   int lane_grid[3] = {148 * 8, 148 * 8, 148 * 8};   // persistent warps of k_lane<0>, k_lane<1>, k_lane_deposit (SMs x resident CTAs)
-  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1;
+  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1;
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -211,8 +216,11 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   s.index_valid = false;
   s.layout = 0;
   s.keys_valid = false;
+  s.prekeys_valid = false;
+  s.fresh = false;
   if (!s.cell_end) {
     CK(cudaMalloc((void**)&s.cell_end, (size_t)(c->ncell + 1) * sizeof(int)));
+    CK(cudaMalloc((void**)&s.cell_end2, (size_t)(c->ncell + 1) * sizeof(int)));
     CK(cudaMalloc((void**)&s.hist, (size_t)(c->ncell + 1) * sizeof(int)));
   }
   if (!s.M4) {
@@ -389,7 +397,7 @@ int mrg_destroy(mrg_ctx* c) {
   cudaFree(c->F6); cudaFree(c->alt_id);
   for (auto& s : c->sp) {
     for (int k = 0; k < 6; k++) cudaFree(s.d[k]);
-    cudaFree(s.id); cudaFree(s.M4); cudaFree(s.cell_end); cudaFree(s.key); cudaFree(s.hist);
+    cudaFree(s.id); cudaFree(s.M4); cudaFree(s.cell_end); cudaFree(s.cell_end2); cudaFree(s.key); cudaFree(s.hist);
     for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
   }
   cudaFree(c->wk_partial); cudaFree(c->wk2); cudaFree(c->sort_key); cudaFree(c->hist); cudaFree(c->cursor);
@@ -592,6 +600,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       const bool quad = c->opt_tile == 4 && s.index_valid && s.layout == 0;
       const bool tiled = !lane && !quad && c->opt_tile && c->opt_tile < 3 && c->opt_deposit == 2 && s.index_valid && s.layout == 0;
       const bool pair = tiled && c->opt_tile == 2;
+      s.prekeys_valid = false;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
       if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz;
@@ -611,7 +620,18 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         k_lane_deposit<<<std::min(blocks, c->lane_grid[2]), 32, 0, c->stream>>>(g, qmult, Q, s.M4, s.cell_end, blocks);
       }
       else if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
-      else if (tiled) k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm);
+      else if (tiled) {
+        int* prekey = nullptr;
+        if (c->opt_fused_sort) {   // keys + histogram of the next order; the corrector scatters by them
+          rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
+          if (rc) return rc;
+          CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+          prekey = s.key;
+        }
+        k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+        s.prekeys_valid = prekey != nullptr;
+        s.keys_valid = false;
+      }
       else if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
       else if (iters == 1) k_predict_run<1><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
       else if (iters == 4) k_predict_run<4><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
@@ -653,6 +673,8 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     }
     CK(cudaMemsetAsync(c->wk2, 0, 2 * sizeof(double), c->stream));
     s.keys_valid = false;
+    s.fresh = false;
+    bool fused_scatter = false;
     if (s.n > 0) {
       const bool lane = c->opt_tile == 3 && s.index_valid && s.layout == 1;
       const bool quad = c->opt_tile == 4 && s.index_valid && s.layout == 0;
@@ -667,7 +689,18 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       if (rc) return rc;
       if (tiled && !pair) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
       int* key_out = nullptr;
-      if ((tiled || lane || quad) && c->opt_fused_keys) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
+      // fused sort: the tiled predictor left the keys of the next order in s.key and their histogram in s.hist
+      const bool scatter = tiled && !pair && s.prekeys_valid && c->opt_fused_sort;
+      SortArrays D{};
+      if (scatter) {   // cell starts of the next order; the kernel advances them to the ends
+        rc = ensure_alt(c, s.cap, true);
+        if (rc) return rc;
+        rc = scan_excl(c, s.hist, s.cell_end2, c->ncell + 1, nullptr);
+        if (rc) return rc;
+        for (int k = 0; k < 6; k++) { D.src[k] = s.d[k]; D.dst[k] = c->alt[k]; }
+        D.id_src = s.id; D.id_dst = c->alt_id;
+      }
+      if ((tiled || lane || quad) && c->opt_fused_keys && !scatter) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
         rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
         if (rc) return rc;
         if (!pair && !lane && !quad) CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
@@ -688,14 +721,28 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         s.hist_valid = false;
       } else if (tiled) {
         k_correct_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, c->slab_bits, c->slab_list,
-                                                    c->slab_count, key_out, s.hist, p->hdt);
-        s.hist_valid = true;
+                                                    c->slab_count, key_out, s.hist, p->hdt, scatter ? s.key : nullptr,
+                                                    s.cell_end2, D);
+        s.hist_valid = !scatter;
+        fused_scatter = scatter;
       } else {
         k_correct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, c->wk_partial, c->slab_bits, c->slab_list, c->slab_count);
       }
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
       if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
+      if (fused_scatter) {   // the spare buffers now hold the updated particles in the next order
+        for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
+        int* old_id = s.id;
+        s.id = c->alt_id;
+        std::swap(s.cap, c->alt_cap);
+        if (old_id) c->alt_id = old_id;
+        else { c->alt_id = nullptr; CK(cudaMalloc((void**)&c->alt_id, (size_t)c->alt_cap * sizeof(int))); }
+        std::swap(s.cell_end, s.cell_end2);
+        s.fresh = true;
+        s.fresh_lookahead = p->hdt;
+      }
+      s.prekeys_valid = false;
       if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c); }
     }
     if (c->nranks > 1) {                                           // F:1312-1315
@@ -712,7 +759,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         k_popc<<<grid_for(nwords, 256), 256, 0, c->stream>>>(c->slab_bits, nwords, c->slab_words); CKL(c);
         rc = scan_excl(c, c->slab_words, c->slab_words, nwords, nullptr);
         if (rc) return rc;
-        k_kick<<<grid_for(slab_n, 256), 256, 0, c->stream>>>(g, P, c->F6, c->slab_bits, c->slab_words, c->slab_list,
+        k_kick<<<grid_for(slab_n, 256), 256, 0, c->stream>>>(g, soa(s), c->F6, c->slab_bits, c->slab_words, c->slab_list,
                                                               c->slab_count, (unsigned)*ranfb, p->Ez00, p->ycent1,
                                                               p->ycent2, 0.05 * g.ymax); CKL(c);
         *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)slab_n);
@@ -792,6 +839,9 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
   CK(cudaSetDevice(c->device));
   Species& s = c->sp[ksp - 1];
   if (s.n == 0) return MRG_OK;
+  if (s.fresh && s.index_valid && s.fresh_lookahead == lookahead) return MRG_OK;   // the fused sort of the last corrector already produced this order
+  s.prekeys_valid = false;
+  s.fresh = false;
   rc = ensure_alt(c, s.cap, true);
   if (rc) return rc;
   rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
@@ -851,6 +901,8 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     c->opt_tile = (int)value;
   } else if (n == "fused_keys") {
     c->opt_fused_keys = value != 0;
+  } else if (n == "fused_sort") {
+    c->opt_fused_sort = value != 0;
   } else if (n == "group_min") {
     if (value < 1 || value > 9) return fail(MRG_ERR_ARG, "group_min must be in 1..9 (particles per sub-iteration group)");
     c->opt_group_min = (int)value;

@@ -32,6 +32,9 @@ constexpr unsigned FULL = 0xffffffffu;
 #ifndef MRG_PRED_MINB
 #define MRG_PRED_MINB 4
 #endif
+#ifndef MRG_PRED_SMEM_TILE
+#define MRG_PRED_SMEM_TILE 0
+#endif
 #ifndef MRG_CORR_MINB
 #define MRG_CORR_MINB 5
 #endif
@@ -448,6 +451,22 @@ __device__ __forceinline__ void warp_wk_store(double wx, double wh, double* __re
   }
 }
 
+// Rank of the lane inside its run of EQUAL, CONTIGUOUS keys among the valid lanes (cell-sorted lanes carry
+// mostly equal keys; equal keys in separate runs are simply claimed separately).  Returns the rank, the
+// run length in `count` and whether the lane heads its run.  Valid lanes must form a prefix of the warp.
+__device__ __forceinline__ int run_rank(int key, bool valid, int lane, int& count, bool& head) {
+  const int prev = __shfl_up_sync(FULL, key, 1);
+  head = valid && (lane == 0 || key != prev);
+  const unsigned heads = __ballot_sync(FULL, head);
+  const unsigned vmask = __ballot_sync(FULL, valid);
+  const unsigned below = heads & ((2u << lane) - 1u);          // heads at or below this lane
+  const int start = 31 - __clz(below | 1u);
+  const unsigned above = heads & ~((2u << lane) - 1u);         // heads above this lane
+  const int end = above ? (__ffs(above) - 1) : __popc(vmask);  // first lane of the next run / number of valid lanes
+  count = end - start;
+  return lane - start;
+}
+
 // wkix/wkih of the warp -> two global accumulators (zeroed by the host before the launch)
 __device__ __forceinline__ void warp_wk_atomic(double wx, double wh, double* __restrict__ acc2) {
   wx = warp_sum(wx);
@@ -462,7 +481,8 @@ constexpr int PRED_SMEM_BYTES = (6 * TILE_ROW_D + 6 * TILE_ACC_D + PR_WARPS * (3
                                 (PR_WARPS * NSTAGE + 1) * 8;
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_PRED_MINB)
 k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
-               const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min) {
+               const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min,
+               int* __restrict__ prekey, int* __restrict__ prehist) {
   // dynamic shared memory (PRED_SMEM_BYTES > 48 KB static limit), carved up by hand
   extern __shared__ __align__(128) double smem_dyn[];
   double* sF = smem_dyn;                                       // [6][TILE_ROW_D]      staged fields
@@ -480,13 +500,17 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     Stream st;
     stream_open(P, t, w, PR_WARPS, lane, sRing + w * (NSTAGE * 6 * STAGE_D), sBar + w * NSTAGE, st);   // particles in flight during the field staging
     if (threadIdx.x == 0) mbar_init(&bar, 1);
+#if MRG_PRED_SMEM_TILE
     for (int e = threadIdx.x; e < 6 * TILE_ACC_D; e += blockDim.x) sM[e] = 0.0;
+#endif
     __syncthreads();
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     double* W = smW + w * (32 * PR_W_STRIDE);
     double* Q = smQ + w * 256;
-    const Target<true> tg(g, M4, sM, t.n0_first, t.ncell, lane);
+    // MRG_PRED_SMEM_TILE = 0: cell-run totals go straight to global memory with red.global.add.f64 (fire and
+    // forget; shared-memory fp64 atomics are compare-and-swap loops on sm_100a)
+    const Target<(MRG_PRED_SMEM_TILE != 0)> tg(g, M4, sM, t.n0_first, t.ncell, lane);
     double acc[18];
 #pragma unroll
     for (int n = 0; n < 18; n++) acc[n] = 0.0;
@@ -516,12 +540,27 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
         key = scatter_factors(g, valid ? pp.qmult : 0.0, o, qvy, wxz);
         if (valid) { wx += k.wx; wh += k.wh; } else key = -1;
         park_factors(W, Q, lane, qvy, wxz, key);
+        if (prekey) {
+          // Order of the NEXT step, decided one pass early: cell of x' + hdt*v' with x', v' from this
+          // pass' dv (the corrector's dv differs only through the field update, so nearly every key is
+          // exact; a key is a sorting hint and never changes a result).  The corrector scatters by it.
+          const double xn = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x), un = fma(pp.hh, k.dvx, c.vx);
+          const double yn = fma(pp.dt, fma(hh2, k.dvy, c.vy), c.y), vn = fma(pp.hh, k.dvy, c.vy);
+          const double zn = fma(pp.dt, fma(hh2, k.dvz, c.vz), c.z), wn = fma(pp.hh, k.dvz, c.vz);
+          const int kcell = sort_cell_folded(g, fma(pp.hdt, un, xn), fma(pp.hdt, vn, yn), fma(pp.hdt, wn, zn));
+          int cnt;
+          bool head;
+          run_rank(kcell, valid, lane, cnt, head);
+          if (valid) prekey[st.a + 32 * it + lane] = kcell;
+          if (head) atomicAdd(prehist + kcell, cnt);
+        }
       }
       __syncwarp();
-      deposit_parked<true>(W, Q, lane, acc, cur, group_min, tg);
+      deposit_parked<(MRG_PRED_SMEM_TILE != 0)>(W, Q, lane, acc, cur, group_min, tg);
       __syncwarp();
     }
-    if (cur >= 0) flush_quad<true>(acc, cur, tg);
+    if (cur >= 0) flush_quad<(MRG_PRED_SMEM_TILE != 0)>(acc, cur, tg);
+#if MRG_PRED_SMEM_TILE
     __syncthreads();
     // flush the accumulator tile: 4 moments of a node = one 32-byte sector
     const int nodes = t.ncell + 2;
@@ -533,6 +572,7 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
         atomicAdd(M4 + 4 * ((size_t)t.n0_first + (size_t)jy * g.nx + (size_t)kz * g.nxy) + rem, v);
       }
     }
+#endif
   }
   warp_wk_atomic(wx, wh, wk_partial);
 }
@@ -547,7 +587,8 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_CORR_MINB)
 k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, const int* __restrict__ cell_end,
                double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits, int* __restrict__ slab_list,
-               int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead) {
+               int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead,
+               const int* __restrict__ prekey, int* __restrict__ cursor, SortArrays D) {
   __shared__ __align__(128) double sF[6 * TILE_ROW_D];
   __shared__ __align__(16) double sRing[PR_WARPS][NSTAGE * 6 * STAGE_D];
   __shared__ __align__(8) unsigned long long sBar[PR_WARPS][NSTAGE];
@@ -565,6 +606,19 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     mbar_wait(&bar, 0);
     const double hh2 = 0.5 * pp.hh;
     const P6 safe = {0.0, 0.5 * g.hy, 0.0, 0.0, 0.0, 0.0};
+    // Fused cell sort, software-pipelined so that neither the key load nor the slot claim (an atomic with
+    // a return value) is waited for: keys are loaded two iterations ahead, slots claimed one ahead.
+    int pk1 = 0, pk2 = 0;        // keys of iterations it + 1, it + 2
+    int cb = 0, crk = 0;         // claim of the current iteration: base (in the run's head lane), rank in the run
+    if (prekey) {
+      int pk0 = 0;
+      if (st.a + lane < st.b) pk0 = __ldcs(prekey + st.a + lane);
+      if (st.a + 32 + lane < st.b) pk1 = __ldcs(prekey + st.a + 32 + lane);
+      int cnt;
+      bool head;
+      crk = run_rank(pk0, st.a + lane < st.b, lane, cnt, head);
+      if (head) cb = atomicAdd(cursor + pk0, cnt);
+    }
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
@@ -572,6 +626,16 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       const int p = st.a + 32 * it + lane;
       const bool valid = p < st.b;
       int kcell = -1;
+      int idv = p;
+      if (valid && P.id) idv = P.id[p];
+      int nb = 0, nrk = 0;
+      if (prekey) {                                           // claim for it + 1, key for it + 2
+        if (p + 64 < st.b) pk2 = __ldcs(prekey + p + 64);
+        int cnt;
+        bool head;
+        nrk = run_rank(pk1, p + 32 < st.b, lane, cnt, head);
+        if (head) nb = atomicAdd(cursor + pk1, cnt);
+      }
       if (!valid) c = safe;                                   // idle lanes push a harmless copy (nothing is stored)
       const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
       double x = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x);      // F:1289-1291
@@ -583,15 +647,26 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       if (__any_sync(FULL, maybe_wrap(g, x, y, z))) {
         if (wrap_pos(g, x, y, z)) vy = -vy;                   // partbc, F:1337
       }
+      int d = p;                                              // slot the updated particle is written to
+      if (prekey) {
+        d = __shfl_sync(FULL, cb, lane - crk) + crk;          // claimed one iteration ago
+        cb = nb; crk = nrk; pk1 = pk2;
+      }
       if (valid) {
         wx += k.wx; wh += k.wh;
-        __stcs(P.x + p, x); __stcs(P.y + p, y); __stcs(P.z + p, z);
-        __stcs(P.vx + p, vx); __stcs(P.vy + p, vy); __stcs(P.vz + p, vz);
+        const int id = idv;
+        if (prekey) {
+          __stcs(D.dst[0] + d, x); __stcs(D.dst[1] + d, y); __stcs(D.dst[2] + d, z);
+          __stcs(D.dst[3] + d, vx); __stcs(D.dst[4] + d, vy); __stcs(D.dst[5] + d, vz);
+          D.id_dst[d] = id;
+        } else {
+          __stcs(P.x + p, x); __stcs(P.y + p, y); __stcs(P.z + p, z);
+          __stcs(P.vx + p, vx); __stcs(P.vy + p, vy); __stcs(P.vz + p, vz);
+        }
         if (pp.drive_on) {
           if ((fabs(z - pp.zcent) < pp.zw) && ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw))) {
-            const int id = P.id ? P.id[p] : p;
             atomicOr(slab_bits + (id >> 5), 1u << (id & 31));
-            slab_list[atomicAdd(slab_count, 1)] = p;
+            slab_list[atomicAdd(slab_count, 1)] = d;
           }
         }
         if (key_out) {

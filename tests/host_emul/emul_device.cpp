@@ -25,6 +25,7 @@ static inline double __dadd_rd(double a, double b) {
   return r;
 }
 static inline int __double2loint(double d) { int64_t u; std::memcpy(&u, &d, 8); return (int)(uint32_t)(u & 0xffffffffu); }
+static inline int __double2hiint(double d) { int64_t u; std::memcpy(&u, &d, 8); return (int)(u >> 32); }
 static inline long long __double_as_longlong(double d) { long long u; std::memcpy(&u, &d, 8); return u; }
 static inline double2 __ldg(const double2* p) { return *p; }
 static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }

@@ -1,12 +1,15 @@
 #!/bin/bash
-# default (tile=1) kernels after the trims: parity, bench (sort cadence variants)
+# parity + bench of the product library and of every variants/libmrg_*.so (default options)
 mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -6 gpurun_out/pytest_gpu.log
+tail -4 gpurun_out/pytest_gpu.log
 timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e "$@" > gpurun_out/bench_main.log 2>&1
-timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e --sort-every-ions 4 "$@" > gpurun_out/bench_ions4.log 2>&1
-timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e --sort-every-ions 8 "$@" > gpurun_out/bench_ions8.log 2>&1
+for v in variants/libmrg_*.so; do
+  [ -f "$v" ] || continue
+  n=$(basename $v .so)
+  MRG_LIB=$PWD/$v timeout 600 python bench.py --steps 8 --warmup 4 --no-cpu --no-e2e "$@" > gpurun_out/bench_$n.log 2>&1
+done
 python - <<'PY'
 import glob, json
 for f in sorted(glob.glob("gpurun_out/bench_*.log")):
@@ -16,9 +19,3 @@ for f in sorted(glob.glob("gpurun_out/bench_*.log")):
     d = json.loads(l[-1]); r = d["roofline"]
     print("%-40s ms/step %.2f pred %.2f corr %.2f clocks %s" % (f, d["ms_per_step"], r["predictor"]["ms_per_launch"], r["corrector"]["ms_per_launch"], d["clocks"]["sm_mhz"]))
 PY
-if [ -n "$MRG_NCU" ]; then
-for k in k_predict_tile k_correct_tile; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"^$k" -s 5 -c 1 \
-    -o gpurun_out/prof2_$k -f python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e > gpurun_out/ncu2_$k.log 2>&1
-done
-fi
