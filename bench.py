@@ -290,8 +290,15 @@ def run_ours(args):
     dominant = kn[0] if tp >= tc else kn[1]
     ach = gb_pred if tp >= tc else gb_corr
     step_bytes = 2 * (bytes_pred + bytes_corr)
+    traffic = None                                       # measured DRAM bytes per launch of the dominant kernel (one ncu capture)
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if tj.get("grid") == [mx, my, mz] and tj.get("ppc") == ppc and tj.get("n_gpus") == world and args.fused_sort:
+            traffic = tj.get(dominant)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "predictor": {"ms_per_launch": tp, "algorithmic_bytes": bytes_pred, "gbs": gb_pred, "frac": gb_pred / peak},
                 "corrector": {"ms_per_launch": tc, "algorithmic_bytes": bytes_corr, "gbs": gb_corr, "frac": gb_corr / peak},
                 "whole_step": {"algorithmic_bytes": step_bytes, "gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 if world == 1 else None,

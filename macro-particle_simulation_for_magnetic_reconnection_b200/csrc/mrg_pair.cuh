@@ -384,9 +384,9 @@ __device__ __forceinline__ void predict_factors(const GP& g, const PushParams& p
 }
 
 // phase B over `nsub` sub-iterations of 8 parked slots; same contract as deposit_parked
-template <int NSUB>
+template <int NSUB, bool TILED>
 __device__ __forceinline__ void deposit_parked64(const double* W, const double* Q, int lane, double* acc, int& cur,
-                                                 const Target<true>& tg) {
+                                                 const Target<TILED>& tg) {
   const int q = lane & 3, pl = lane >> 2;
 #pragma unroll 1
   for (int sub = 0; sub < NSUB; sub++) {
@@ -412,7 +412,7 @@ __device__ __forceinline__ void deposit_parked64(const double* W, const double* 
         const unsigned rest = __ballot_sync(FULL, !done);
         if (rest == 0u) break;
         const int kk = __shfl_sync(FULL, key, __ffs(rest) - 1);
-        if (cur >= 0) flush_quad<true>(acc, cur, tg);
+        if (cur >= 0) flush_quad<TILED>(acc, cur, tg);
 #pragma unroll
         for (int n = 0; n < 18; n++) acc[n] = 0.0;
         cur = kk;
@@ -447,13 +447,15 @@ k_predict_pair(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     PairStream st;
     pstream_open<PRED_NST>(P, t, w, NW, lane, sRing + w * (PRED_NST * PRING_D), sBar + w * PRED_NST, st);
     if (threadIdx.x == 0) mbar_init(&bar, 1);
+#if MRG_PRED_SMEM_TILE
     for (int e = threadIdx.x; e < 6 * TILE_ACC_D; e += blockDim.x) sM[e] = 0.0;
+#endif
     __syncthreads();
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     double* W = sPark + w * PARK_D;
     double* Q = W + 64 * PR_W_STRIDE;
-    const Target<true> tg(g, M4, sM, t.n0_first, t.ncell, lane);
+    const Target<(MRG_PRED_SMEM_TILE != 0)> tg(g, M4, sM, t.n0_first, t.ncell, lane);
     double acc[18];
 #pragma unroll
     for (int n = 0; n < 18; n++) acc[n] = 0.0;
@@ -488,10 +490,11 @@ k_predict_pair(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
         park_slot(W, Q, 2 * lane + 1, qvy, wxz, key);
       }
       __syncwarp();
-      deposit_parked64<8>(W, Q, lane, acc, cur, tg);
+      deposit_parked64<8, (MRG_PRED_SMEM_TILE != 0)>(W, Q, lane, acc, cur, tg);
       __syncwarp();
     }
-    if (cur >= 0) flush_quad<true>(acc, cur, tg);
+    if (cur >= 0) flush_quad<(MRG_PRED_SMEM_TILE != 0)>(acc, cur, tg);
+#if MRG_PRED_SMEM_TILE
     __syncthreads();
     // flush the accumulator tile: 4 moments of a node = one 32-byte sector
     const int nodes = t.ncell + 2;
@@ -503,6 +506,7 @@ k_predict_pair(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
         atomicAdd(M4 + 4 * ((size_t)t.n0_first + (size_t)jy * g.nx + (size_t)kz * g.nxy) + rem, v);
       }
     }
+#endif
   }
   warp_wk_store(wx, wh, wk_partial, NW);
 }

@@ -467,6 +467,14 @@ __device__ __forceinline__ int run_rank(int key, bool valid, int lane, int& coun
   return lane - start;
 }
 
+// A streaming int load the compiler must issue where it is written (asm volatile is not sunk towards its
+// first use, which is what happens to a plain load under register pressure).
+__device__ __forceinline__ int ld_early(const int* p) {
+  int v;
+  asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // wkix/wkih of the warp -> two global accumulators (zeroed by the host before the launch)
 __device__ __forceinline__ void warp_wk_atomic(double wx, double wh, double* __restrict__ acc2) {
   wx = warp_sum(wx);
@@ -627,10 +635,10 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       const bool valid = p < st.b;
       int kcell = -1;
       int idv = p;
-      if (valid && P.id) idv = P.id[p];
+      if (valid && P.id) idv = ld_early(P.id + p);
       int nb = 0, nrk = 0;
       if (prekey) {                                           // claim for it + 1, key for it + 2
-        if (p + 64 < st.b) pk2 = __ldcs(prekey + p + 64);
+        if (p + 64 < st.b) pk2 = ld_early(prekey + p + 64);
         int cnt;
         bool head;
         nrk = run_rank(pk1, p + 32 < st.b, lane, cnt, head);
