@@ -168,7 +168,8 @@ def workload_config(n, args):
                         "ions+electrons mi/me=100, dt=1.2, aimpl=0.6 (BASELINE configs[%s])"
                         % (mx, my, mz, args.ppc, "1" if n == 1 else ("2" if n == 8 else "1 scaled")),
             "grid": [mx, my, mz], "ppc": args.ppc, "species": 2, "particles_per_gpu": 2 * mx * my * mz * args.ppc // n,
-            "sharding": "round-robin particle ownership l = rank+1 (mod N), replicated grids, NCCL fp64 allreduce of J/chi",
+            "sharding": ("z-slab ownership by initial position" if (args.shard == "slab" and n > 1) else
+                         "round-robin particle ownership l = rank+1 (mod N)") + ", replicated grids, NCCL fp64 allreduce of J/chi",
             "sort_every": args.sort_every, "sort_every_ions": args.sort_every_ions or args.sort_every, "deposit": args.deposit, "iters": args.iters, "tile": args.tile,
             "fused_keys": args.fused_keys, "fused_sort": args.fused_sort,
             "l2": "inputs larger than L2 (12.9 GB of particle arrays per GPU vs 126 MB)"}
@@ -203,6 +204,7 @@ def run_ours(args):
     ctx.set_option("tile", args.tile)
     ctx.set_option("fused_keys", args.fused_keys)
     ctx.set_option("fused_sort", args.fused_sort)
+    ctx.set_option("shard", 1 if args.shard == "slab" else 0)
     # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
     ranfb = 7331
     for ksp in (1, 2):
@@ -395,6 +397,8 @@ def main():
     ap.add_argument("--tile", type=int, default=1)
     ap.add_argument("--fused-keys", type=int, default=1)
     ap.add_argument("--fused-sort", type=int, default=1)
+    ap.add_argument("--shard", default="slab", choices=["slab", "roundrobin"],
+                    help="particle ownership for --gpus > 1: z slabs of the initial positions, or the reference's round-robin")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

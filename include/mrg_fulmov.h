@@ -152,6 +152,13 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *   "fused_keys" 1 (default) = a tiled corrector that does not scatter emits
  *                the next sort keys (cell of x + hdt*v), so mrg_sort(ksp, hdt)
  *                skips its key pass
+ *   "shard"      ownership used by mrg_loadpt when nranks > 1: 0 (default) = the
+ *                reference's round-robin l = rank+1 (mod nranks), F:1162;
+ *                1 = the particles whose INITIAL z lies in z slab `rank` of
+ *                nranks equal slabs (local order = increasing l).  Moments
+ *                summed over ranks do not depend on the ownership; with
+ *                replicated grids the slab choice keeps every GPU's particles
+ *                dense in the cells it touches
  *   "iters"      particles per warp / 32 of the untiled predictor (4..32)
  *   "group_min"  smallest stray group (particles) that is pre-reduced        */
 int mrg_set_option(mrg_ctx* ctx, const char* name, int64_t value);

@@ -161,7 +161,7 @@ struct mrg_ctx {
   void* comm = nullptr;
   // options / counters
   int lane_grid[3] = {148 * 8, 148 * 8, 148 * 8};   // persistent warps of k_lane<0>, k_lane<1>, k_lane_deposit (SMs x resident CTAs)
-  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1;
+  int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -520,11 +520,14 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
   const GP& g = c->g;
   const long long npr = (long long)g.mx * g.my * g.mz * ppc;       // F:8937-8957
   const long long first = c->rank + 1, stride = c->nranks;         // F:219, F:1162
-  const long long n = owned_count(npr, first, stride);
+  long long n = owned_count(npr, first, stride);
   if (n >= (1LL << 31) - 64) return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU");
   Species& s = c->sp[ksp - 1];
-  rc = alloc_species(c, s, n);
-  if (rc) return rc;
+  const bool slab = c->opt_shard == 1 && c->nranks > 1;
+  if (!slab) {
+    rc = alloc_species(c, s, n);
+    if (rc) return rc;
+  }
   LoadParams L;
   loadpt_table(vth, vdr, L.fv2, &L.v2, &L.dv2);
   L.vdr = vdr; L.vbeam = vbeam;
@@ -534,7 +537,25 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
   L.rrz = 0.25 * g.zmax; L.rry = 0.075 * g.ymax;                                    // F:9026-9027
   L.sa = (unsigned)*ranfa; L.sb = (unsigned)*ranfb;
   L.first = first; L.stride = stride;
-  if (n > 0) { k_loadpt<<<grid_for(n, 256), 256, 0, c->stream>>>(g, L, soa(s)); CKL(c); }
+  if (slab) {   // z-slab ownership: count, scan, fill (local order = increasing l)
+    if (npr >= (1LL << 31)) return fail(MRG_ERR_ARG, "slab loading needs npr < 2^31");
+    const long long nb = (npr + 255) / 256;
+    int* bc = nullptr;
+    CK(cudaMalloc((void**)&bc, (size_t)(nb + 1) * sizeof(int)));
+    CK(cudaMemsetAsync(bc + nb, 0, sizeof(int), c->stream));
+    k_loadpt_slab_count<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, npr, c->nranks, c->rank, bc); CKL(c);
+    rc = scan_excl(c, bc, bc, nb + 1, nullptr);
+    if (rc) { cudaFree(bc); return rc; }
+    int total = 0;
+    CK(cudaMemcpyAsync(&total, bc + nb, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    n = total;
+    rc = alloc_species(c, s, n);
+    if (rc) { cudaFree(bc); return rc; }
+    if (n > 0) { k_loadpt_slab_fill<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, soa(s), npr, c->nranks, c->rank, bc); CKL(c); }
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(bc));
+  } else if (n > 0) { k_loadpt<<<grid_for(n, 256), 256, 0, c->stream>>>(g, L, soa(s)); CKL(c); }
   CK(cudaStreamSynchronize(c->stream));
   // every rank of the reference runs the whole serial loader: 3 ranfp + 4 ranf draws per particle
   *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, 3ull * (unsigned long long)npr);
@@ -903,6 +924,9 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     c->opt_fused_keys = value != 0;
   } else if (n == "fused_sort") {
     c->opt_fused_sort = value != 0;
+  } else if (n == "shard") {
+    if (value < 0 || value > 1) return fail(MRG_ERR_ARG, "shard must be 0 (round-robin, the reference) or 1 (z slabs)");
+    c->opt_shard = (int)value;
   } else if (n == "group_min") {
     if (value < 1 || value > 9) return fail(MRG_ERR_ARG, "group_min must be in 1..9 (particles per sub-iteration group)");
     c->opt_group_min = (int)value;

@@ -546,10 +546,48 @@ struct LoadParams {
   unsigned sa, sb;
   long long first, stride;
 };
+// one particle of the serial loader: l0 = l - 1 (global index), written to local slot m
+__device__ __forceinline__ void loadpt_one(const GP& g, const LoadParams& L, const ParticleSoA& P, unsigned long long l0, long long m);
+
 __global__ void k_loadpt(GP g, LoadParams L, ParticleSoA P) {
   const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (m >= P.n) return;
-  const unsigned long long l0 = (unsigned long long)(L.first - 1 + m * L.stride);  // l-1
+  loadpt_one(g, L, P, (unsigned long long)(L.first - 1 + m * L.stride), m);
+}
+
+// z-slab ownership (option "shard" = 1): rank r owns the particles whose INITIAL z lies in slab r of nslab equal
+// slabs of [-hz/2, zmax-hz/2).  z of particle l is the third ranfp draw, F:8949.
+__device__ __forceinline__ bool loadpt_in_slab(const GP& g, const LoadParams& L, unsigned long long l0, int nslab, int slab) {
+  unsigned s = lcg_skip(L.sb, 3ull * l0 + 2ull);
+  s = lcg_next(s);
+  const double z = __dsub_rn(__dmul_rn(g.zmax, (double)s * (1.0 / 2147483648.0)), L.half_hz);
+  int q = (int)((z + L.half_hz) / g.zmax * nslab);
+  q = min(max(q, 0), nslab - 1);
+  return q == slab;
+}
+// pass 1: per-block (256 consecutive l) count of owned particles
+__global__ void __launch_bounds__(256) k_loadpt_slab_count(GP g, LoadParams L, long long npr, int nslab, int slab, int* __restrict__ block_count) {
+  const long long l0 = blockIdx.x * 256LL + threadIdx.x;
+  const bool mine = l0 < npr && loadpt_in_slab(g, L, (unsigned long long)l0, nslab, slab);
+  const int c = __syncthreads_count(mine);
+  if (threadIdx.x == 0) block_count[blockIdx.x] = c;
+}
+// pass 2: owned particles of a block go to consecutive local slots in l order (block_off = exclusive scan of pass 1)
+__global__ void __launch_bounds__(256) k_loadpt_slab_fill(GP g, LoadParams L, ParticleSoA P, long long npr, int nslab, int slab,
+                                                          const int* __restrict__ block_off) {
+  __shared__ int wcnt[8];
+  const long long l0 = blockIdx.x * 256LL + threadIdx.x;
+  const bool mine = l0 < npr && loadpt_in_slab(g, L, (unsigned long long)l0, nslab, slab);
+  const unsigned b = __ballot_sync(0xffffffffu, mine);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) wcnt[w] = __popc(b);
+  __syncthreads();
+  int off = block_off[blockIdx.x];
+  for (int q = 0; q < w; q++) off += wcnt[q];
+  if (mine) loadpt_one(g, L, P, (unsigned long long)l0, off + __popc(b & ((1u << lane) - 1u)));
+}
+
+__device__ __forceinline__ void loadpt_one(const GP& g, const LoadParams& L, const ParticleSoA& P, unsigned long long l0, long long m) {
   const double inv = 1.0 / 2147483648.0;
   unsigned s = lcg_skip(L.sb, 3ull * l0);
   s = lcg_next(s); const double x = __dsub_rn(__dmul_rn(g.xmax, (double)s * inv), L.half_hx);  // F:8947

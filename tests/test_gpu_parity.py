@@ -423,6 +423,47 @@ def test_device_loadpt_bit_exact(mrg, nranks):
             np.testing.assert_array_equal(got[c], arrs[c])
 
 
+# ---- z-slab ownership of the device loader: same particle set, same summed moments --------------
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_device_loadpt_slab_ownership(mrg, nranks):
+    p = U.make_parm(12, 10, 16)
+    ppc = 9
+    npr = p.mx * p.my * p.mz * ppc
+    f12 = U.smooth_fields(p, seed=5)
+    a6 = O.field_prep(p, f12)
+    ksp = 2
+    q, w = U.QSPEC[ksp], U.WSPEC[ksp]
+    arrs, a, b = O.loadpt(p, ppc, U.vth(ksp), 0.0, U.VBEAM[ksp])
+    r = O.fulmov(p, a6, *[x.copy() for x in arrs], q, w, 1, nranks=1, want_raw=True)
+    raw_sum = [np.zeros(O.mxyzA(p)) for _ in range(4)]
+    total, zs = 0, []
+    for rank in range(nranks):
+        ctx = new_ctx(mrg, p, rank=rank, nranks=nranks)
+        ctx.set_option("shard", 1)
+        ga, gb = ctx.loadpt(ksp, ppc, U.vth(ksp), 0.0, U.VBEAM[ksp])
+        assert (ga, gb) == (a, b)
+        n = ctx.num_local(ksp)
+        total += n
+        got = ctx.download(ksp, n)                  # local order = increasing l
+        lo, hi = -p.hz / 2 + p.zmax * rank / nranks, -p.hz / 2 + p.zmax * (rank + 1) / nranks
+        assert np.all(got[2] >= lo - 1e-9) and np.all(got[2] < hi + 1e-9)
+        zs.append(got[2])
+        ctx.close()
+        one = new_ctx(mrg, p)                       # the rank's share pushed without a communicator
+        one.set_fields(f12)
+        one.upload(ksp, *got)
+        one.sort(ksp, p.hdt)
+        one.fulmov(ksp, q, w, 1, params_of(mrg, p))
+        part = one.moments(ksp, folded=False)
+        for c in range(4):
+            raw_sum[c] += part[c]
+        one.close()
+    assert total == npr
+    np.testing.assert_array_equal(np.sort(np.concatenate(zs)), np.sort(arrs[2]))
+    for c in range(4):
+        assert U.rel_l2(raw_sum[c], r["raw"][c]) < MTOL
+
+
 # ---- error behaviour of the C ABI --------------------------------------------------------------------
 def test_abi_errors(mrg, case):
     p, sp, ranfb, f12, a6 = case
