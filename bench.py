@@ -171,7 +171,7 @@ def workload_config(n, args):
             "sharding": ("z-slab ownership by initial position" if (args.shard == "slab" and n > 1) else
                          "round-robin particle ownership l = rank+1 (mod N)") + ", replicated grids, NCCL fp64 allreduce of J/chi",
             "sort_every": args.sort_every, "sort_every_ions": args.sort_every_ions or args.sort_every, "deposit": args.deposit, "iters": args.iters, "tile": args.tile,
-            "fused_keys": args.fused_keys, "fused_sort": args.fused_sort,
+            "fused_keys": args.fused_keys, "fused_sort": args.fused_sort, "defer": args.defer, "planes": args.planes,
             "l2": "inputs larger than L2 (12.9 GB of particle arrays per GPU vs 126 MB)"}
 
 
@@ -205,6 +205,8 @@ def run_ours(args):
     ctx.set_option("fused_keys", args.fused_keys)
     ctx.set_option("fused_sort", args.fused_sort)
     ctx.set_option("shard", 1 if args.shard == "slab" else 0)
+    ctx.set_option("planes", args.planes)
+    ctx.set_option("defer", args.defer)
     # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
     ranfb = 7331
     for ksp in (1, 2):
@@ -227,15 +229,20 @@ def run_ours(args):
 
     state = {"ranfb": ranfb, "step": 0, "tp": [], "tc": []}
 
+    fptr = [[t.data_ptr() for t in fs] for fs in fsets]
+
     def step_resident():
-        ctx.set_fields_device([t.data_ptr() for t in fsets[0]])
-        for ksp in (1, 2):
-            ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"])
-            state["tp"].append(ctx.last_kernel_ms())
-        ctx.set_fields_device([t.data_ptr() for t in fsets[1]])
+        # the field arrays are resident in HBM (as a device-side emfild would leave them) and read in place
+        ctx.bind_fields_device(fptr[0])
+        wk = [ctx.fulmov_deferred(ksp, QSPEC[ksp], WSPEC[ksp], params) if args.defer
+              else ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"]) for ksp in (1, 2)]
+        ctx.bind_fields_device(fptr[1])        # queued behind the moment sums: new fields need the moments
         for ksp in (1, 2):
             _, _, state["ranfb"] = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, params, state["ranfb"])
-            state["tc"].append(ctx.last_kernel_ms())
+        for ksp in (1, 2):
+            state["tp"].append(ctx.pass_ms(ksp, 1))
+            state["tc"].append(ctx.pass_ms(ksp, 0))
+        state["wk"] = wk
         state["step"] += 1
         for ksp in (1, 2):
             every = args.sort_every_ions if (ksp == 1 and args.sort_every_ions) else args.sort_every
@@ -322,21 +329,35 @@ def run_ours(args):
         for name in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe"):
             setattr(c, name, pinned(n_grid))
         c.ranfb = state["ranfb"]
-        fm = mrg.Fulmov(c, ipar=rank + 1, size=world, device=local, sort_interval=args.sort_every, ctx=ctx)
+        fm = mrg.Fulmov(c, ipar=rank + 1, size=world, device=local, sort_interval=args.sort_every, ctx=ctx,
+                        hints=bool(args.hints), defer=bool(args.defer))
         dummy = [np.zeros(1)] * 6
         npr = ntot_particles // 2
+        FN = mrg.host.FIELD_NAMES
+        for name, arr in zip(FN, hsets[0]):
+            setattr(c, name, arr)
+        estate = {"n": 0}
 
         def step_e2e():
-            for name, arr in zip(mrg.host.FIELD_NAMES, hsets[0]):
-                setattr(c, name, arr)
-            fm.fields_changed()
+            # the trans protocol (F:749-807) with host arrays: prefld rewrites bx,by,bz; the two ipc=1 calls fill
+            # COMMON /srimp7/; emfild rewrites ex..bz; the two ipc=0 calls; renewal ex0 <- ex.  "Rewrites" = the
+            # COMMON member now is another pinned array (the host solver is not part of the timed path).
+            new = hsets[(estate["n"] + 1) % 2]
+            for i in (3, 4, 5):
+                setattr(c, FN[i], new[i])
+            fm.fields_changed(fm.MASK_B)
             for ksp in (1, 2):
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 1, ksp)
-            for name, arr in zip(mrg.host.FIELD_NAMES, hsets[1]):
-                setattr(c, name, arr)
-            fm.fields_changed()
+            fm.finish_moments()
+            for i in (0, 1, 2):
+                setattr(c, FN[i], new[i])
+            fm.fields_changed(fm.MASK_NEW)
             for ksp in (1, 2):
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 0, ksp)
+            for i in range(6):
+                setattr(c, FN[i + 6], getattr(c, FN[i]))
+            fm.fields_renewed()
+            estate["n"] += 1
 
         ne = max(2, min(args.steps, 5))
         step_e2e()
@@ -355,7 +376,9 @@ def run_ours(args):
         e2e = {"value": ntot_particles * ne / te, "unit": UNIT, "h2d_bytes_per_step": cnt_e["h2d_bytes"] // ne,
                "d2h_bytes_per_step": cnt_e["d2h_bytes"] // ne, "steps": ne, "ms_per_step": 1e3 * te / ne,
                "note": "host fields in pinned memory -> mrg_set_fields (H2D), moments -> COMMON /srimp7/ arrays (D2H) every "
-                       "step through the Fulmov mirror of the reference call; particles stay resident in HBM by design"}
+                       "step through the Fulmov mirror of the reference call; particles stay resident in HBM by design; "
+                       + ("the host marks its field updates (prefld: bx..bz, emfild: ex..bz, renewal on the device)"
+                          if args.hints else "no field hints: all of COMMON /fields/ is uploaded in both phases")}
         barrier()
 
     cpu = None
@@ -399,6 +422,9 @@ def main():
     ap.add_argument("--fused-sort", type=int, default=1)
     ap.add_argument("--shard", default="slab", choices=["slab", "roundrobin"],
                     help="particle ownership for --gpus > 1: z slabs of the initial positions, or the reference's round-robin")
+    ap.add_argument("--planes", type=int, default=-1, help="restricted field preparation: -1 = when N > 1, 0 = off, 1 = on")
+    ap.add_argument("--defer", type=int, default=1, help="1 = moment sum + fold on the second stream (overlaps the next kernel)")
+    ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -100,6 +100,17 @@ int mrg_set_fields(mrg_ctx* ctx, uint32_t mask, const double* const f12[12]);
 int mrg_set_fields_device(mrg_ctx* ctx, uint32_t mask,
                           const double* const f12_dev[12]);
 
+/* Zero-copy variant: the context reads the caller's DEVICE arrays in place
+ * (no copy is made).  The selected arrays must stay valid and unchanged until
+ * they are replaced by another set/bind call.  For a device-resident field
+ * solve that already owns ex..bz0 in HBM.                                   */
+int mrg_bind_fields_device(mrg_ctx* ctx, uint32_t mask,
+                           const double* const f12_dev[12]);
+/* "Renewal: ex0 <- ex" of trans, F:796-807, on the device copies: after the
+ * host has done that loop on its own arrays it calls this instead of
+ * uploading ex0..bz0 again (they equal the ex..bz the device already has).  */
+int mrg_renew_fields(mrg_ctx* ctx);
+
 /* fulmov, F:1044-1390, for this rank's particles of species ksp (1-based):
  *   section 0 (F:1127-1152)  blend + outmesh3 + filt3e, cached while neither
  *                            the fields nor aimpl/bxc../ifil* change;
@@ -121,6 +132,13 @@ int mrg_fulmov(mrg_ctx* ctx, int32_t ksp, double qmult, double wmult,
  * are skipped.                                                              */
 int mrg_get_moments(mrg_ctx* ctx, int32_t ksp, double* qjx, double* qjy,
                     double* qjz, double* q, int32_t folded);
+/* Deferred mode only: host arrays (the caller's COMMON /srimp7/ members,
+ * ideally page-locked) that every later mrg_fulmov(ipc >= 1) of species ksp
+ * copies its folded moments into right after the fold, on the communication
+ * stream, so the transfer overlaps the next species' particle kernel.  A
+ * following mrg_get_moments with the same pointers only waits.  NULL = none. */
+int mrg_set_moment_sink(mrg_ctx* ctx, int32_t ksp, double* qjx, double* qjy,
+                        double* qjz, double* q);
 /* Device pointers of the same four arrays (folded), valid until the next
  * mrg_fulmov(ipc>=1) of that species; for a device-resident field solve.    */
 int mrg_get_moments_device(mrg_ctx* ctx, int32_t ksp, const double* dev4[4]);
@@ -159,6 +177,21 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                summed over ranks do not depend on the ownership; with
  *                replicated grids the slab choice keeps every GPU's particles
  *                dense in the cells it touches
+ *   "planes"     restricted field preparation: the tiled corrector and
+ *                mrg_sort record which z planes the next pass gathers from,
+ *                and section 0 (blend/filter/ghost fill) then runs on those
+ *                planes and their stencil neighbours only; a rank that owns a
+ *                z slab prepares its slab instead of the whole replicated
+ *                grid.  -1 (default) = on when nranks > 1, 0 = off, 1 = on.
+ *                Needs |vz|*dt < hz (like partbc, which wraps once)
+ *   "defer"      1 = mrg_fulmov(ipc >= 1) returns once its work is queued: the
+ *                NCCL moment sum and the fold run on a second stream and
+ *                overlap the next species' particle kernel.  *wkix, *wkih are
+ *                then written when the host next waits for that species:
+ *                mrg_get_moments, mrg_get_moments_device, the next
+ *                mrg_fulmov(ipc >= 1) of the species, or mrg_synchronize (the
+ *                pointers must stay valid until then).  0 (default) = every
+ *                call completes before it returns
  *   "iters"      particles per warp / 32 of the untiled predictor (4..32)
  *   "group_min"  smallest stray group (particles) that is pre-reduced        */
 int mrg_set_option(mrg_ctx* ctx, const char* name, int64_t value);
@@ -170,6 +203,23 @@ int mrg_get_counters(mrg_ctx* ctx, int64_t out[3], int32_t reset);
 /* Device-time of the particle kernel of the last mrg_fulmov call (CUDA
  * events on the library's stream), in milliseconds.                         */
 int mrg_last_kernel_ms(mrg_ctx* ctx, double* ms);
+
+/* Same for the last call of species ksp with ipc == 0 / ipc >= 1 (waits for
+ * that kernel only); usable in deferred mode.                               */
+int mrg_pass_ms(mrg_ctx* ctx, int32_t ksp, int32_t ipc, double* ms);
+
+/* Field preparations since the last reset: [0] runs of section 0,
+ * [1] of which restricted to a plane set, [2] planes finalized by those.    */
+int mrg_get_prep_stats(mrg_ctx* ctx, int64_t out[3], int32_t reset);
+
+/* Host-only helper behind option "planes" (no GPU needed; exported so the
+ * dependency analysis can be tested on its own): occ[kp], kp = 0..mz, marks
+ * the z planes of the particles' gather cells; out come the planes to blend
+ * (listB, k values), to filter (listGI, k values) and to finalize (listG,
+ * extended index k+2; bit 30 marks a NaN guard plane), each with room for
+ * mz+4 entries, and their lengths n[0..2].                                  */
+int mrg_plane_sets(int32_t mz, const uint8_t* occ, int32_t* listB,
+                   int32_t* listGI, int32_t* listG, int32_t n[3]);
 
 /* Device-side stopwatch on the library's stream (where every kernel of this
  * context is launched): record marks slot 0..7, elapsed gives the CUDA-event

@@ -21,7 +21,8 @@ SYMBOLS = [
     "mrg_loadpt", "mrg_set_fields", "mrg_set_fields_device", "mrg_fulmov", "mrg_get_moments",
     "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_sort", "mrg_set_option",
     "mrg_get_counters", "mrg_last_kernel_ms", "mrg_event_record", "mrg_event_elapsed_ms",
-    "mrg_synchronize",
+    "mrg_synchronize", "mrg_bind_fields_device", "mrg_renew_fields", "mrg_pass_ms", "mrg_get_prep_stats",
+    "mrg_set_moment_sink", "mrg_plane_sets",
 ]
 
 
@@ -76,6 +77,12 @@ def load(build_if_missing=True):
     L.mrg_loadpt.argtypes = [vp, i32, i32, C.c_double, C.c_double, C.c_double, C.POINTER(i32), C.POINTER(i32)]
     L.mrg_set_fields.argtypes = [vp, C.c_uint32, C.POINTER(dp)]
     L.mrg_set_fields_device.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+    L.mrg_bind_fields_device.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
+    L.mrg_renew_fields.argtypes = [vp]
+    L.mrg_plane_sets.argtypes = [i32, C.POINTER(C.c_uint8), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.mrg_set_moment_sink.argtypes = [vp, i32, dp, dp, dp, dp]
+    L.mrg_pass_ms.argtypes = [vp, i32, i32, dp]
+    L.mrg_get_prep_stats.argtypes = [vp, C.POINTER(i64), i32]
     L.mrg_fulmov.argtypes = [vp, i32, C.c_double, C.c_double, i32, C.POINTER(StepParams), C.POINTER(i32), dp, dp]
     L.mrg_get_moments.argtypes = [vp, i32, dp, dp, dp, dp, i32]
     L.mrg_get_moments_device.argtypes = [vp, i32, C.POINTER(vp)]

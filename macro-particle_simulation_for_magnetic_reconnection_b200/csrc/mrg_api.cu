@@ -112,6 +112,19 @@ struct Species {
   bool keys_valid = false;
   bool hist_valid = false;     // s.hist matches s.key (the pair corrector emits keys only)
   double keys_lookahead = 0.0;
+  // z planes kp of the gather cells of the next pass (bit kp, kp = 0..mz), tracked by the tiled corrector and the
+  // sort; valid for passes whose hdt equals zocc_lookahead.  Lets ensure_prep prepare only the planes in use.
+  unsigned* zocc = nullptr;
+  std::vector<unsigned> zocc_host;
+  bool zocc_valid = false;
+  double zocc_lookahead = 0.0;
+  // deferred completion (option "defer"): the moment sum, fold and wkix/wkih of the last ipc>=1 call run on the
+  // communication stream; done marks their end, wk_user receives wkix/wkih when the host next waits for them
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+  double* wk_user[2] = {nullptr, nullptr};
+  double* sink[4] = {nullptr, nullptr, nullptr, nullptr};   // host arrays the folded moments are copied to as soon as they exist
+  bool sink_filled = false;
 };
 
 struct PrepKey {
@@ -130,10 +143,13 @@ struct mrg_ctx {
   int device = 0, rank = 0, nranks = 1, nspecies = 2;
   GP g;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // particle kernel of the call in flight (= pass_ev of its species / phase)
+  cudaEvent_t pass_ev[MRG_MAX_SPECIES][2][2] = {};   // [species][ipc != 0][begin, end]
+  bool pass_timed[MRG_MAX_SPECIES][2] = {};
   cudaEvent_t user_ev[8] = {};
   // fields
   double* f12[12] = {};
+  const double* fcur[12] = {};   // what k_blend reads: f12[k], or the caller's device array after mrg_bind_fields_device
   double* A6[6] = {};
   double* T1[6] = {};
   double* T2[6] = {};
@@ -142,6 +158,11 @@ struct mrg_ctx {
   unsigned long long field_version = 0;
   bool fields_set = false, prep_valid = false;
   PrepKey prep_key{};
+  // planes of F6 (extended index k+2) the cached preparation covers; prep_full = all of them
+  bool prep_full = true;
+  std::vector<char> prep_planes;
+  int* plane_lists = nullptr;    // device copy of the three plane lists of a restricted preparation
+  long long prep_count = 0, prep_restricted_count = 0, prep_planes_sum = 0;
   // species
   Species sp[MRG_MAX_SPECIES];
   double* alt[6] = {};     // shared spare particle buffer (sort / download)
@@ -159,9 +180,14 @@ struct mrg_ctx {
   double* h_pinned = nullptr; size_t h_pinned_bytes = 0;
   // nccl
   void* comm = nullptr;
+  cudaStream_t cstream = nullptr;   // communication stream of the deferred mode (allreduce + fold overlap the next kernel)
+  cudaEvent_t ev_kernel = nullptr;
+  double* wk_pinned = nullptr;      // [MRG_MAX_SPECIES][2] wkix/wkih landing zone of the deferred mode
   // options / counters
   int lane_grid[3] = {148 * 8, 148 * 8, 148 * 8};   // persistent warps of k_lane<0>, k_lane<1>, k_lane_deposit (SMs x resident CTAs)
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
+  int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
+  int opt_defer = 0;
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -218,6 +244,7 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   s.keys_valid = false;
   s.prekeys_valid = false;
   s.fresh = false;
+  s.zocc_valid = false;
   if (!s.cell_end) {
     CK(cudaMalloc((void**)&s.cell_end, (size_t)(c->ncell + 1) * sizeof(int)));
     CK(cudaMalloc((void**)&s.cell_end2, (size_t)(c->ncell + 1) * sizeof(int)));
@@ -265,26 +292,149 @@ int scan_excl(mrg_ctx* c, const int* in, int* out, long long n, int* total_dev) 
   return MRG_OK;
 }
 
-// F:1127-1148 on the device, cached on (fields version, aimpl, dc, ifil*)
-int ensure_prep(mrg_ctx* c, const mrg_step_params* p) {
+// host side of a deferred ipc>=1 call: wait for the species' moment sum and hand out wkix/wkih
+int complete_moments(mrg_ctx* c, int k) {
+  Species& s = c->sp[k];
+  if (!s.pending) return MRG_OK;
+  CK(cudaEventSynchronize(s.done));
+  if (s.wk_user[0]) *s.wk_user[0] = c->wk_pinned[2 * k + 0];
+  if (s.wk_user[1]) *s.wk_user[1] = c->wk_pinned[2 * k + 1];
+  s.wk_user[0] = s.wk_user[1] = nullptr;
+  s.pending = false;
+  return MRG_OK;
+}
+
+// ---- plane tracking -----------------------------------------------------------
+bool tracking(const mrg_ctx* c) { return c->opt_planes == 1 || (c->opt_planes < 0 && c->nranks > 1); }
+int zocc_words(const mrg_ctx* c) { return (c->g.mz + 1 + 31) / 32; }
+
+// zero the species' plane bitmap before a kernel that marks it (nullptr when tracking is off)
+int zocc_begin(mrg_ctx* c, Species& s, unsigned** out) {
+  *out = nullptr;
+  s.zocc_valid = false;
+  if (!tracking(c)) return MRG_OK;
+  const int nw = zocc_words(c);
+  if (!s.zocc) CK(cudaMalloc((void**)&s.zocc, (size_t)nw * sizeof(unsigned)));
+  CK(cudaMemsetAsync(s.zocc, 0, (size_t)nw * sizeof(unsigned), c->stream));
+  *out = s.zocc;
+  return MRG_OK;
+}
+// queue the copy of the bitmap to the host; the caller synchronises the stream afterwards
+int zocc_fetch(mrg_ctx* c, Species& s, double lookahead) {
+  const int nw = zocc_words(c);
+  s.zocc_host.assign(nw, 0u);
+  CK(cudaMemcpyAsync(s.zocc_host.data(), s.zocc, (size_t)nw * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  s.zocc_valid = true;
+  s.zocc_lookahead = lookahead;
+  return MRG_OK;
+}
+bool occ_bit(const Species& s, int kp) { return (s.zocc_host[kp >> 5] >> (kp & 31)) & 1u; }
+
+// Plane sets of a restricted preparation from the occupancy occ[kp], kp = 0..mz (see ensure_prep):
+//   G      extended planes (k+2) of F6 to finalize: k = kp-1..kp+1
+//   listGI interior planes of G: where the filter sweeps run
+//   listB  planes to blend: listGI widened by 2 either side (periodic z sweep) + periodic images of G's ghosts
+//   listG  G as a list, plus the guard planes (| PLANE_GUARD) just outside it
+struct PlaneSets {
+  std::vector<char> G;
+  std::vector<int> listB, listGI, listG;
+};
+void plane_sets(int mz, const std::vector<char>& occ, PlaneSets& ps) {
+  const int nz = mz + 4;
+  ps.G.assign(nz, 0);
+  ps.listB.clear(); ps.listGI.clear(); ps.listG.clear();
+  for (int kp = 0; kp <= mz; kp++)
+    if (occ[kp]) ps.G[kp + 1] = ps.G[kp + 2] = ps.G[kp + 3] = 1;
+  std::vector<char> GI(mz, 0), B(mz, 0);
+  for (int k = 0; k < mz; k++) GI[k] = ps.G[k + 2];
+  for (int k = 0; k < mz; k++)
+    for (int d = -2; d <= 2; d++) B[k] |= GI[((k + d) % mz + mz) % mz];
+  if (ps.G[1]) B[mz - 1] = 1;              // ghost plane k = -1 copies the blend of plane mz-1
+  if (ps.G[mz + 2]) B[0] = 1;              // k = mz   <- plane 0
+  if (ps.G[mz + 3]) B[1] = 1;              // k = mz+1 <- plane 1
+  for (int k = 0; k < mz; k++) { if (B[k]) ps.listB.push_back(k); if (GI[k]) ps.listGI.push_back(k); }
+  for (int e = 0; e < nz; e++) {
+    if (ps.G[e]) ps.listG.push_back(e);
+    else if ((e > 0 && ps.G[e - 1]) || (e + 1 < nz && ps.G[e + 1])) ps.listG.push_back(e | PLANE_GUARD);
+  }
+}
+
+// F:1127-1148 on the device, cached on (fields version, aimpl, dc, ifil*).
+//
+// Restricted preparation: a particle whose gather cell lies on plane kp reads F6 on planes kp-1..kp+1 only
+// (F:1217-1270).  When every species' plane bitmap is valid for this hdt, only those planes are finalized
+// (set G, extended index k+2), the filters run on the interior planes of G (x and y sweeps stay inside a
+// plane), the z sweep needs the blend two planes either side (periodic, F:7365-7395), and the ghost planes
+// k = -1, mz, mz+1 of G need the blend of their periodic images (F:3088-3148).  The planes just outside G are
+// filled with NaN.  Precondition (shared with partbc, which wraps once): no particle moves more than one cell
+// in z per step.
+int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
   if (p->ifilx < 0 || p->ifily < 0 || p->ifilz < 0) return fail(MRG_ERR_ARG, "negative filter count");
   PrepKey key{p->aimpl, p->bxc, p->byc, p->bzc, p->ifilx, p->ifily, p->ifilz, c->field_version};
-  if (c->prep_valid && key == c->prep_key) return MRG_OK;
   const GP& g = c->g;
-  const long long nin = (long long)g.mx * (g.my + 1) * g.mz;
+  const int mz = g.mz, nz = g.nz;
+  auto usable = [&](const Species& s) { return s.n == 0 || (s.zocc_valid && s.zocc_lookahead == p->hdt); };
+  if (c->prep_valid && key == c->prep_key) {
+    if (c->prep_full) return MRG_OK;
+    bool covered = ksp >= 1;          // ksp = 0: the caller wants every plane
+    if (covered) {
+      const Species& s = c->sp[ksp - 1];
+      covered = usable(s);
+      if (covered && s.n > 0)
+        for (int kp = 0; kp <= mz && covered; kp++)
+          if (occ_bit(s, kp)) covered = c->prep_planes[kp + 1] && c->prep_planes[kp + 2] && c->prep_planes[kp + 3];
+    }
+    if (covered) return MRG_OK;
+  }
+  // which planes?
+  bool restricted = ksp >= 1 && tracking(c) && p->ifilz <= 1;
+  for (int k = 0; k < c->nspecies && restricted; k++) restricted = usable(c->sp[k]);
+  PlaneSets ps;
+  ps.G.assign(nz, 0);
+  if (restricted) {
+    std::vector<char> occ(mz + 1, 0);
+    for (int k = 0; k < c->nspecies; k++) {
+      const Species& s = c->sp[k];
+      if (s.n == 0) continue;
+      for (int kp = 0; kp <= mz; kp++) occ[kp] |= (char)occ_bit(s, kp);
+    }
+    plane_sets(mz, occ, ps);
+    if (ps.listB.empty() || (long long)ps.listB.size() * 4 > (long long)mz * 3) restricted = false;   // not worth it
+  }
+  const std::vector<int>&listB = ps.listB, &listGI = ps.listGI, &listG = ps.listG;
+  const std::vector<char>& G = ps.G;
   const int B = 256;
-  CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->f12[k];
+  const int *dB = nullptr, *dGI = nullptr, *dG = nullptr;
+  int nB = mz, nGI = mz, nG = nz;
+  if (restricted) {
+    if (!c->plane_lists) CK(cudaMalloc((void**)&c->plane_lists, (size_t)(3 * (nz + 4)) * sizeof(int)));
+    std::vector<int> all(3 * (nz + 4), 0);
+    std::copy(listB.begin(), listB.end(), all.begin());
+    std::copy(listGI.begin(), listGI.end(), all.begin() + (nz + 4));
+    std::copy(listG.begin(), listG.end(), all.begin() + 2 * (nz + 4));
+    CK(cudaMemcpyAsync(c->plane_lists, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));   // `all` is pageable and goes out of scope
+    dB = c->plane_lists; dGI = c->plane_lists + (nz + 4); dG = c->plane_lists + 2 * (nz + 4);
+    nB = (int)listB.size(); nGI = (int)listGI.size(); nG = (int)listG.size();
+  }
+  const long long per = (long long)g.mx * (g.my + 1);
+  CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->fcur[k];
   Ptr6 A, T1, T2; for (int k = 0; k < 6; k++) { A.p[k] = c->A6[k]; T1.p[k] = c->T1[k]; T2.p[k] = c->T2[k]; }
-  k_blend<<<grid_for(nin, B), B, 0, c->stream>>>(g, f, A, T1, p->aimpl, 1.0 - p->aimpl, p->bxc, p->byc, p->bzc); CKL(c);
+  k_blend<<<grid_for(per * nB, B), B, 0, c->stream>>>(g, f, A, T1, p->aimpl, 1.0 - p->aimpl, p->bxc, p->byc, p->bzc, dB, nB); CKL(c);
   Ptr6 src = T1, dst = T2;
   auto as_const = [](const Ptr6& q) { CPtr6 r; for (int k = 0; k < 6; k++) r.p[k] = q.p[k]; return r; };
-  for (int n = 0; n < p->ifilz; n++) { k_filter<2><<<grid_for(nin, B), B, 0, c->stream>>>(g, as_const(src), dst); CKL(c); std::swap(src, dst); }
-  for (int n = 0; n < p->ifilx; n++) { k_filter<0><<<grid_for(nin, B), B, 0, c->stream>>>(g, as_const(src), dst); CKL(c); std::swap(src, dst); }
-  for (int n = 0; n < p->ifily; n++) { k_filter<1><<<grid_for(nin, B), B, 0, c->stream>>>(g, as_const(src), dst); CKL(c); std::swap(src, dst); }
-  k_finalize<<<grid_for(g.ntot, B), B, 0, c->stream>>>(g, as_const(A), as_const(src), c->F6, p->bxc, p->byc, p->bzc); CKL(c);
+  for (int n = 0; n < p->ifilz; n++) { k_filter<2><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
+  for (int n = 0; n < p->ifilx; n++) { k_filter<0><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
+  for (int n = 0; n < p->ifily; n++) { k_filter<1><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
+  k_finalize<<<grid_for((long long)g.nxy * nG, B), B, 0, c->stream>>>(g, as_const(A), as_const(src), c->F6, p->bxc, p->byc, p->bzc, dG, nG); CKL(c);
   c->prep_key = key;
   c->prep_valid = true;
+  c->prep_full = !restricted;
+  if (restricted) c->prep_planes.assign(G.begin(), G.end());
+  else c->prep_planes.assign(nz, 1);
+  c->prep_count++;
+  if (restricted) { c->prep_restricted_count++; c->prep_planes_sum += nG; }
   return MRG_OK;
 }
 
@@ -368,11 +518,19 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   CK(cudaFuncSetAttribute(k_predict_pair<PRED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PredSmem<PRED_NW>::bytes));
   CK(cudaFuncSetAttribute(k_correct_pair<CORR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CorrSmem<CORR_NW>::bytes));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-  CK(cudaEventCreate(&c->ev0));
-  CK(cudaEventCreate(&c->ev1));
+  {
+    int lo = 0, hi = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&c->cstream, cudaStreamNonBlocking, hi));   // the moment sum must not queue behind particle CTAs
+  }
+  CK(cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming));
+  for (auto& sp : c->sp) CK(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
+  CK(cudaMallocHost((void**)&c->wk_pinned, MRG_MAX_SPECIES * 2 * sizeof(double)));
+  for (int k = 0; k < MRG_MAX_SPECIES; k++)
+    for (int q = 0; q < 4; q++) CK(cudaEventCreate(&c->pass_ev[k][q >> 1][q & 1]));
   for (int k = 0; k < 8; k++) CK(cudaEventCreate(&c->user_ev[k]));
   const size_t gb = (size_t)ntot * sizeof(double);
-  for (int k = 0; k < 12; k++) { CK(cudaMalloc((void**)&c->f12[k], gb)); CK(cudaMemsetAsync(c->f12[k], 0, gb, c->stream)); }
+  for (int k = 0; k < 12; k++) { CK(cudaMalloc((void**)&c->f12[k], gb)); CK(cudaMemsetAsync(c->f12[k], 0, gb, c->stream)); c->fcur[k] = c->f12[k]; }
   for (int k = 0; k < 6; k++) {
     CK(cudaMalloc((void**)&c->A6[k], gb)); CK(cudaMalloc((void**)&c->T1[k], gb)); CK(cudaMalloc((void**)&c->T2[k], gb));
     CK(cudaMemsetAsync(c->A6[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T1[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T2[k], 0, gb, c->stream));
@@ -391,6 +549,7 @@ int mrg_destroy(mrg_ctx* c) {
   if (!c) return MRG_OK;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
+  if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 12; k++) cudaFree(c->f12[k]);
   for (int k = 0; k < 6; k++) { cudaFree(c->A6[k]); cudaFree(c->T1[k]); cudaFree(c->T2[k]); cudaFree(c->alt[k]); cudaFree(c->tmp6[k]); }
@@ -398,12 +557,19 @@ int mrg_destroy(mrg_ctx* c) {
   for (auto& s : c->sp) {
     for (int k = 0; k < 6; k++) cudaFree(s.d[k]);
     cudaFree(s.id); cudaFree(s.M4); cudaFree(s.cell_end); cudaFree(s.cell_end2); cudaFree(s.key); cudaFree(s.hist);
+    cudaFree(s.zocc);
+    if (s.done) cudaEventDestroy(s.done);
     for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
   }
   cudaFree(c->wk_partial); cudaFree(c->wk2); cudaFree(c->sort_key); cudaFree(c->hist); cudaFree(c->cursor);
   cudaFree(c->scan_tiles); cudaFree(c->slab_bits); cudaFree(c->slab_words); cudaFree(c->slab_list); cudaFree(c->slab_count);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
-  cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+  if (c->wk_pinned) cudaFreeHost(c->wk_pinned);
+  cudaFree(c->plane_lists);
+  if (c->ev_kernel) cudaEventDestroy(c->ev_kernel);
+  if (c->cstream) cudaStreamDestroy(c->cstream);
+  for (int k = 0; k < MRG_MAX_SPECIES; k++)
+    for (int q = 0; q < 4; q++) if (c->pass_ev[k][q >> 1][q & 1]) cudaEventDestroy(c->pass_ev[k][q >> 1][q & 1]);
   for (int k = 0; k < 8; k++) cudaEventDestroy(c->user_ev[k]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -563,15 +729,23 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
   return MRG_OK;
 }
 
+// kind: cudaMemcpyHostToDevice / cudaMemcpyDeviceToDevice copy into the context's own arrays;
+// cudaMemcpyDefault = bind (no copy: k_blend reads the caller's device arrays)
 static int set_fields_impl(mrg_ctx* c, uint32_t mask, const double* const f12[12], cudaMemcpyKind kind) {
   if (!c) return fail(MRG_ERR_ARG, "null context");
   if (mask >> 12) return fail(MRG_ERR_ARG, "mask has bits above 11");
   CK(cudaSetDevice(c->device));
+  // new fields exist only after the moments they were solved from: order the particle stream behind any
+  // moment sum still running on the communication stream (deferred mode)
+  for (int k = 0; k < c->nspecies; k++)
+    if (c->sp[k].pending) CK(cudaStreamWaitEvent(c->stream, c->sp[k].done, 0));
   const size_t gb = (size_t)c->g.ntot * sizeof(double);
   for (int k = 0; k < 12; k++) {
     if (!((mask >> k) & 1u)) continue;
     if (!f12 || !f12[k]) return fail(MRG_ERR_ARG, "selected field pointer is null");
+    if (kind == cudaMemcpyDefault) { c->fcur[k] = f12[k]; continue; }
     CK(cudaMemcpyAsync(c->f12[k], f12[k], gb, kind, c->stream));
+    c->fcur[k] = c->f12[k];
     if (kind == cudaMemcpyHostToDevice) c->h2d += (long long)gb;
   }
   if (kind == cudaMemcpyHostToDevice) CK(cudaStreamSynchronize(c->stream));
@@ -585,6 +759,22 @@ int mrg_set_fields(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
 int mrg_set_fields_device(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
   return set_fields_impl(c, mask, f12, cudaMemcpyDeviceToDevice);
 }
+int mrg_bind_fields_device(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
+  return set_fields_impl(c, mask, f12, cudaMemcpyDefault);
+}
+// F:796-807 ("Renewal: ex0 <- ex") on the device copies of the fields.
+int mrg_renew_fields(mrg_ctx* c) {
+  if (!c) return fail(MRG_ERR_ARG, "null context");
+  if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
+  CK(cudaSetDevice(c->device));
+  const size_t gb = (size_t)c->g.ntot * sizeof(double);
+  for (int k = 0; k < 6; k++) {
+    CK(cudaMemcpyAsync(c->f12[k + 6], c->fcur[k], gb, cudaMemcpyDeviceToDevice, c->stream));
+    c->fcur[k + 6] = c->f12[k + 6];
+  }
+  c->field_version++;
+  return MRG_OK;
+}
 
 int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc, const mrg_step_params* p,
                int32_t* ranfb, double* wkix, double* wkih) {
@@ -596,7 +786,11 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
   CK(cudaSetDevice(c->device));
   Species& s = c->sp[ksp - 1];
   if (!s.M4) { rc = alloc_species(c, s, 0); if (rc) return rc; }
-  rc = ensure_prep(c, p);
+  if (ipc >= 1) { rc = complete_moments(c, ksp - 1); if (rc) return rc; }   // M4 / out4 are about to be reused
+  c->ev0 = c->pass_ev[ksp - 1][ipc != 0][0];
+  c->ev1 = c->pass_ev[ksp - 1][ipc != 0][1];
+  c->pass_timed[ksp - 1][ipc != 0] = false;
+  rc = ensure_prep(c, p, ksp);
   if (rc) return rc;
   const GP& g = c->g;
   PushParams pp;
@@ -664,16 +858,43 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CK(cudaEventRecord(c->ev1, c->stream));
       if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c); }   // k_lane / k_*_quad sum wkix/wkih themselves
     }
+    // moment sum + fold; in deferred mode they run on the communication stream, so the next call's particle
+    // kernel overlaps them and the host does not wait here
+    cudaStream_t ms = c->stream;
+    if (c->opt_defer) {
+      CK(cudaEventRecord(c->ev_kernel, c->stream));
+      CK(cudaStreamWaitEvent(c->cstream, c->ev_kernel, 0));
+      ms = c->cstream;
+    }
     if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
-      int n = g_nccl.AllReduce(s.M4, s.M4, (size_t)g.ntot * 4 + 2, kNcclFloat64, kNcclSum, c->comm, c->stream);
+      int n = g_nccl.AllReduce(s.M4, s.M4, (size_t)g.ntot * 4 + 2, kNcclFloat64, kNcclSum, c->comm, ms);
       if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
     }
     Ptr4 o; for (int k = 0; k < 4; k++) o.p[k] = s.out4[k];
-    k_fold_unpack<<<grid_for(g.ntot, 256), 256, 0, c->stream>>>(g, s.M4, o, 1); CKL(c);   // F:2398, 2544
+    k_fold_unpack<<<grid_for(g.ntot, 256), 256, 0, ms>>>(g, s.M4, o, 1); CKL(c);   // F:2398, 2544
+    s.have_moments = true;
+    if (c->opt_defer) {
+      CK(cudaMemcpyAsync(c->wk_pinned + 2 * (ksp - 1), s.M4 + (size_t)g.ntot * 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, ms));
+      s.sink_filled = false;
+      if (s.sink[0] || s.sink[1] || s.sink[2] || s.sink[3]) {   // D2H of the moments overlaps the next particle kernel too
+        for (int k = 0; k < 4; k++) {
+          if (!s.sink[k]) continue;
+          CK(cudaMemcpyAsync(s.sink[k], s.out4[k], (size_t)g.ntot * sizeof(double), cudaMemcpyDeviceToHost, ms));
+          c->d2h += (long long)g.ntot * (long long)sizeof(double);
+        }
+        s.sink_filled = true;
+      }
+      CK(cudaEventRecord(s.done, ms));
+      s.pending = true;
+      s.wk_user[0] = wkix; s.wk_user[1] = wkih;
+      c->pass_timed[ksp - 1][1] = s.n > 0;
+      c->d2h += 2 * (long long)sizeof(double);
+      return MRG_OK;
+    }
+    s.sink_filled = false;
     CK(cudaMemcpyAsync(wk_host, s.M4 + (size_t)g.ntot * 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    s.have_moments = true;
   } else {
     int slab_n = 0;
     if (pp.drive_on) {
@@ -727,6 +948,9 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         if (!pair && !lane && !quad) CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
         key_out = s.key;
       }
+      unsigned* zocc = nullptr;
+      if (tiled && !pair) { rc = zocc_begin(c, s, &zocc); if (rc) return rc; }
+      else s.zocc_valid = false;
       CK(cudaEventRecord(c->ev0, c->stream));
       if (quad) {
         Slab sl{c->slab_bits, c->slab_list, c->slab_count};
@@ -743,7 +967,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       } else if (tiled) {
         k_correct_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, c->slab_bits, c->slab_list,
                                                     c->slab_count, key_out, s.hist, p->hdt, scatter ? s.key : nullptr,
-                                                    s.cell_end2, D);
+                                                    s.cell_end2, D, zocc);
         s.hist_valid = !scatter;
         fused_scatter = scatter;
       } else {
@@ -751,6 +975,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       }
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
+      if (zocc) { rc = zocc_fetch(c, s, p->hdt); if (rc) return rc; }   // completed by the synchronize below
       if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
       if (fused_scatter) {   // the spare buffers now hold the updated particles in the next order
         for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
@@ -788,6 +1013,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     }
     CK(cudaStreamSynchronize(c->stream));
   }
+  c->pass_timed[ksp - 1][ipc != 0] = s.n > 0;
   if (s.n > 0) {
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -807,6 +1033,8 @@ int mrg_get_moments(mrg_ctx* c, int32_t ksp, double* qjx, double* qjy, double* q
   Species& s = c->sp[ksp - 1];
   if (!s.have_moments) return fail(MRG_ERR_STATE, "no ipc>=1 call has produced moments for this species yet");
   CK(cudaSetDevice(c->device));
+  rc = complete_moments(c, ksp - 1);
+  if (rc) return rc;
   double* h[4] = {qjx, qjy, qjz, q};
   const size_t gb = (size_t)c->g.ntot * sizeof(double);
   double* const* src = s.out4;
@@ -817,10 +1045,22 @@ int mrg_get_moments(mrg_ctx* c, int32_t ksp, double* qjx, double* qjy, double* q
   }
   for (int k = 0; k < 4; k++) {
     if (!h[k]) continue;
+    if (folded && s.sink_filled && h[k] == s.sink[k]) continue;   // already delivered by the deferred call
     CK(cudaMemcpyAsync(h[k], src[k], gb, cudaMemcpyDeviceToHost, c->stream));
     c->d2h += (long long)gb;
   }
   CK(cudaStreamSynchronize(c->stream));
+  return MRG_OK;
+}
+
+int mrg_set_moment_sink(mrg_ctx* c, int32_t ksp, double* qjx, double* qjy, double* qjz, double* q) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  rc = complete_moments(c, ksp - 1);
+  if (rc) return rc;
+  Species& s = c->sp[ksp - 1];
+  s.sink[0] = qjx; s.sink[1] = qjy; s.sink[2] = qjz; s.sink[3] = q;
+  s.sink_filled = false;
   return MRG_OK;
 }
 
@@ -829,6 +1069,8 @@ int mrg_get_moments_device(mrg_ctx* c, int32_t ksp, const double* dev4[4]) {
   if (rc) return rc;
   Species& s = c->sp[ksp - 1];
   if (!s.have_moments) return fail(MRG_ERR_STATE, "no ipc>=1 call has produced moments for this species yet");
+  rc = complete_moments(c, ksp - 1);
+  if (rc) return rc;
   for (int k = 0; k < 4; k++) dev4[k] = s.out4[k];
   return MRG_OK;
 }
@@ -836,7 +1078,7 @@ int mrg_get_moments_device(mrg_ctx* c, int32_t ksp, const double* dev4[4]) {
 int mrg_get_prepared_fields(mrg_ctx* c, const mrg_step_params* p, double* const a6[6]) {
   if (!c || !p || !a6) return fail(MRG_ERR_ARG, "null argument");
   CK(cudaSetDevice(c->device));
-  int rc = ensure_prep(c, p);
+  int rc = ensure_prep(c, p, 0);   // every plane
   if (rc) return rc;
   const size_t gb = (size_t)c->g.ntot * sizeof(double);
   Ptr6 o;
@@ -868,13 +1110,20 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
   rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
   if (rc) return rc;
   const int B = 256;
+  // planes the next pass gathers from: kept when the last corrector tracked them for this look-ahead
+  unsigned* zocc = nullptr;
+  if (!(s.zocc_valid && s.zocc_lookahead == lookahead)) { rc = zocc_begin(c, s, &zocc); if (rc) return rc; }
   if (!(s.keys_valid && s.keys_lookahead == lookahead)) {   // the corrector may already have emitted the keys
     CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
-    k_sort_keys<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, s.key, s.hist); CKL(c);
-  } else if (!s.hist_valid) {
-    CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
-    k_key_hist<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.hist); CKL(c);
+    k_sort_keys<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, s.key, s.hist, zocc); CKL(c);
+  } else {
+    if (!s.hist_valid) {
+      CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+      k_key_hist<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.hist); CKL(c);
+    }
+    if (zocc) { k_mark_planes<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, zocc); CKL(c); }
   }
+  if (zocc) { rc = zocc_fetch(c, s, lookahead); if (rc) return rc; }   // completed by the synchronize below
   s.keys_valid = false;
   const bool lane_layout = c->opt_tile == 3;
   rc = scan_excl(c, s.hist, lane_layout ? c->cursor : s.cell_end, c->ncell + 1, nullptr);
@@ -927,6 +1176,13 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
   } else if (n == "shard") {
     if (value < 0 || value > 1) return fail(MRG_ERR_ARG, "shard must be 0 (round-robin, the reference) or 1 (z slabs)");
     c->opt_shard = (int)value;
+  } else if (n == "planes") {
+    if (value < -1 || value > 1) return fail(MRG_ERR_ARG, "planes must be -1 (when nranks > 1), 0 (never) or 1 (always)");
+    c->opt_planes = (int)value;
+    for (auto& sp : c->sp) sp.zocc_valid = false;
+  } else if (n == "defer") {
+    if (!value) { for (int k = 0; k < c->nspecies; k++) { int rc = complete_moments(c, k); if (rc) return rc; } }
+    c->opt_defer = value != 0;
   } else if (n == "group_min") {
     if (value < 1 || value > 9) return fail(MRG_ERR_ARG, "group_min must be in 1..9 (particles per sub-iteration group)");
     c->opt_group_min = (int)value;
@@ -970,6 +1226,41 @@ int mrg_synchronize(mrg_ctx* c) {
   if (!c) return fail(MRG_ERR_ARG, "null context");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
+  CK(cudaStreamSynchronize(c->cstream));
+  for (int k = 0; k < c->nspecies; k++) { int rc = complete_moments(c, k); if (rc) return rc; }
+  return MRG_OK;
+}
+
+int mrg_pass_ms(mrg_ctx* c, int32_t ksp, int32_t ipc, double* ms) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (!ms) return fail(MRG_ERR_ARG, "null argument");
+  *ms = 0.0;
+  if (!c->pass_timed[ksp - 1][ipc != 0]) return MRG_OK;
+  CK(cudaSetDevice(c->device));
+  cudaEvent_t* e = c->pass_ev[ksp - 1][ipc != 0];
+  CK(cudaEventSynchronize(e[1]));
+  float f = 0.f;
+  CK(cudaEventElapsedTime(&f, e[0], e[1]));
+  *ms = f;
+  return MRG_OK;
+}
+
+int mrg_plane_sets(int32_t mz, const uint8_t* occ, int32_t* listB, int32_t* listGI, int32_t* listG, int32_t n[3]) {
+  if (mz < 4 || !occ || !listB || !listGI || !listG || !n) return fail(MRG_ERR_ARG, "bad argument");
+  PlaneSets ps;
+  plane_sets(mz, std::vector<char>(occ, occ + mz + 1), ps);
+  std::copy(ps.listB.begin(), ps.listB.end(), listB);
+  std::copy(ps.listGI.begin(), ps.listGI.end(), listGI);
+  std::copy(ps.listG.begin(), ps.listG.end(), listG);
+  n[0] = (int32_t)ps.listB.size(); n[1] = (int32_t)ps.listGI.size(); n[2] = (int32_t)ps.listG.size();
+  return MRG_OK;
+}
+
+int mrg_get_prep_stats(mrg_ctx* c, int64_t out[3], int32_t reset) {
+  if (!c || !out) return fail(MRG_ERR_ARG, "null argument");
+  out[0] = c->prep_count; out[1] = c->prep_restricted_count; out[2] = c->prep_planes_sum;
+  if (reset) { c->prep_count = 0; c->prep_restricted_count = 0; c->prep_planes_sum = 0; }
   return MRG_OK;
 }
 

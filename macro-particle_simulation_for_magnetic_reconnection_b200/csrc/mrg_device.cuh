@@ -158,6 +158,18 @@ __device__ __forceinline__ int sort_cell_folded(const GP& g, double x, double y,
   return ip + g.mx * (jp + g.my * kp);
 }
 
+// z plane kp of the gather cell of the NEXT pass over this particle: the exact z part of F:1165 (half-step
+// estimate), partbcEST (F:1941-1947) and F:1177, with make_stencil's clamp.  The passes read the prepared
+// fields on planes kp-1..kp+1 only, which lets a rank prepare just the planes near its particles.
+__device__ __forceinline__ int gather_plane(const GP& g, double z, double vz, double hdt) {
+  double rz = __dadd_rn(z, __dmul_rn(hdt, vz));
+  const bool zge = ge_pos(rz, g.zhi), zle = le_neg(rz, g.zlo);
+  rz = __dadd_rn(rz, zge ? -g.zmaxe : (zle ? g.zmaxe : 0.0));
+  double d;
+  const int kp = floor_pos(__dadd_rn(__dmul_rn(g.hzi, rz), 0.500000001), d);
+  return min(max(kp, 0), g.mz);
+}
+
 // Gather of the six prepared fields (F:1217-1270) from the packed array
 // F6[node][6] = (exa,eya,eza,bxa,bya,bza): 9 x 128-bit loads per stencil row.
 // The 18 weights are formed as fx*(fy*fz); the sum order differs from the

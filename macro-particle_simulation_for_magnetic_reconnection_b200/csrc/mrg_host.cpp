@@ -18,7 +18,9 @@ struct HostState {
   mrg_ctx* ctx = nullptr;
   bool resident[MRG_MAX_SPECIES] = {false, false, false, false};
   int corrector_calls[MRG_MAX_SPECIES] = {0, 0, 0, 0};
-  bool fields_dirty = true, auto_fields = true;
+  bool auto_fields = true;
+  unsigned dirty = 0xFFFu;     // members of COMMON /fields/ the device copy is stale for
+  bool renew = false;          // ex0 <- ex still to be repeated on the device
   int sort_interval = 1;
   bool exit_on_error = true;
   int status = 0;
@@ -51,7 +53,12 @@ void mrg_host_unbind(void) {
   H = HostState();
 }
 
-void mrg_host_fields_changed(void) { H.fields_dirty = true; }
+void mrg_host_fields_changed(void) { H.dirty = 0xFFFu; }
+void mrg_host_fields_changed_mask(uint32_t mask) { H.dirty |= (mask & 0xFFFu); }
+void mrg_host_fields_renewed(void) {
+  if (H.auto_fields) H.dirty |= 0xFC0u;
+  else H.renew = true;
+}
 void mrg_host_set_auto_fields(int32_t on) { H.auto_fields = on != 0; }
 void mrg_host_set_sort_interval(int32_t n) { H.sort_interval = n < 0 ? 0 : n; }
 void mrg_host_set_exit_on_error(int32_t on) { H.exit_on_error = on != 0; }
@@ -95,11 +102,18 @@ void fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz,
     if (rc) return die("mrg_upload_particles", rc);
     H.resident[k - 1] = true;
   }
-  if (H.fields_dirty || (H.auto_fields && k == 1)) {
+  if (H.auto_fields && k == 1) H.dirty = 0xFFFu;
+  if (H.renew) {                                          // F:796-807 on the device copies
+    rc = mrg_renew_fields(H.ctx);
+    if (rc) return die("mrg_renew_fields", rc);
+    H.renew = false;
+    H.dirty &= ~0xFC0u;
+  }
+  if (H.dirty) {
     const double* f12[12] = {v.ex, v.ey, v.ez, v.bx, v.by, v.bz, v.ex0, v.ey0, v.ez0, v.bx0, v.by0, v.bz0};
-    rc = mrg_set_fields(H.ctx, 0xFFFu, f12);
+    rc = mrg_set_fields(H.ctx, H.dirty, f12);
     if (rc) return die("mrg_set_fields", rc);
-    H.fields_dirty = false;
+    H.dirty = 0;
   }
   mrg_step_params p;
   p.dt = *v.dt; p.adt = *v.adt; p.hdt = *v.hdt; p.aimpl = *v.aimpl;

@@ -49,6 +49,13 @@ void mrg_host_unbind(void);
  * always moves ions first after a field change, F:761-766, 782-787). */
 void mrg_host_fields_changed(void);
 void mrg_host_set_auto_fields(int32_t on);
+/* Finer hints for a host that marks its three field updates in trans (turn
+ * auto_fields off first): bit i of mask = member i of COMMON /fields/ changed
+ * on the host (prefld F:759 -> 0x038 bx,by,bz; emfild F:771 -> 0x03F ex..bz);
+ * renewed = the host ran the loop ex0 <- ex (F:796-807), which is then
+ * repeated on the device copies instead of uploading ex0..bz0. */
+void mrg_host_fields_changed_mask(uint32_t mask);
+void mrg_host_fields_renewed(void);
 /* Cell-sort every n-th corrector call of a species (0 = never). */
 void mrg_host_set_sort_interval(int32_t n);
 /* 0: return to the caller after an error (mrg_host_status() != 0) instead of

@@ -22,25 +22,52 @@ struct CPtr6 { const double* p[6]; };
 struct CPtr12 { const double* p[12]; };
 struct Ptr4 { double* p[4]; };
 
+// Warp-aggregated marking of occupied planes: bit kp of occ[] (all lanes call; lanes with valid = false mark
+// nothing).  `cache` remembers the plane the warp marked last, so a cell-sorted warp issues one atomic per run.
+__device__ __forceinline__ void mark_plane(unsigned* __restrict__ occ, int kp, bool valid, int& cache) {
+  const int lo = __reduce_min_sync(0xffffffffu, valid ? kp : 0x7fffffff);
+  const int hi = __reduce_max_sync(0xffffffffu, valid ? kp : -1);
+  if (hi < 0 || (lo == hi && lo == cache)) return;              // warp-uniform
+  const int lane = threadIdx.x & 31;
+  if (lo == hi) {
+    if (lane == 0) atomicOr(occ + (lo >> 5), 1u << (lo & 31));
+    cache = lo;
+  } else {
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned m = __match_any_sync(act, kp);
+      if (lane == __ffs(m) - 1) atomicOr(occ + (kp >> 5), 1u << (kp & 31));
+    }
+    cache = -1;
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Field preparation.  Interior = i in [0,mx), j in [0,my], k in [0,mz).
 // All arithmetic follows the source association with _rn intrinsics so the
 // prepared fields are bit-identical to the CPU restatement.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ bool interior_ijk(const GP& g, long long t, int& i, int& j, int& k) {
-  const long long n = (long long)g.mx * (g.my + 1) * g.mz;
+// `planes` != nullptr restricts the work to the listed z planes (k values): the
+// particle passes of a rank that owns a z slab only read the prepared fields
+// near its particles, so the other planes need not be prepared (PlaneSet in
+// mrg_api.cu works out which planes each stage needs).
+__device__ __forceinline__ bool interior_ijk(const GP& g, long long t, const int* __restrict__ planes, int nplanes,
+                                             int& i, int& j, int& k) {
+  const long long n = (long long)g.mx * (g.my + 1) * nplanes;
   if (t >= n) return false;
   i = (int)(t % g.mx);
   long long r = t / g.mx;
   j = (int)(r % (g.my + 1));
   k = (int)(r / (g.my + 1));
+  if (planes) k = planes[k];
   return true;
 }
 
 // F:1127-1139: A = aimpl*f + (1-aimpl)*f0 (+dc for B); then F:7351-7359: T = A - dc.
-__global__ void k_blend(GP g, CPtr12 f, Ptr6 A, Ptr6 T, double aimpl, double om, double bxc, double byc, double bzc) {
+__global__ void k_blend(GP g, CPtr12 f, Ptr6 A, Ptr6 T, double aimpl, double om, double bxc, double byc, double bzc,
+                        const int* __restrict__ planes, int nplanes) {
   int i, j, k;
-  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k)) return;
+  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, planes, nplanes, i, j, k)) return;
   const int m = node_of(g, i, j, k);
   const double dc[6] = {0.0, 0.0, 0.0, bxc, byc, bzc};
 #pragma unroll
@@ -55,9 +82,9 @@ __global__ void k_blend(GP g, CPtr12 f, Ptr6 A, Ptr6 T, double aimpl, double om,
 // One (-1,4,10,4,-1)/16 sweep, F:7365-7395 (AXIS=2, z), F:7401-7434 (AXIS=0, x),
 // F:7438-7492 (AXIS=1, y with wall mirror rows; rows j=0 and j=my are copied).
 template <int AXIS>
-__global__ void k_filter(GP g, CPtr6 S, Ptr6 D) {
+__global__ void k_filter(GP g, CPtr6 S, Ptr6 D, const int* __restrict__ planes, int nplanes) {
   int i, j, k;
-  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k)) return;
+  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, planes, nplanes, i, j, k)) return;
   const int m = node_of(g, i, j, k);
 #pragma unroll
   for (int c = 0; c < 6; c++) {
@@ -99,16 +126,31 @@ __global__ void k_filter(GP g, CPtr6 S, Ptr6 D) {
 // interior nodes take the filtered value + dc (F:7498-7506); every ghost node
 // takes what outmesh3 (F:3088-3148) left there BEFORE the filter ran, i.e. the
 // unfiltered blend A of the periodic image, or zero on rows j=-1, my+1.
-__global__ void k_finalize(GP g, CPtr6 A, CPtr6 T, double* __restrict__ F6, double bxc, double byc, double bzc) {
-  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (t >= g.ntot) return;
+// With a plane list the entries are EXTENDED plane indices k+2; an entry with
+// bit 30 set is a guard plane (just outside the prepared set) and is filled
+// with NaN, so a gather that strays beyond the prepared planes cannot pass
+// unnoticed.
+constexpr int PLANE_GUARD = 1 << 30;
+__global__ void k_finalize(GP g, CPtr6 A, CPtr6 T, double* __restrict__ F6, double bxc, double byc, double bzc,
+                           const int* __restrict__ planes, int nplanes) {
+  long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= (long long)g.nxy * nplanes) return;
+  bool guard = false;
+  if (planes) {
+    const int e = planes[t / g.nxy];
+    guard = (e & PLANE_GUARD) != 0;
+    t = (t % g.nxy) + (long long)(e & ~PLANE_GUARD) * g.nxy;
+  }
   const int i = (int)(t % g.nx) - 2;
   const int j = (int)((t / g.nx) % g.ny) - 1;
   const int k = (int)(t / g.nxy) - 2;
   const bool in = (i >= 0 && i < g.mx && j >= 0 && j <= g.my && k >= 0 && k < g.mz);
   const double dc[6] = {0.0, 0.0, 0.0, bxc, byc, bzc};
   double out[6];
-  if (in) {
+  if (guard) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) out[c] = __longlong_as_double(0x7ff8000000000000ll);
+  } else if (in) {
 #pragma unroll
     for (int c = 0; c < 6; c++) out[c] = __dadd_rn(T.p[c][t], dc[c]);
   } else if (j < 0 || j > g.my) {
@@ -451,10 +493,15 @@ __global__ void __launch_bounds__(SCAN_BLOCK) k_scan_apply(const int* __restrict
 // ---------------------------------------------------------------------------
 // Cell sort (maintenance).  key = cell of wrap(x + lookahead*v), i fastest.
 // ---------------------------------------------------------------------------
-__global__ void k_sort_keys(GP g, ParticleSoA P, double lookahead, int* __restrict__ key, int* __restrict__ hist) {
+__global__ void k_sort_keys(GP g, ParticleSoA P, double lookahead, int* __restrict__ key, int* __restrict__ hist,
+                            unsigned* __restrict__ zocc) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const bool valid = t < P.n;
   int kcell = -1;
+  if (zocc) {   // planes the next pass gathers from (exact, unlike the key)
+    int cache = -1;
+    mark_plane(zocc, valid ? gather_plane(g, P.z[t], P.vz[t], lookahead) : 0, valid, cache);
+  }
   if (valid) {
     double x = fma(lookahead, P.vx[t], P.x[t]);
     double y = fma(lookahead, P.vy[t], P.y[t]);
@@ -504,6 +551,14 @@ __global__ void k_unpermute(long long n, const int* __restrict__ id, const doubl
 // local index; word_off = exclusive popcount scan; the n-th slab particle (in
 // l order) uses state*lambda^(n+1).
 // ---------------------------------------------------------------------------
+// planes the next pass gathers from, for an order whose keys were not made by k_sort_keys
+__global__ void k_mark_planes(GP g, ParticleSoA P, double lookahead, unsigned* __restrict__ zocc) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool valid = t < P.n;
+  int cache = -1;
+  mark_plane(zocc, valid ? gather_plane(g, P.z[t], P.vz[t], lookahead) : 0, valid, cache);
+}
+
 __global__ void k_popc(const unsigned* __restrict__ bits, long long nwords, int* __restrict__ out) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t < nwords) out[t] = __popc(bits[t]);

@@ -596,7 +596,7 @@ __global__ void __launch_bounds__(PR_WARPS * 32, MRG_CORR_MINB)
 k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, const int* __restrict__ cell_end,
                double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits, int* __restrict__ slab_list,
                int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead,
-               const int* __restrict__ prekey, int* __restrict__ cursor, SortArrays D) {
+               const int* __restrict__ prekey, int* __restrict__ cursor, SortArrays D, unsigned* __restrict__ zocc) {
   __shared__ __align__(128) double sF[6 * TILE_ROW_D];
   __shared__ __align__(16) double sRing[PR_WARPS][NSTAGE * 6 * STAGE_D];
   __shared__ __align__(8) unsigned long long sBar[PR_WARPS][NSTAGE];
@@ -618,6 +618,7 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     // a return value) is waited for: keys are loaded two iterations ahead, slots claimed one ahead.
     int pk1 = 0, pk2 = 0;        // keys of iterations it + 1, it + 2
     int cb = 0, crk = 0;         // claim of the current iteration: base (in the run's head lane), rank in the run
+    int zcache = -1;             // last plane this warp marked in zocc
     if (prekey) {
       int pk0 = 0;
       if (st.a + lane < st.b) pk0 = __ldcs(prekey + st.a + lane);
@@ -655,6 +656,7 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       if (__any_sync(FULL, maybe_wrap(g, x, y, z))) {
         if (wrap_pos(g, x, y, z)) vy = -vy;                   // partbc, F:1337
       }
+      if (zocc) mark_plane(zocc, gather_plane(g, z, vz, lookahead), valid, zcache);   // planes of the next pass' gather
       int d = p;                                              // slot the updated particle is written to
       if (prekey) {
         d = __shfl_sync(FULL, cb, lane - crk) + crk;          // claimed one iteration ago

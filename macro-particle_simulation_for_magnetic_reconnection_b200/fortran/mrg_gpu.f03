@@ -18,6 +18,12 @@
 !*        ierr = mrg_host_set_unique_id(id)                             *
 !*   5. call mrg_pull_particles before restrt(iresrt=2) / diag1 and     *
 !*      mrg_host_particles_changed after restrt(iresrt=1).              *
+!*   6. (optional, saves 3/4 of the host->device field traffic) mark    *
+!*      the three places where trans changes COMMON /fields/:           *
+!*        call mrg_host_set_auto_fields(0)         ! once, before trans *
+!*        call mrg_host_fields_changed_mask(56)    ! after prefld F:759 *
+!*        call mrg_host_fields_changed_mask(63)    ! after emfild F:771 *
+!*        call mrg_host_fields_renewed()           ! after F:796-807    *
 !***********************************************************************
       module mrg_gpu
       use, intrinsic :: iso_c_binding
@@ -72,6 +78,24 @@
         subroutine mrg_host_fields_changed () &
                      bind(C,name='mrg_host_fields_changed')
         end subroutine mrg_host_fields_changed
+!
+        subroutine mrg_host_set_auto_fields (on) &
+                     bind(C,name='mrg_host_set_auto_fields')
+          import :: C_INT32_T
+          integer(C_INT32_T),value :: on
+        end subroutine mrg_host_set_auto_fields
+!
+!  bit i-1 of mask = i-th member of common/fields/ was rewritten on the host
+        subroutine mrg_host_fields_changed_mask (mask) &
+                     bind(C,name='mrg_host_fields_changed_mask')
+          import :: C_INT32_T
+          integer(C_INT32_T),value :: mask
+        end subroutine mrg_host_fields_changed_mask
+!
+!  the host has run the renewal loop ex0 <- ex (F:796-807)
+        subroutine mrg_host_fields_renewed () &
+                     bind(C,name='mrg_host_fields_renewed')
+        end subroutine mrg_host_fields_renewed
 !
         subroutine mrg_host_set_sort_interval (n) &
                      bind(C,name='mrg_host_set_sort_interval')

@@ -137,6 +137,13 @@ class MrgContext:
         arr = (C.c_void_p * 12)(*ptrs)
         check(self.lib.mrg_set_fields_device(self.h, mask, arr))
 
+    def bind_fields_device(self, ptrs, mask=0xFFF):
+        arr = (C.c_void_p * 12)(*ptrs)
+        check(self.lib.mrg_bind_fields_device(self.h, mask, arr))
+
+    def renew_fields(self):
+        check(self.lib.mrg_renew_fields(self.h))
+
     def prepared_fields(self, params):
         out = [np.zeros(self.n_grid) for _ in range(6)]
         arr = (capi.dp * 6)(*[as_dp(a) for a in out])
@@ -150,6 +157,25 @@ class MrgContext:
         check(self.lib.mrg_fulmov(self.h, ksp, qmult, wmult, ipc, C.byref(params), C.byref(st),
                                   C.byref(wkix), C.byref(wkih)))
         return wkix.value, wkih.value, st.value
+
+    def fulmov_deferred(self, ksp, qmult, wmult, params):
+        """ipc=1 call in deferred mode (option "defer"): returns a pair of c_double that the library fills
+        with wkix/wkih when the host next waits for the species (moments(), synchronize())."""
+        st = C.c_int32(0)
+        wk = (C.c_double(), C.c_double())
+        check(self.lib.mrg_fulmov(self.h, ksp, qmult, wmult, 1, C.byref(params), C.byref(st),
+                                  C.byref(wk[0]), C.byref(wk[1])))
+        return wk
+
+    def pass_ms(self, ksp, ipc):
+        ms = C.c_double()
+        check(self.lib.mrg_pass_ms(self.h, ksp, ipc, C.byref(ms)))
+        return ms.value
+
+    def prep_stats(self, reset=False):
+        out = (C.c_int64 * 3)()
+        check(self.lib.mrg_get_prep_stats(self.h, out, 1 if reset else 0))
+        return {"preps": out[0], "restricted": out[1], "planes": out[2]}
 
     def moments(self, ksp, folded=True, out=None):
         arrs = out if out is not None else [np.zeros(self.n_grid) for _ in range(4)]
@@ -200,9 +226,21 @@ class Fulmov:
     mod(it,nha)==0 on io_pe==1 (F:1320-1328), ranfb advanced by the kick.
     The host particle arrays are only read on the first call per species (or
     after particles_changed); use pull() before host code looks at them.
+
+    Field traffic.  Without hints every ksp==1 call uploads all of COMMON /fields/ (the mirror cannot see
+    what the host changed).  A host that marks its three field updates avoids most of it:
+        fields_changed(MASK_B)      after prefld (F:759, writes bx,by,bz)
+        fields_changed(MASK_NEW)    after emfild (F:771, writes ex..bz)
+        fields_renewed()            after the renewal loop ex0 <- ex (F:796-807): done on the device
+    With `defer=True` the two ipc=1 calls only queue their work: the NCCL sum, the fold and the copy of
+    the moments into COMMON /srimp7/ of one species overlap the particle kernel of the next;
+    `finish_moments()` (call it before emfild reads /srimp7/) waits and fills wkix/wkih/edec.
     """
 
-    def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1, ctx=None):
+    MASK_NEW, MASK_B, MASK_OLD, MASK_ALL = 0x03F, 0x038, 0xFC0, 0xFFF
+
+    def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1, ctx=None, hints=False,
+                 defer=False):
         self.c = common
         self.ipar, self.size = ipar, size
         self.resident = {}
@@ -216,15 +254,59 @@ class Fulmov:
                 if uid is None:
                     raise ValueError("size > 1 needs the NCCL unique id broadcast from rank 0")
                 self.ctx.comm_init(uid)
-        self.fields_dirty = True
+        self.hints = hints
+        self.dirty = self.MASK_ALL
+        self.renew = False
         self.sort_interval = sort_interval
         self.ncorr = {1: 0, 2: 0}
+        self.defer = defer
+        self.inflight = {}
+        self.ctx.set_option("defer", 1 if defer else 0)
+        self.sinks = {}
 
-    def fields_changed(self):
-        self.fields_dirty = True
+    def fields_changed(self, mask=0xFFF):
+        self.dirty |= mask
+
+    def fields_renewed(self):
+        """The host has copied ex..bz into ex0..bz0 (F:796-807)."""
+        if self.hints:
+            self.renew = True
+        else:
+            self.dirty |= self.MASK_OLD
 
     def particles_changed(self, ksp):
         self.resident.pop(ksp, None)
+
+    def _moment_arrays(self, ksp):
+        c = self.c
+        return [c.qix, c.qiy, c.qiz, c.qi] if ksp == 1 else [c.qex, c.qey, c.qez, c.qe]
+
+    def _push_fields(self, ksp):
+        if not self.hints and ksp == 1:
+            self.dirty = self.MASK_ALL
+        if self.renew:
+            self.ctx.renew_fields()
+            self.renew = False
+            self.dirty &= ~self.MASK_OLD
+        if self.dirty:
+            self.ctx.set_fields(self.c.fields(), mask=self.dirty)
+            self.dirty = 0
+
+    def _record_wk(self, ksp, wkix, wkih):
+        c = self.c
+        c.wkix, c.wkih = wkix, wkih
+        if c.it % c.nha == 0 and c.io_pe == 1:
+            col = 5 if ksp == 1 else 7
+            c.edec[col - 1, c.ldec - 1] = wkix
+            c.edec[col, c.ldec - 1] = wkih
+
+    def finish_moments(self):
+        """Deferred mode: wait for the queued ipc=1 calls; COMMON /srimp7/, wkix/wkih, edec are then set."""
+        for ksp in sorted(self.inflight):
+            wk = self.inflight[ksp]
+            self.ctx.moments(ksp, folded=True, out=self._moment_arrays(ksp))
+            self._record_wk(ksp, wk[0].value, wk[1].value)
+        self.inflight = {}
 
     def __call__(self, x, y, z, vx, vy, vz, qmult, wmult, npr, ipc, ksp):
         c = self.c
@@ -233,18 +315,21 @@ class Fulmov:
         if not self.resident.get(ksp):
             self.ctx.upload(ksp, x[:npr], y[:npr], z[:npr], vx[:npr], vy[:npr], vz[:npr], self.ipar, self.size)
             self.resident[ksp] = npr
-        if self.fields_dirty or ksp == 1:
-            self.ctx.set_fields(c.fields())
-            self.fields_dirty = False
+        if ipc == 0 and self.inflight:
+            self.finish_moments()
+        self._push_fields(ksp)
+        if ipc >= 1 and self.defer:
+            out = self._moment_arrays(ksp)
+            key = tuple(a.ctypes.data for a in out)
+            if self.sinks.get(ksp) != key:
+                check(self.ctx.lib.mrg_set_moment_sink(self.ctx.h, ksp, *[as_dp(a) for a in out]))
+                self.sinks[ksp] = key
+            self.inflight[ksp] = self.ctx.fulmov_deferred(ksp, qmult, wmult, c.step_params())
+            return
         wkix, wkih, c.ranfb = self.ctx.fulmov(ksp, qmult, wmult, ipc, c.step_params(), c.ranfb)
-        c.wkix, c.wkih = wkix, wkih
-        if c.it % c.nha == 0 and c.io_pe == 1:
-            col = 5 if ksp == 1 else 7
-            c.edec[col - 1, c.ldec - 1] = wkix
-            c.edec[col, c.ldec - 1] = wkih
+        self._record_wk(ksp, wkix, wkih)
         if ipc >= 1:
-            out = [c.qix, c.qiy, c.qiz, c.qi] if ksp == 1 else [c.qex, c.qey, c.qez, c.qe]
-            self.ctx.moments(ksp, folded=True, out=out)
+            self.ctx.moments(ksp, folded=True, out=self._moment_arrays(ksp))
         else:
             self.ncorr[ksp] += 1
             if self.sort_interval and self.ncorr[ksp] % self.sort_interval == 0:

@@ -79,4 +79,22 @@ void emul_push(const double* gp /*packed GP doubles*/, const int* gi, const doub
     for (int kz = 0; kz < 3; kz++) for (int ix = 0; ix < 3; ix++) qvy_wxz[8 + kz * 3 + ix] = s.fx[ix] * s.fz[kz];
   }
 }
+
+// gather_plane (plane bookkeeping of the restricted preparation) against the kp make_stencil<true> finds for the
+// same particle: returns gather_plane - stencil kp (must be 0)
+int emul_gather_plane_diff(const double* gp, const int* gi, double x, double y, double z, double vx, double vy, double vz, double hdt) {
+  GP g;
+  g.mx = gi[0]; g.my = gi[1]; g.mz = gi[2];
+  g.nx = g.mx + 4; g.ny = g.my + 3; g.nz = g.mz + 4; g.nxy = g.nx * g.ny; g.ntot = (long long)g.nxy * g.nz;
+  g.xmax = gp[0]; g.ymax = gp[1]; g.zmax = gp[2];
+  g.hx = g.xmax / g.mx; g.hy = g.ymax / g.my; g.hz = g.zmax / g.mz;
+  g.hxi = 0.9999999999999 / g.hx; g.hyi = 0.9999999999999 / g.hy; g.hzi = 0.9999999999999 / g.hz;
+  g.xmaxe = 0.9999999999999 * g.xmax; g.zmaxe = 0.9999999999999 * g.zmax;
+  g.xlo = -(g.hx / 2); g.xhi = g.xmax - g.hx / 2; g.zlo = -(g.hz / 2); g.zhi = g.zmax - g.hz / 2; g.ymax2 = 2.0 * g.ymax;
+  double rx = __dadd_rn(x, __dmul_rn(hdt, vx)), ry = __dadd_rn(y, __dmul_rn(hdt, vy)), rz = __dadd_rn(z, __dmul_rn(hdt, vz));
+  wrap_pos(g, rx, ry, rz);
+  Stencil s;
+  make_stencil<true>(g, rx, ry, rz, s);
+  return gather_plane(g, z, vz, hdt) - s.kp;
+}
 }

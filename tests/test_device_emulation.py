@@ -30,6 +30,7 @@ def emul():
     L = C.CDLL(so)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     L.emul_push.argtypes = [dp, ip, dp, dp] + [C.c_double] * 6 + [C.c_int, dp, dp, ip, dp]
+    L.emul_gather_plane_diff.argtypes = [dp, ip] + [C.c_double] * 7
     return L
 
 
@@ -101,3 +102,19 @@ def test_device_arithmetic_matches_oracle(emul, ksp):
                 M[m, keys[l] + ix + jy * nx + kz * nxy] += fac[l, g9] * fac[l, 8 + r]
     for m in range(4):
         assert U.rel_l2(M[m], r1["raw"][m]) < 1e-12
+
+
+def test_gather_plane_is_the_stencil_plane(emul):
+    """gather_plane (what the corrector and the sort record for the restricted field preparation) is the kp
+    the next pass' make_stencil computes, seams included."""
+    p = U.make_parm(8, 6, 8)
+    rng = np.random.default_rng(5)
+    arrs = _edge_particles(p, rng, 600)
+    arrs[5][5:10] = [-0.4, 0.4, -0.4, 0.4, 0.0]          # cross the z seams
+    gp = np.array([p.xmax, p.ymax, p.zmax])
+    gi = np.array([p.mx, p.my, p.mz], dtype=np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    for hdt in (0.0, 0.6, 5.0):
+        for l in range(len(arrs[0])):
+            d = emul.emul_gather_plane_diff(gp.ctypes.data_as(dp), gi.ctypes.data_as(ip), *[float(a[l]) for a in arrs], hdt)
+            assert d == 0, (hdt, l)
