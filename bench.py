@@ -163,6 +163,8 @@ def run_reference(args):
 
 
 def workload_config(n, args):
+    if getattr(args, "slab_of", None):
+        n = args.slab_of[0]
     mx, my, mz = GRIDS[n] if not args.grid else tuple(args.grid)
     return {"workload": "two-flux-bundle equilibrium (rec_3d80A / param_080A.h), %dx%dx%d grid, %d ppc/species, "
                         "ions+electrons mi/me=100, dt=1.2, aimpl=0.6 (BASELINE configs[%s])"
@@ -193,6 +195,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     mx, my, mz = GRIDS[args.gpus] if not args.grid else tuple(args.grid)
+    if args.slab_of:      # one GPU holds what one rank of an N-GPU job holds (no NCCL): development aid, not a bench line
+        mx, my, mz = GRIDS[args.slab_of[0]]
     ppc = args.ppc
     ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, rank=rank, nranks=world, device=local)
     if world > 1:
@@ -205,6 +209,10 @@ def run_ours(args):
     ctx.set_option("fused_keys", args.fused_keys)
     ctx.set_option("fused_sort", args.fused_sort)
     ctx.set_option("shard", 1 if args.shard == "slab" else 0)
+    if args.slab_of:
+        ctx.set_option("shard", 1)
+        ctx.set_option("slab_of", args.slab_of[0])
+        ctx.set_option("slab_index", args.slab_of[1])
     ctx.set_option("planes", args.planes)
     ctx.set_option("defer", args.defer)
     # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
@@ -212,7 +220,7 @@ def run_ours(args):
     for ksp in (1, 2):
         _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
     nloc = ctx.num_local(1) + ctx.num_local(2)
-    ntot_particles = 2 * mx * my * mz * ppc
+    ntot_particles = 2 * mx * my * mz * ppc if not args.slab_of else nloc
     n_grid = ctx.n_grid
     c = mrg.Common(4, 4, 4, 1.0, 1.0, 1.0, dt=DT, aimpl=AIMPL, wce_by_wpe=WCE, Ez00=EZ00)   # scalars only
     c.mx, c.my, c.mz, c.xmax, c.ymax, c.zmax = mx, my, mz, HX * mx, HY * my, HZ * mz
@@ -392,6 +400,9 @@ def run_ours(args):
     if rank == 0:
         cfg = workload_config(args.gpus, args)
         cfg["parallelism"] = "particle-sharded x%d" % world
+        if args.slab_of:
+            cfg["emulated_rank"] = "slab %d of %d on one GPU, no NCCL sum (development aid, not a bench line)" % (args.slab_of[1], args.slab_of[0])
+        cfg["prep"] = ctx.prep_stats()
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
@@ -424,6 +435,8 @@ def main():
                     help="particle ownership for --gpus > 1: z slabs of the initial positions, or the reference's round-robin")
     ap.add_argument("--planes", type=int, default=-1, help="restricted field preparation: -1 = when N > 1, 0 = off, 1 = on")
     ap.add_argument("--defer", type=int, default=1, help="1 = moment sum + fold on the second stream (overlaps the next kernel)")
+    ap.add_argument("--slab-of", type=int, nargs=2, default=None, metavar=("N", "I"),
+                    help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
@@ -431,6 +444,8 @@ def main():
     args = ap.parse_args()
     if args.gpus not in GRIDS and not args.grid:
         raise SystemExit("--gpus must be 1, 2, 4 or 8 (or give --grid)")
+    if args.slab_of:
+        args.no_e2e = True
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -177,6 +177,10 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                summed over ranks do not depend on the ownership; with
  *                replicated grids the slab choice keeps every GPU's particles
  *                dense in the cells it touches
+ *   "slab_of", "slab_index"  sizing aid for "shard" = 1: mrg_loadpt loads z
+ *                slab slab_index of slab_of whatever nranks is, so that one
+ *                GPU can hold exactly what one rank of a larger job holds
+ *                (slab_of = 0, the default, means nranks / rank)
  *   "planes"     restricted field preparation: the tiled corrector and
  *                mrg_sort record which z planes the next pass gathers from,
  *                and section 0 (blend/filter/ghost fill) then runs on those

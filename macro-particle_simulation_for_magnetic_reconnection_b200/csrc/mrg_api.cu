@@ -9,6 +9,7 @@
 #include "mrg_lane.cuh"
 #include "mrg_quad.cuh"
 
+#include <cuda.h>
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -117,7 +118,14 @@ struct Species {
   unsigned* zocc = nullptr;
   std::vector<unsigned> zocc_host;
   bool zocc_valid = false;
+  bool zocc_approx = false;    // recorded by the corrector with contracted arithmetic: good to +-1 plane, widened by ensure_prep
   double zocc_lookahead = 0.0;
+  // z planes of the current sort order that own slots (exact, from the cell index): tiled launches cover
+  // only the arc kz0 .. kz0+nkz-1 (mod mz) instead of every pencil of the replicated grid
+  unsigned* kocc = nullptr;
+  std::vector<unsigned> kocc_host;
+  bool hull_valid = false, kocc_pending = false;
+  int kz0 = 0, nkz = 0;
   // deferred completion (option "defer"): the moment sum, fold and wkix/wkih of the last ipc>=1 call run on the
   // communication stream; done marks their end, wk_user receives wkix/wkih when the host next waits for them
   cudaEvent_t done = nullptr;
@@ -188,6 +196,7 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_slab_n = 0, opt_slab_i = 0;   // "slab_of"/"slab_index": mrg_loadpt loads slab i of n whatever nranks is (sizing aid)
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
 };
@@ -195,6 +204,45 @@ struct mrg_ctx {
 namespace {
 
 int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+// ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+TensorMapEncodeFn g_encode = nullptr;
+int tensor_map_init() {
+  if (g_encode) return MRG_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (q != cudaDriverEntryPointSuccess || !fn) return fail(MRG_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+  g_encode = (TensorMapEncodeFn)fn;
+  return MRG_OK;
+}
+// the six SoA rows of a particle set as a [6][cap] fp64 tensor; box = 32 slots x 6 rows
+int particle_map(const double* base, long long cap, CUtensorMap* tm) {
+  int rc = tensor_map_init();
+  if (rc) return rc;
+  const cuuint64_t gdim[2] = {(cuuint64_t)cap, 6};
+  const cuuint64_t gstr[1] = {(cuuint64_t)cap * sizeof(double)};
+  const cuuint32_t box[2] = {32, 6}, estr[2] = {1, 1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MRG_ERR_CUDA, "cuTensorMapEncodeTiled(particles) failed: " + std::to_string((int)r));
+  return MRG_OK;
+}
+// an int32 array (ids, sort keys) as a 1-D tensor; box = 32 elements
+int int_map(const int* base, long long n, CUtensorMap* tm) {
+  int rc = tensor_map_init();
+  if (rc) return rc;
+  const cuuint64_t gdim[1] = {(cuuint64_t)std::max<long long>(n, 32)};
+  const cuuint64_t gstr[1] = {0};          // rank 1 has no strides; the encoder still wants a pointer
+  const cuuint32_t box[1] = {32}, estr[1] = {1};
+  CUresult r = g_encode(tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 1, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MRG_ERR_CUDA, "cuTensorMapEncodeTiled(int32) failed: " + std::to_string((int)r));
+  return MRG_OK;
+}
 
 int ensure(mrg_ctx* c, void** p, long long* cap, long long need, size_t elem) {
   if (*cap >= need && *p) return MRG_OK;
@@ -230,11 +278,12 @@ long long owned_count(long long npr, long long first, long long stride) {
 int alloc_species(mrg_ctx* c, Species& s, long long n) {
   long long cap = ((n + 63) / 64) * 64 + 64;
   if (s.cap < cap) {
-    for (int k = 0; k < 6; k++) {
-      if (s.d[k]) CK(cudaFree(s.d[k]));
-      s.d[k] = nullptr;
-      CK(cudaMalloc((void**)&s.d[k], (size_t)cap * sizeof(double)));
-    }
+    // the six arrays of a set are rows of ONE block (row stride = cap), so that a 2-D TMA box can fetch the
+    // same 32 slots of all six with one instruction (particle_map)
+    if (s.d[0]) CK(cudaFree(s.d[0]));
+    for (int k = 0; k < 6; k++) s.d[k] = nullptr;
+    CK(cudaMalloc((void**)&s.d[0], (size_t)cap * 6 * sizeof(double)));
+    for (int k = 1; k < 6; k++) s.d[k] = s.d[0] + (size_t)k * cap;
     s.cap = cap;
   }
   if (s.id) { CK(cudaFree(s.id)); s.id = nullptr; }
@@ -245,6 +294,7 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   s.prekeys_valid = false;
   s.fresh = false;
   s.zocc_valid = false;
+  s.hull_valid = false;
   if (!s.cell_end) {
     CK(cudaMalloc((void**)&s.cell_end, (size_t)(c->ncell + 1) * sizeof(int)));
     CK(cudaMalloc((void**)&s.cell_end2, (size_t)(c->ncell + 1) * sizeof(int)));
@@ -262,11 +312,10 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
 // so that buffers (and their id arrays) can be swapped by mrg_sort
 int ensure_alt(mrg_ctx* c, long long cap, bool exact) {
   if (exact ? (c->alt_cap == cap) : (c->alt_cap >= cap)) return MRG_OK;
-  for (int k = 0; k < 6; k++) {
-    if (c->alt[k]) CK(cudaFree(c->alt[k]));
-    c->alt[k] = nullptr;
-    CK(cudaMalloc((void**)&c->alt[k], (size_t)cap * sizeof(double)));
-  }
+  if (c->alt[0]) CK(cudaFree(c->alt[0]));
+  for (int k = 0; k < 6; k++) c->alt[k] = nullptr;
+  CK(cudaMalloc((void**)&c->alt[0], (size_t)cap * 6 * sizeof(double)));
+  for (int k = 1; k < 6; k++) c->alt[k] = c->alt[0] + (size_t)k * cap;
   if (c->alt_id) CK(cudaFree(c->alt_id));
   c->alt_id = nullptr;
   CK(cudaMalloc((void**)&c->alt_id, (size_t)cap * sizeof(int)));
@@ -320,15 +369,62 @@ int zocc_begin(mrg_ctx* c, Species& s, unsigned** out) {
   return MRG_OK;
 }
 // queue the copy of the bitmap to the host; the caller synchronises the stream afterwards
-int zocc_fetch(mrg_ctx* c, Species& s, double lookahead) {
+int zocc_fetch(mrg_ctx* c, Species& s, double lookahead, bool approx) {
   const int nw = zocc_words(c);
   s.zocc_host.assign(nw, 0u);
   CK(cudaMemcpyAsync(s.zocc_host.data(), s.zocc, (size_t)nw * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
   s.zocc_valid = true;
+  s.zocc_approx = approx;
   s.zocc_lookahead = lookahead;
   return MRG_OK;
 }
 bool occ_bit(const Species& s, int kp) { return (s.zocc_host[kp >> 5] >> (kp & 31)) & 1u; }
+// OR the species' gather planes into occ[0..mz]
+void add_occupancy(const Species& s, int mz, std::vector<char>& occ) {
+  if (s.n == 0) return;
+  for (int kp = 0; kp <= mz; kp++) {
+    if (!occ_bit(s, kp)) continue;
+    occ[kp] = 1;
+    if (s.zocc_approx && kp < mz) {        // +-1 plane, and the clamp plane kp = mz next to the seam (F:1177 with z within 1e-9 hz of zmax - hz/2)
+      occ[(kp + mz - 1) % mz] = 1;
+      occ[(kp + 1) % mz] = 1;
+      if (kp <= 1 || kp >= mz - 2) occ[mz] = 1;
+    }
+  }
+}
+// key-plane occupancy of the order being built -> bitmap on the host after the caller's synchronize
+int kocc_begin(mrg_ctx* c, Species& s, const int* cell_start) {
+  if (!tracking(c)) return MRG_OK;
+  const int nw = zocc_words(c);
+  if (!s.kocc) CK(cudaMalloc((void**)&s.kocc, (size_t)nw * sizeof(unsigned)));
+  CK(cudaMemsetAsync(s.kocc, 0, (size_t)nw * sizeof(unsigned), c->stream));
+  k_plane_occupancy<<<grid_for(c->g.mz, 128), 128, 0, c->stream>>>(cell_start, c->g.mx * c->g.my, c->g.mz, s.kocc); CKL(c);
+  s.kocc_host.assign(nw, 0u);
+  CK(cudaMemcpyAsync(s.kocc_host.data(), s.kocc, (size_t)nw * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  s.kocc_pending = true;
+  return MRG_OK;
+}
+// after the synchronize: smallest arc of planes that holds every particle of the new order
+void kocc_finish(mrg_ctx* c, Species& s) {
+  s.hull_valid = false;
+  if (!s.kocc_pending) return;
+  s.kocc_pending = false;
+  const int mz = c->g.mz;
+  auto bit = [&](int k) { return (s.kocc_host[k >> 5] >> (k & 31)) & 1u; };
+  int best_len = 0, best_start = 0;        // longest circular run of empty planes
+  for (int k0 = 0; k0 < mz; k0++) {
+    if (bit(k0) || !bit((k0 + mz - 1) % mz)) continue;   // runs start right after an occupied plane
+    int len = 0;
+    while (len < mz && !bit((k0 + len) % mz)) len++;
+    if (len > best_len) { best_len = len; best_start = k0; }
+  }
+  bool any = false;
+  for (int k = 0; k < mz; k++) any = any || bit(k);
+  if (!any) return;
+  s.kz0 = (best_start + best_len) % mz;
+  s.nkz = mz - best_len;
+  s.hull_valid = true;
+}
 
 // Plane sets of a restricted preparation from the occupancy occ[kp], kp = 0..mz (see ensure_prep):
 //   G      extended planes (k+2) of F6 to finalize: k = kp-1..kp+1
@@ -381,9 +477,12 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
     if (covered) {
       const Species& s = c->sp[ksp - 1];
       covered = usable(s);
-      if (covered && s.n > 0)
+      if (covered && s.n > 0) {
+        std::vector<char> occ(mz + 1, 0);
+        add_occupancy(s, mz, occ);
         for (int kp = 0; kp <= mz && covered; kp++)
-          if (occ_bit(s, kp)) covered = c->prep_planes[kp + 1] && c->prep_planes[kp + 2] && c->prep_planes[kp + 3];
+          if (occ[kp]) covered = c->prep_planes[kp + 1] && c->prep_planes[kp + 2] && c->prep_planes[kp + 3];
+      }
     }
     if (covered) return MRG_OK;
   }
@@ -394,11 +493,7 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   ps.G.assign(nz, 0);
   if (restricted) {
     std::vector<char> occ(mz + 1, 0);
-    for (int k = 0; k < c->nspecies; k++) {
-      const Species& s = c->sp[k];
-      if (s.n == 0) continue;
-      for (int kp = 0; kp <= mz; kp++) occ[kp] |= (char)occ_bit(s, kp);
-    }
+    for (int k = 0; k < c->nspecies; k++) add_occupancy(c->sp[k], mz, occ);
     plane_sets(mz, occ, ps);
     if (ps.listB.empty() || (long long)ps.listB.size() * 4 > (long long)mz * 3) restricted = false;   // not worth it
   }
@@ -502,6 +597,7 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   g.ymax2 = 2.0 * ymax;
   auto hi32 = [](double v) { long long b; memcpy(&b, &v, 8); return (int)(b >> 32); };
   g.xhi_h = hi32(g.xhi); g.xlo_h = hi32(g.xlo); g.ymax_h = hi32(g.ymax); g.zhi_h = hi32(g.zhi); g.zlo_h = hi32(g.zlo);
+  g.kz0 = 0; g.nkz = mz;
   c->ncell = (long long)mx * my * mz;
   {
     cudaDeviceProp prop;
@@ -552,12 +648,13 @@ int mrg_destroy(mrg_ctx* c) {
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 12; k++) cudaFree(c->f12[k]);
-  for (int k = 0; k < 6; k++) { cudaFree(c->A6[k]); cudaFree(c->T1[k]); cudaFree(c->T2[k]); cudaFree(c->alt[k]); cudaFree(c->tmp6[k]); }
+  for (int k = 0; k < 6; k++) { cudaFree(c->A6[k]); cudaFree(c->T1[k]); cudaFree(c->T2[k]); cudaFree(c->tmp6[k]); }
+  cudaFree(c->alt[0]);
   cudaFree(c->F6); cudaFree(c->alt_id);
   for (auto& s : c->sp) {
-    for (int k = 0; k < 6; k++) cudaFree(s.d[k]);
+    cudaFree(s.d[0]);
     cudaFree(s.id); cudaFree(s.M4); cudaFree(s.cell_end); cudaFree(s.cell_end2); cudaFree(s.key); cudaFree(s.hist);
-    cudaFree(s.zocc);
+    cudaFree(s.zocc); cudaFree(s.kocc);
     if (s.done) cudaEventDestroy(s.done);
     for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
   }
@@ -689,7 +786,9 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
   long long n = owned_count(npr, first, stride);
   if (n >= (1LL << 31) - 64) return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU");
   Species& s = c->sp[ksp - 1];
-  const bool slab = c->opt_shard == 1 && c->nranks > 1;
+  const int nslab = c->opt_slab_n > 0 ? c->opt_slab_n : c->nranks;
+  const int islab = c->opt_slab_n > 0 ? c->opt_slab_i : c->rank;
+  const bool slab = c->opt_shard == 1 && nslab > 1;
   if (!slab) {
     rc = alloc_species(c, s, n);
     if (rc) return rc;
@@ -709,7 +808,7 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
     int* bc = nullptr;
     CK(cudaMalloc((void**)&bc, (size_t)(nb + 1) * sizeof(int)));
     CK(cudaMemsetAsync(bc + nb, 0, sizeof(int), c->stream));
-    k_loadpt_slab_count<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, npr, c->nranks, c->rank, bc); CKL(c);
+    k_loadpt_slab_count<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, npr, nslab, islab, bc); CKL(c);
     rc = scan_excl(c, bc, bc, nb + 1, nullptr);
     if (rc) { cudaFree(bc); return rc; }
     int total = 0;
@@ -718,7 +817,7 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
     n = total;
     rc = alloc_species(c, s, n);
     if (rc) { cudaFree(bc); return rc; }
-    if (n > 0) { k_loadpt_slab_fill<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, soa(s), npr, c->nranks, c->rank, bc); CKL(c); }
+    if (n > 0) { k_loadpt_slab_fill<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, soa(s), npr, nslab, islab, bc); CKL(c); }
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaFree(bc));
   } else if (n > 0) { k_loadpt<<<grid_for(n, 256), 256, 0, c->stream>>>(g, L, soa(s)); CKL(c); }
@@ -818,7 +917,9 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       s.prekeys_valid = false;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
-      if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz;
+      GP gl = g;                               // tiled launches cover only the z planes of the order that own slots
+      if (tiled && s.hull_valid) { gl.kz0 = s.kz0; gl.nkz = s.nkz; }
+      if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * gl.nkz;
       if (lane) blocks = ((g.mx + LT_CELLS - 1) / LT_CELLS) * g.my * g.mz;
       if (quad) blocks = ((g.mx + QT_CELLS - 1) / QT_CELLS) * g.my * g.mz;
       const int nparts = pair ? blocks * PRED_NW : (tiled ? 1 : blocks);   // pair kernels: one partial per warp; tiled: two atomic accumulators
@@ -834,7 +935,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         k_lane<1><<<std::min(blocks, c->lane_grid[1]), 32, 0, c->stream>>>(g, pp, P, Q, c->F6, s.cell_end, s.M4 + (size_t)g.ntot * 4, Slab{nullptr, nullptr, nullptr}, nullptr, 0.0, blocks); CKL(c);
         k_lane_deposit<<<std::min(blocks, c->lane_grid[2]), 32, 0, c->stream>>>(g, qmult, Q, s.M4, s.cell_end, blocks);
       }
-      else if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
+      else if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(gl, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
       else if (tiled) {
         int* prekey = nullptr;
         if (c->opt_fused_sort) {   // keys + histogram of the next order; the corrector scatters by them
@@ -843,7 +944,10 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
           CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
           prekey = s.key;
         }
-        k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+        CUtensorMap tmP;
+        rc = particle_map(s.d[0], s.cap, &tmP);
+        if (rc) return rc;
+        k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(gl, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
         s.prekeys_valid = prekey != nullptr;
         s.keys_valid = false;
       }
@@ -923,9 +1027,11 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       const bool tiled = !lane && !quad && c->opt_tile && c->opt_tile < 3 && s.index_valid && s.layout == 0;
       const bool pair = tiled && c->opt_tile == 2;
       const int B = lane ? 32 : (pair ? CORR_NW * 32 : ((tiled || quad) ? 128 : 256));
+      GP gl = g;
+      if (tiled && s.hull_valid) { gl.kz0 = s.kz0; gl.nkz = s.nkz; }
       const int blocks = lane ? ((g.mx + LT_CELLS - 1) / LT_CELLS) * g.my * g.mz
                               : quad ? ((g.mx + QT_CELLS - 1) / QT_CELLS) * g.my * g.mz
-                              : (tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * g.mz : grid_for(s.n, B));
+                              : (tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * gl.nkz : grid_for(s.n, B));
       const int nparts = pair ? blocks * CORR_NW : (tiled ? 1 : blocks);
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
@@ -938,6 +1044,8 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         rc = ensure_alt(c, s.cap, true);
         if (rc) return rc;
         rc = scan_excl(c, s.hist, s.cell_end2, c->ncell + 1, nullptr);
+        if (rc) return rc;
+        rc = kocc_begin(c, s, s.cell_end2);
         if (rc) return rc;
         for (int k = 0; k < 6; k++) { D.src[k] = s.d[k]; D.dst[k] = c->alt[k]; }
         D.id_src = s.id; D.id_dst = c->alt_id;
@@ -962,12 +1070,20 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         s.hist_valid = false;
       } else if (pair) {
         Slab sl{c->slab_bits, c->slab_list, c->slab_count};
-        k_correct_pair<CORR_NW><<<blocks, B, CorrSmem<CORR_NW>::bytes, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, sl, key_out, p->hdt);
+        k_correct_pair<CORR_NW><<<blocks, B, CorrSmem<CORR_NW>::bytes, c->stream>>>(gl, pp, P, c->F6, s.cell_end, c->wk_partial, sl, key_out, p->hdt);
         s.hist_valid = false;
       } else if (tiled) {
-        k_correct_tile<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk_partial, c->slab_bits, c->slab_list,
-                                                    c->slab_count, key_out, s.hist, p->hdt, scatter ? s.key : nullptr,
-                                                    s.cell_end2, D, zocc);
+        CUtensorMap tmP, tmId, tmKey;
+        memset(&tmId, 0, sizeof(tmId));
+        memset(&tmKey, 0, sizeof(tmKey));
+        rc = particle_map(s.d[0], s.cap, &tmP);
+        if (!rc && s.id) rc = int_map(s.id, s.cap, &tmId);
+        if (!rc && scatter) rc = int_map(s.key, s.key_cap, &tmKey);
+        if (rc) return rc;
+        for (int k = 0; k < 6; k++) D.src_rw[k] = s.d[k];
+        k_correct_tile<<<blocks, B, 0, c->stream>>>(gl, pp, tmP, tmId, tmKey, s.id ? 1 : 0, c->F6, s.cell_end, c->wk_partial,
+                                                    c->slab_bits, c->slab_list, c->slab_count, key_out, s.hist, p->hdt,
+                                                    scatter ? 1 : 0, s.cell_end2, D, zocc);
         s.hist_valid = !scatter;
         fused_scatter = scatter;
       } else {
@@ -975,7 +1091,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       }
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
-      if (zocc) { rc = zocc_fetch(c, s, p->hdt); if (rc) return rc; }   // completed by the synchronize below
+      if (zocc) { rc = zocc_fetch(c, s, p->hdt, true); if (rc) return rc; }   // completed by the synchronize below
       if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
       if (fused_scatter) {   // the spare buffers now hold the updated particles in the next order
         for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
@@ -1012,6 +1128,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       }
     }
     CK(cudaStreamSynchronize(c->stream));
+    if (fused_scatter) kocc_finish(c, s);   // planes of the order the particles are in now
   }
   c->pass_timed[ksp - 1][ipc != 0] = s.n > 0;
   if (s.n > 0) {
@@ -1123,11 +1240,13 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
     }
     if (zocc) { k_mark_planes<<<grid_for(s.n, B), B, 0, c->stream>>>(c->g, soa(s), lookahead, zocc); CKL(c); }
   }
-  if (zocc) { rc = zocc_fetch(c, s, lookahead); if (rc) return rc; }   // completed by the synchronize below
+  if (zocc) { rc = zocc_fetch(c, s, lookahead, false); if (rc) return rc; }   // completed by the synchronize below
   s.keys_valid = false;
   const bool lane_layout = c->opt_tile == 3;
   rc = scan_excl(c, s.hist, lane_layout ? c->cursor : s.cell_end, c->ncell + 1, nullptr);
   if (rc) return rc;
+  s.kocc_pending = false;
+  if (!lane_layout) { rc = kocc_begin(c, s, s.cell_end); if (rc) return rc; }
   SortArrays A;
   for (int k = 0; k < 6; k++) { A.src[k] = s.d[k]; A.dst[k] = c->alt[k]; }
   A.id_src = s.id; A.id_dst = c->alt_id;
@@ -1139,6 +1258,7 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
     k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.cell_end, A); CKL(c);
   }
   CK(cudaStreamSynchronize(c->stream));
+  kocc_finish(c, s);
   s.index_valid = true;
   s.layout = lane_layout ? 1 : 0;
   // the spare buffer becomes the species' storage and vice versa
@@ -1176,6 +1296,13 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
   } else if (n == "shard") {
     if (value < 0 || value > 1) return fail(MRG_ERR_ARG, "shard must be 0 (round-robin, the reference) or 1 (z slabs)");
     c->opt_shard = (int)value;
+  } else if (n == "slab_of") {
+    if (value < 0 || value > 4096) return fail(MRG_ERR_ARG, "slab_of must be 0 (= nranks) or a slab count");
+    c->opt_slab_n = (int)value;
+    if (c->opt_slab_i >= std::max(c->opt_slab_n, 1)) c->opt_slab_i = 0;
+  } else if (n == "slab_index") {
+    if (value < 0 || value >= std::max(c->opt_slab_n, 1)) return fail(MRG_ERR_ARG, "slab_index must be in [0, slab_of)");
+    c->opt_slab_i = (int)value;
   } else if (n == "planes") {
     if (value < -1 || value > 1) return fail(MRG_ERR_ARG, "planes must be -1 (when nranks > 1), 0 (never) or 1 (always)");
     c->opt_planes = (int)value;

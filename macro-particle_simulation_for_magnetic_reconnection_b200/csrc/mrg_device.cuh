@@ -24,6 +24,7 @@ struct GP {
   double zlo, zhi;
   double ymax2;            // 2*ymax             (F:1867)
   int xhi_h, xlo_h, ymax_h, zhi_h, zlo_h;   // high words of the partbc limits (maybe_wrap pre-test)
+  int kz0, nkz;            // z planes of the sort order that hold particles: kz0 .. kz0+nkz-1 (mod mz); tiled launches cover only these
 };
 
 // node index of (i,j,k) in the (-2:mx+1,-1:my+1,-2:mz+1) layout
@@ -168,6 +169,14 @@ __device__ __forceinline__ int gather_plane(const GP& g, double z, double vz, do
   double d;
   const int kp = floor_pos(__dadd_rn(__dmul_rn(g.hzi, rz), 0.500000001), d);
   return min(max(kp, 0), g.mz);
+}
+
+// The same plane with contracted arithmetic and no wrap (three fp64 instructions instead of seven, no branch): for
+// a wrapped z the result lies in [-1, mz] and, folded into [0, mz), is within one plane of gather_plane -- or
+// gather_plane is the clamp value mz and the folded result is a plane next to the seam.  The corrector records
+// this one; ensure_prep widens accordingly (add_occupancy in mrg_api.cu).
+__device__ __forceinline__ int gather_plane_fast(const GP& g, double z, double vz, double hdt) {
+  return __double2loint(__dadd_rd(fma(g.hzi, fma(hdt, vz, z), 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
 }
 
 // Gather of the six prepared fields (F:1217-1270) from the packed array

@@ -521,6 +521,7 @@ __global__ void k_sort_keys(GP g, ParticleSoA P, double lookahead, int* __restri
 struct SortArrays {
   const double* src[6]; double* dst[6];
   const int* id_src; int* id_dst;
+  double* src_rw[6];     // the set being read, writable (corrector that updates in place)
 };
 __global__ void k_sort_scatter(long long n, const int* __restrict__ key, int* __restrict__ cursor, SortArrays A) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -551,6 +552,14 @@ __global__ void k_unpermute(long long n, const int* __restrict__ id, const doubl
 // local index; word_off = exclusive popcount scan; the n-th slab particle (in
 // l order) uses state*lambda^(n+1).
 // ---------------------------------------------------------------------------
+// z planes of a cell-sorted order that hold particles: bit k of occ[] is set when the cells of plane k own slots.
+// `start` is the exclusive scan of the cell histogram (ncell + 1 entries), read BEFORE the scatter advances it.
+__global__ void k_plane_occupancy(const int* __restrict__ start, int cells_per_plane, int mz, unsigned* __restrict__ occ) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= mz) return;
+  if (start[(size_t)(k + 1) * cells_per_plane] > start[(size_t)k * cells_per_plane]) atomicOr(occ + (k >> 5), 1u << (k & 31));
+}
+
 // planes the next pass gathers from, for an order whose keys were not made by k_sort_keys
 __global__ void k_mark_planes(GP g, ParticleSoA P, double lookahead, unsigned* __restrict__ zocc) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;

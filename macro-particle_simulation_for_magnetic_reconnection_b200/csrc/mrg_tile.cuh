@@ -19,6 +19,7 @@
 // the L1 / global atomic path, so results never depend on how well the order
 // fits.  F:n = /root/reference/@mrg37-080A.f03 line n.
 #pragma once
+#include <cuda.h>   // CUtensorMap (type only; the descriptors are encoded on the host in mrg_api.cu)
 #include "mrg_kernels.cuh"
 
 namespace mrg {
@@ -266,7 +267,7 @@ __device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, unsi
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   unsigned ok = 0;
 #pragma unroll 1
-  for (int spin = 0; spin < (1 << 26); spin++) {
+  for (int spin = 0; spin < (1 << 22); spin++) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
@@ -292,7 +293,8 @@ __device__ __forceinline__ Tile tile_of(const GP& g, const int* __restrict__ cel
   Tile t;
   const int tx = tile % ntx, r = tile / ntx;
   t.j = r % g.my;
-  t.k = r / g.my;
+  t.k = g.kz0 + r / g.my;                                     // the launch covers planes kz0 .. kz0+nkz-1 (mod mz)
+  if (t.k >= g.mz) t.k -= g.mz;
   t.i0 = tx * TILE_CELLS;
   t.ncell = min(TILE_CELLS, g.mx - t.i0);
   const int c0 = t.i0 + g.mx * (t.j + g.my * t.k);
@@ -367,77 +369,119 @@ __device__ __forceinline__ Kick gather_rotate(const GP& g, const PushParams& pp,
 
 // ---------------------------------------------------------------------------
 // Particle streams.  The NW warps of a CTA split the tile's iterations (32
-// particles each) evenly; every warp pulls its own slice through an NSTAGE-deep
-// ring of shared-memory stages filled by 1-D bulk TMA (six copies per stage,
-// one per SoA array), so the HBM latency is covered by the ring and costs no
-// registers.  A stage holds STAGE_D = 34 doubles per array: bulk copies need
-// 16-byte aligned addresses, so the copy starts at the even index below the
-// slice start (the arrays are allocated with >= 64 elements of slack).
+// particles each) evenly; every warp pulls its own slice through an NS-deep
+// ring of shared-memory stages.  A stage is filled by ONE 2-D tensor TMA copy:
+// the six SoA arrays of a particle set are rows of one allocation, so the box
+// {32 slots} x {6 rows} of the [6][cap] fp64 tensor brings the 32 particles of
+// an iteration (1536 B).  A box must start on a 16-byte boundary of the inner
+// dimension (an unaligned coordinate is an illegal-instruction fault), so the
+// tile's slot range is extended downwards to a multiple of 4 slots and the up
+// to 3 extra leading lanes of its first iteration are masked like the trailing
+// ones of its last.  The corrector adds two 1-D boxes of 32 int32 to the
+// same stage and mbarrier: the slots' original indices and their next-order
+// sort keys.  Issuing a stage costs one elected lane a dozen instructions;
+// the earlier six 1-D bulk copies with their 64-bit address arithmetic were
+// a quarter of the corrector's instruction stream.
 // ---------------------------------------------------------------------------
-constexpr int NSTAGE = 3;
-constexpr int STAGE_D = 34;
+#ifndef MRG_PRED_NSTAGE
+#define MRG_PRED_NSTAGE 3
+#endif
+#ifndef MRG_CORR_NSTAGE
+#define MRG_CORR_NSTAGE 4
+#endif
+constexpr int NSTAGE = 3;          // ring depth of the experimental families (mrg_pair.cuh, mrg_quad.cuh)
+constexpr int STAGE_D = 34;        // their stage: 34 doubles per array (1-D bulk copies start on an even slot)
 constexpr int STAGE_BYTES = STAGE_D * 8;
+constexpr int TSTAGE_P = 6 * 32 * 8;              // particle box of a stage
+constexpr int TSTAGE_PIK = TSTAGE_P + 128 + 128;  // + ids + keys
+
+__device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)   // evict-first, as bulk_g2s_stream
+      : "memory");
+}
+__device__ __forceinline__ void tma_box_1d(void* dst, const CUtensorMap* tm, int c0, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2}], [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(tm), "r"(c0), "r"(smem_u32(bar)), "l"(0x12F0000000000000ull)
+      : "memory");
+}
 
 struct Stream {
-  int a, b;         // this warp's particle slots [a, b)
+  int a, b;         // this warp's particle slots [a, b); a is a multiple of 4 slots ...
+  int lo;           // ... and slots below lo (only in the tile's first iteration) belong to the previous tile
   int nit;          // iterations
   int issued;       // iterations whose copies have been issued
-  double* ring;     // [NSTAGE][6][STAGE_D]
-  unsigned long long* bar;   // [NSTAGE]
+  unsigned char* ring;       // [NS][STAGE]
+  unsigned long long* bar;   // [NS]
 };
+// the descriptors of a launch: particles always; ids / keys may be absent (nullptr)
+struct StreamMaps { const CUtensorMap* p; const CUtensorMap* id; const CUtensorMap* key; };
 
-__device__ __forceinline__ void stream_issue(const ParticleSoA& P, Stream& st, int lane) {
+template <int NS, int STAGE>
+__device__ __forceinline__ void stream_issue(const StreamMaps& M, Stream& st, int lane) {
   if (st.issued < st.nit) {
     if (lane == 0) {
-      const int slot = st.issued % NSTAGE;
-      const int e = (st.a + 32 * st.issued) & ~1;
-      double* dst = st.ring + slot * 6 * STAGE_D;
+      const int slot = st.issued % NS;
+      const int e = st.a + 32 * st.issued;
+      unsigned char* dst = st.ring + slot * STAGE;
       unsigned long long* bar = st.bar + slot;
-      mbar_expect_tx(bar, 6u * STAGE_BYTES);
-      bulk_g2s_stream(dst + 0 * STAGE_D, P.x + e, STAGE_BYTES, bar);
-      bulk_g2s_stream(dst + 1 * STAGE_D, P.y + e, STAGE_BYTES, bar);
-      bulk_g2s_stream(dst + 2 * STAGE_D, P.z + e, STAGE_BYTES, bar);
-      bulk_g2s_stream(dst + 3 * STAGE_D, P.vx + e, STAGE_BYTES, bar);
-      bulk_g2s_stream(dst + 4 * STAGE_D, P.vy + e, STAGE_BYTES, bar);
-      bulk_g2s_stream(dst + 5 * STAGE_D, P.vz + e, STAGE_BYTES, bar);
+      mbar_expect_tx(bar, (unsigned)TSTAGE_P + (M.id ? 128u : 0u) + (M.key ? 128u : 0u));
+      tma_box_2d(dst, M.p, e, 0, bar);
+      if (M.id) tma_box_1d(dst + TSTAGE_P, M.id, e, bar);
+      if (M.key) tma_box_1d(dst + TSTAGE_P + 128, M.key, e, bar);
     }
     st.issued++;
   }
 }
 
 // iterations [w*N/NW, (w+1)*N/NW) of the tile's N = ceil(len/32) go to warp w; starts the ring
-__device__ __forceinline__ void stream_open(const ParticleSoA& P, const Tile& t, int w, int nwarps, int lane, double* ring,
+template <int NS, int STAGE>
+__device__ __forceinline__ void stream_open(const StreamMaps& M, const Tile& t, int w, int nwarps, int lane, unsigned char* ring,
                                             unsigned long long* bar, Stream& st) {
-  const int N = (t.p1 - t.p0 + 31) >> 5;
+  const int base = t.p0 & ~3;                                  // box alignment: 4 slots = 16 bytes of int32, 32 of fp64
+  const int N = (t.p1 - base + 31) >> 5;
   const int i0 = (w * N) / nwarps, i1 = ((w + 1) * N) / nwarps;
-  st.a = t.p0 + 32 * i0;
-  st.b = min(t.p0 + 32 * i1, t.p1);
+  st.a = base + 32 * i0;
+  st.b = min(base + 32 * i1, t.p1);
+  st.lo = t.p0;
   st.nit = i1 - i0;
   st.issued = 0;
   st.ring = ring;
   st.bar = bar;
   if (lane == 0) {
 #pragma unroll
-    for (int s = 0; s < NSTAGE; s++) mbar_init(bar + s, 1);
+    for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
   }
   __syncwarp();
 #pragma unroll
-  for (int s = 0; s < NSTAGE - 1; s++) stream_issue(P, st, lane);
+  for (int s = 0; s < NS - 1; s++) stream_issue<NS, STAGE>(M, st, lane);
 }
 
 // one particle's six phase-space coordinates
 struct P6 { double x, y, z, vx, vy, vz; };
 
-// wait for iteration `it` of the stream, hand lane `lane` its particle, keep the ring full.
-// Must be called by the whole warp, after a __syncwarp() that ends the previous iteration's reads.
-__device__ __forceinline__ void stream_next(const ParticleSoA& P, Stream& st, int it, int lane, P6& o) {
-  stream_issue(P, st, lane);                                   // refill the slot consumed in iteration it-1
-  const int slot = it % NSTAGE;
-  mbar_wait(st.bar + slot, (unsigned)((it / NSTAGE) & 1));
-  const int start = st.a + 32 * it;
-  const double* src = st.ring + slot * 6 * STAGE_D + (start & 1) + lane;
-  o.x = src[0 * STAGE_D]; o.y = src[1 * STAGE_D]; o.z = src[2 * STAGE_D];
-  o.vx = src[3 * STAGE_D]; o.vy = src[4 * STAGE_D]; o.vz = src[5 * STAGE_D];
+template <int NS>
+__device__ __forceinline__ void stream_wait(const Stream& st, int it) {
+  mbar_wait(st.bar + it % NS, (unsigned)((it / NS) & 1));
+}
+// lane's particle of iteration `it` (whose stage has been waited for)
+template <int NS, int STAGE>
+__device__ __forceinline__ void stream_read(const Stream& st, int it, int lane, P6& o) {
+  const double* src = reinterpret_cast<const double*>(st.ring + (it % NS) * STAGE) + lane;
+  o.x = src[0]; o.y = src[32]; o.z = src[64];
+  o.vx = src[96]; o.vy = src[128]; o.vz = src[160];
+}
+template <int NS, int STAGE>
+__device__ __forceinline__ int stream_read_id(const Stream& st, int it, int lane) {
+  return reinterpret_cast<const int*>(st.ring + (it % NS) * STAGE + TSTAGE_P)[lane];
+}
+template <int NS, int STAGE>
+__device__ __forceinline__ int stream_read_key(const Stream& st, int it, int lane) {
+  return reinterpret_cast<const int*>(st.ring + (it % NS) * STAGE + TSTAGE_P + 128)[lane];
 }
 
 // per-warp partial sums of wkix/wkih (F:1282-1283) -> wk_partial[2*(block*nwarps + w)]
@@ -453,16 +497,16 @@ __device__ __forceinline__ void warp_wk_store(double wx, double wh, double* __re
 
 // Rank of the lane inside its run of EQUAL, CONTIGUOUS keys among the valid lanes (cell-sorted lanes carry
 // mostly equal keys; equal keys in separate runs are simply claimed separately).  Returns the rank, the
-// run length in `count` and whether the lane heads its run.  Valid lanes must form a prefix of the warp.
+// run length in `count` and whether the lane heads its run.  The valid lanes must be contiguous.
 __device__ __forceinline__ int run_rank(int key, bool valid, int lane, int& count, bool& head) {
   const int prev = __shfl_up_sync(FULL, key, 1);
-  head = valid && (lane == 0 || key != prev);
-  const unsigned heads = __ballot_sync(FULL, head);
   const unsigned vmask = __ballot_sync(FULL, valid);
+  head = valid && (lane == 0 || key != prev || !((vmask >> (lane - 1)) & 1u));
+  const unsigned heads = __ballot_sync(FULL, head);
   const unsigned below = heads & ((2u << lane) - 1u);          // heads at or below this lane
   const int start = 31 - __clz(below | 1u);
   const unsigned above = heads & ~((2u << lane) - 1u);         // heads above this lane
-  const int end = above ? (__ffs(above) - 1) : __popc(vmask);  // first lane of the next run / number of valid lanes
+  const int end = above ? (__ffs(above) - 1) : (32 - __clz(vmask));   // first lane of the next run / one past the last valid lane
   count = end - start;
   return lane - start;
 }
@@ -485,28 +529,32 @@ __device__ __forceinline__ void warp_wk_atomic(double wx, double wh, double* __r
 // ---------------------------------------------------------------------------
 // Predictor on TMA-staged tiles.
 // ---------------------------------------------------------------------------
-constexpr int PRED_SMEM_BYTES = (6 * TILE_ROW_D + 6 * TILE_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + 256 + NSTAGE * 6 * STAGE_D)) * 8 +
-                                (PR_WARPS * NSTAGE + 1) * 8;
+constexpr int PNS = MRG_PRED_NSTAGE, CNS = MRG_CORR_NSTAGE;
+constexpr int PRED_ACC_D = MRG_PRED_SMEM_TILE ? 6 * TILE_ACC_D : 0;      // the accumulator tile exists only when it is used
+constexpr int PRED_RING_BYTES = PR_WARPS * PNS * TSTAGE_P;               // first in the carve-up: tensor TMA wants 128-byte aligned boxes
+constexpr int PRED_SMEM_BYTES = PRED_RING_BYTES + (6 * TILE_ROW_D + PRED_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + 256)) * 8 +
+                                (PR_WARPS * PNS + 1) * 8;
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_PRED_MINB)
-k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
+k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, const double* __restrict__ F6, double* __restrict__ M4,
                const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min,
                int* __restrict__ prekey, int* __restrict__ prehist) {
   // dynamic shared memory (PRED_SMEM_BYTES > 48 KB static limit), carved up by hand
-  extern __shared__ __align__(128) double smem_dyn[];
-  double* sF = smem_dyn;                                       // [6][TILE_ROW_D]      staged fields
-  double* sM = sF + 6 * TILE_ROW_D;                            // [6][TILE_ACC_D]      moment accumulators
-  double* smW = sM + 6 * TILE_ACC_D;                           // [warps][32*PR_W_STRIDE]
+  extern __shared__ __align__(1024) unsigned char smem_pred[];
+  unsigned char* sRing = smem_pred;                            // [warps][PNS][TSTAGE_P]  particle stages
+  double* sF = reinterpret_cast<double*>(smem_pred + PRED_RING_BYTES);   // [6][TILE_ROW_D]  staged fields
+  double* sM = sF + 6 * TILE_ROW_D;                            // [6][TILE_ACC_D]      moment accumulators (optional)
+  double* smW = sM + PRED_ACC_D;                               // [warps][32*PR_W_STRIDE]
   double* smQ = smW + PR_WARPS * 32 * PR_W_STRIDE;             // [warps][256]
-  double* sRing = smQ + PR_WARPS * 256;                        // [warps][NSTAGE*6*STAGE_D]
-  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sRing + PR_WARPS * NSTAGE * 6 * STAGE_D);   // [warps][NSTAGE] + 1
-  unsigned long long& bar = sBar[PR_WARPS * NSTAGE];
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smQ + PR_WARPS * 256);   // [warps][PNS] + 1
+  unsigned long long& bar = sBar[PR_WARPS * PNS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Tile t = tile_of(g, cell_end, blockIdx.x);
   const bool busy = t.p1 > t.p0;                              // block-uniform
   double wx = 0.0, wh = 0.0;
   if (busy) {
     Stream st;
-    stream_open(P, t, w, PR_WARPS, lane, sRing + w * (NSTAGE * 6 * STAGE_D), sBar + w * NSTAGE, st);   // particles in flight during the field staging
+    const StreamMaps maps{&tmP, nullptr, nullptr};
+    stream_open<PNS, TSTAGE_P>(maps, t, w, PR_WARPS, lane, sRing + w * (PNS * TSTAGE_P), sBar + w * PNS, st);   // particles in flight during the field staging
     if (threadIdx.x == 0) mbar_init(&bar, 1);
 #if MRG_PRED_SMEM_TILE
     for (int e = threadIdx.x; e < 6 * TILE_ACC_D; e += blockDim.x) sM[e] = 0.0;
@@ -528,8 +576,11 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
-      stream_next(P, st, it, lane, c);
-      const bool valid = st.a + 32 * it + lane < st.b;
+      stream_issue<PNS, TSTAGE_P>(maps, st, lane);           // refill the slot consumed in iteration it-1
+      stream_wait<PNS>(st, it);
+      stream_read<PNS, TSTAGE_P>(st, it, lane, c);
+      const int p = st.a + 32 * it + lane;
+      const bool valid = p >= st.lo && p < st.b;
       {
         double qvy[8], wxz[9];
         int key = -1;
@@ -559,7 +610,7 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
           int cnt;
           bool head;
           run_rank(kcell, valid, lane, cnt, head);
-          if (valid) prekey[st.a + 32 * it + lane] = kcell;
+          if (valid) prekey[p] = kcell;
           if (head) atomicAdd(prehist + kcell, cnt);
         }
       }
@@ -591,15 +642,23 @@ k_predict_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
 // wrap(x' + lookahead*v') (next step's sort key) and the cell histogram, which
 // lets mrg_sort skip its key pass.  The key is a sorting hint only (any value
 // gives the same results), so it is formed with contracted arithmetic.
+//
+// Fused cell sort (prekey): the keys of the next order arrive in the ring with
+// the particles.  The stage of iteration it+1 is waited for during iteration
+// it (it was issued CNS-1 = 3 iterations earlier), its keys are ranked and the
+// slots of its cell runs claimed with one atomic per run, so neither the key
+// nor the claim (an atomic with a return value) is waited for when iteration
+// it+1 needs them.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_CORR_MINB)
-k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, const int* __restrict__ cell_end,
-               double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits, int* __restrict__ slab_list,
-               int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist, double lookahead,
-               const int* __restrict__ prekey, int* __restrict__ cursor, SortArrays D, unsigned* __restrict__ zocc) {
+k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmId,
+               const __grid_constant__ CUtensorMap tmKey, int have_id, const double* __restrict__ F6,
+               const int* __restrict__ cell_end, double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits,
+               int* __restrict__ slab_list, int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist,
+               double lookahead, int scatter, int* __restrict__ cursor, SortArrays D, unsigned* __restrict__ zocc) {
+  __shared__ __align__(128) unsigned char sRing[PR_WARPS][CNS * TSTAGE_PIK];
   __shared__ __align__(128) double sF[6 * TILE_ROW_D];
-  __shared__ __align__(16) double sRing[PR_WARPS][NSTAGE * 6 * STAGE_D];
-  __shared__ __align__(8) unsigned long long sBar[PR_WARPS][NSTAGE];
+  __shared__ __align__(8) unsigned long long sBar[PR_WARPS][CNS];
   __shared__ __align__(8) unsigned long long bar;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Tile t = tile_of(g, cell_end, blockIdx.x);
@@ -607,43 +666,43 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
   double wx = 0.0, wh = 0.0;
   if (busy) {
     Stream st;
-    stream_open(P, t, w, PR_WARPS, lane, sRing[w], sBar[w], st);
+    const StreamMaps maps{&tmP, have_id ? &tmId : nullptr, scatter ? &tmKey : nullptr};
+    stream_open<CNS, TSTAGE_PIK>(maps, t, w, PR_WARPS, lane, sRing[w], sBar[w], st);
     if (threadIdx.x == 0) mbar_init(&bar, 1);
     __syncthreads();
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     const double hh2 = 0.5 * pp.hh;
     const P6 safe = {0.0, 0.5 * g.hy, 0.0, 0.0, 0.0, 0.0};
-    // Fused cell sort, software-pipelined so that neither the key load nor the slot claim (an atomic with
-    // a return value) is waited for: keys are loaded two iterations ahead, slots claimed one ahead.
-    int pk1 = 0, pk2 = 0;        // keys of iterations it + 1, it + 2
     int cb = 0, crk = 0;         // claim of the current iteration: base (in the run's head lane), rank in the run
-    int zcache = -1;             // last plane this warp marked in zocc
-    if (prekey) {
-      int pk0 = 0;
-      if (st.a + lane < st.b) pk0 = __ldcs(prekey + st.a + lane);
-      if (st.a + 32 + lane < st.b) pk1 = __ldcs(prekey + st.a + 32 + lane);
+    int rlo = 0x7fffffff, rhi = -0x7fffffff;   // range of next-pass gather planes seen by this lane, relative to t.k
+    if (st.nit > 0) stream_wait<CNS>(st, 0);                  // warp-uniform; a warp of a thin tile may have no iteration
+    if (scatter && st.nit > 0) {
+      const int pk0 = stream_read_key<CNS, TSTAGE_PIK>(st, 0, lane);
       int cnt;
       bool head;
-      crk = run_rank(pk0, st.a + lane < st.b, lane, cnt, head);
+      crk = run_rank(pk0, st.a + lane >= st.lo && st.a + lane < st.b, lane, cnt, head);
       if (head) cb = atomicAdd(cursor + pk0, cnt);
     }
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
-      stream_next(P, st, it, lane, c);
+      stream_issue<CNS, TSTAGE_PIK>(maps, st, lane);         // refill the slot consumed in iteration it-1
+      stream_read<CNS, TSTAGE_PIK>(st, it, lane, c);         // stage `it` was waited for one iteration ago
       const int p = st.a + 32 * it + lane;
-      const bool valid = p < st.b;
+      const bool valid = p >= st.lo && p < st.b;
       int kcell = -1;
-      int idv = p;
-      if (valid && P.id) idv = ld_early(P.id + p);
+      const int idv = have_id ? stream_read_id<CNS, TSTAGE_PIK>(st, it, lane) : p;
       int nb = 0, nrk = 0;
-      if (prekey) {                                           // claim for it + 1, key for it + 2
-        if (p + 64 < st.b) pk2 = ld_early(prekey + p + 64);
-        int cnt;
-        bool head;
-        nrk = run_rank(pk1, p + 32 < st.b, lane, cnt, head);
-        if (head) nb = atomicAdd(cursor + pk1, cnt);
+      if (it + 1 < st.nit) {                                  // warp-uniform
+        stream_wait<CNS>(st, it + 1);
+        if (scatter) {                                        // claim the slots of iteration it + 1
+          const int pk1 = stream_read_key<CNS, TSTAGE_PIK>(st, it + 1, lane);
+          int cnt;
+          bool head;
+          nrk = run_rank(pk1, p + 32 < st.b, lane, cnt, head);
+          if (head) nb = atomicAdd(cursor + pk1, cnt);
+        }
       }
       if (!valid) c = safe;                                   // idle lanes push a harmless copy (nothing is stored)
       const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
@@ -656,22 +715,29 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       if (__any_sync(FULL, maybe_wrap(g, x, y, z))) {
         if (wrap_pos(g, x, y, z)) vy = -vy;                   // partbc, F:1337
       }
-      if (zocc) mark_plane(zocc, gather_plane(g, z, vz, lookahead), valid, zcache);   // planes of the next pass' gather
+      if (zocc) {
+        // z plane of the next pass' gather cell, relative to this tile's plane, good to +-1 (contracted arithmetic,
+        // folded in index space); ensure_prep widens the recorded planes by one
+        int kq = gather_plane_fast(g, z, vz, lookahead) - t.k;
+        const int hmz = g.mz >> 1;
+        kq = kq > hmz ? kq - g.mz : (kq < -hmz ? kq + g.mz : kq);
+        if (valid) { rlo = min(rlo, kq); rhi = max(rhi, kq); }
+      }
       int d = p;                                              // slot the updated particle is written to
-      if (prekey) {
+      if (scatter) {
         d = __shfl_sync(FULL, cb, lane - crk) + crk;          // claimed one iteration ago
-        cb = nb; crk = nrk; pk1 = pk2;
+        cb = nb; crk = nrk;
       }
       if (valid) {
         wx += k.wx; wh += k.wh;
         const int id = idv;
-        if (prekey) {
+        if (scatter) {
           __stcs(D.dst[0] + d, x); __stcs(D.dst[1] + d, y); __stcs(D.dst[2] + d, z);
           __stcs(D.dst[3] + d, vx); __stcs(D.dst[4] + d, vy); __stcs(D.dst[5] + d, vz);
           D.id_dst[d] = id;
         } else {
-          __stcs(P.x + p, x); __stcs(P.y + p, y); __stcs(P.z + p, z);
-          __stcs(P.vx + p, vx); __stcs(P.vy + p, vy); __stcs(P.vz + p, vz);
+          __stcs(D.src_rw[0] + p, x); __stcs(D.src_rw[1] + p, y); __stcs(D.src_rw[2] + p, z);
+          __stcs(D.src_rw[3] + p, vx); __stcs(D.src_rw[4] + p, vy); __stcs(D.src_rw[5] + p, vz);
         }
         if (pp.drive_on) {
           if ((fabs(z - pp.zcent) < pp.zw) && ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw))) {
@@ -692,6 +758,18 @@ k_correct_tile(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
         }
       }
       __syncwarp();
+    }
+    if (zocc) {                                               // one range per warp; bits already set cost a load only
+      rlo = __reduce_min_sync(FULL, rlo);
+      rhi = __reduce_max_sync(FULL, rhi);
+      if (lane == 0 && rlo <= rhi) {
+        for (int r = max(rlo, -g.mz); r <= min(rhi, g.mz); r++) {
+          int k = t.k + r;
+          k = k < 0 ? k + g.mz : (k >= g.mz ? k - g.mz : k);
+          k = min(max(k, 0), g.mz - 1);
+          if (!((__ldcg(zocc + (k >> 5)) >> (k & 31)) & 1u)) atomicOr(zocc + (k >> 5), 1u << (k & 31));
+        }
+      }
     }
   }
   warp_wk_atomic(wx, wh, wk_partial);

@@ -82,7 +82,8 @@ void emul_push(const double* gp /*packed GP doubles*/, const int* gi, const doub
 
 // gather_plane (plane bookkeeping of the restricted preparation) against the kp make_stencil<true> finds for the
 // same particle: returns gather_plane - stencil kp (must be 0)
-int emul_gather_plane_diff(const double* gp, const int* gi, double x, double y, double z, double vx, double vy, double vz, double hdt) {
+int emul_gather_plane_diff(const double* gp, const int* gi, double x, double y, double z, double vx, double vy, double vz, double hdt,
+                           int* exact, int* fast) {
   GP g;
   g.mx = gi[0]; g.my = gi[1]; g.mz = gi[2];
   g.nx = g.mx + 4; g.ny = g.my + 3; g.nz = g.mz + 4; g.nxy = g.nx * g.ny; g.ntot = (long long)g.nxy * g.nz;
@@ -95,6 +96,8 @@ int emul_gather_plane_diff(const double* gp, const int* gi, double x, double y, 
   wrap_pos(g, rx, ry, rz);
   Stencil s;
   make_stencil<true>(g, rx, ry, rz, s);
+  if (fast) *fast = gather_plane_fast(g, z, vz, hdt);
+  if (exact) *exact = gather_plane(g, z, vz, hdt);
   return gather_plane(g, z, vz, hdt) - s.kp;
 }
 }

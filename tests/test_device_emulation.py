@@ -30,7 +30,7 @@ def emul():
     L = C.CDLL(so)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
     L.emul_push.argtypes = [dp, ip, dp, dp] + [C.c_double] * 6 + [C.c_int, dp, dp, ip, dp]
-    L.emul_gather_plane_diff.argtypes = [dp, ip] + [C.c_double] * 7
+    L.emul_gather_plane_diff.argtypes = [dp, ip] + [C.c_double] * 7 + [ip, ip]
     return L
 
 
@@ -105,16 +105,34 @@ def test_device_arithmetic_matches_oracle(emul, ksp):
 
 
 def test_gather_plane_is_the_stencil_plane(emul):
-    """gather_plane (what the corrector and the sort record for the restricted field preparation) is the kp
-    the next pass' make_stencil computes, seams included."""
+    """gather_plane (what the sort records for the restricted field preparation) is the kp the next pass'
+    make_stencil computes, seams included; gather_plane_fast (what the corrector records, contracted and
+    unwrapped) is within one plane of it, or next to the seam when the exact value is the clamp plane mz."""
     p = U.make_parm(8, 6, 8)
     rng = np.random.default_rng(5)
     arrs = _edge_particles(p, rng, 600)
     arrs[5][5:10] = [-0.4, 0.4, -0.4, 0.4, 0.0]          # cross the z seams
+    # wrapped positions right at the seams, where the exact path wraps or clamps and the fast one folds
+    zs = [-p.hz / 2, np.nextafter(-p.hz / 2, 1), p.zmax - p.hz / 2 - 1e-10 * p.hz, np.nextafter(p.zmax - p.hz / 2, 0),
+          p.zmax - p.hz / 2 - 5e-10 * p.hz, 0.5 * p.hz, np.nextafter(0.5 * p.hz, 0), np.nextafter(1.5 * p.hz, 2 * p.hz)]
+    arrs[2][20:20 + len(zs)] = zs
+    arrs[5][20:20 + len(zs)] = 0.0
     gp = np.array([p.xmax, p.ymax, p.zmax])
     gi = np.array([p.mx, p.my, p.mz], dtype=np.int32)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int)
+    ex, fa = C.c_int(), C.c_int()
+    mz = p.mz
     for hdt in (0.0, 0.6, 5.0):
         for l in range(len(arrs[0])):
-            d = emul.emul_gather_plane_diff(gp.ctypes.data_as(dp), gi.ctypes.data_as(ip), *[float(a[l]) for a in arrs], hdt)
+            d = emul.emul_gather_plane_diff(gp.ctypes.data_as(dp), gi.ctypes.data_as(ip), *[float(a[l]) for a in arrs], hdt,
+                                            C.byref(ex), C.byref(fa))
             assert d == 0, (hdt, l)
+            z_ok = -p.hz / 2 <= arrs[2][l] < p.zmax - p.hz / 2          # the corrector only sees wrapped z
+            if not z_ok or abs(hdt * arrs[5][l]) >= p.hz:
+                continue
+            assert -1 <= fa.value <= mz, (hdt, l, fa.value)
+            f = fa.value % mz
+            if ex.value == mz:
+                assert f in (0, 1, mz - 2, mz - 1), (hdt, l, ex.value, fa.value)
+            else:
+                assert min((ex.value - f) % mz, (f - ex.value) % mz) <= 1, (hdt, l, ex.value, fa.value)
