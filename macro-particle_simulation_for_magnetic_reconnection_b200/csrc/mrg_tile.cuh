@@ -739,15 +739,23 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
           __stcs(D.src_rw[0] + p, x); __stcs(D.src_rw[1] + p, y); __stcs(D.src_rw[2] + p, z);
           __stcs(D.src_rw[3] + p, vx); __stcs(D.src_rw[4] + p, vy); __stcs(D.src_rw[5] + p, vz);
         }
-        if (pp.drive_on) {
-          if ((fabs(z - pp.zcent) < pp.zw) && ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw))) {
-            atomicOr(slab_bits + (id >> 5), 1u << (id & 31));
-            slab_list[atomicAdd(slab_count, 1)] = d;
-          }
-        }
         if (key_out) {
           kcell = sort_cell_folded(g, fma(lookahead, vx, x), fma(lookahead, vy, y), fma(lookahead, vz, z));
           key_out[p] = kcell;
+        }
+      }
+      if (pp.drive_on) {                                      // slab of the E x B drive kick, F:1343-1345
+        const bool in_slab = valid && (fabs(z - pp.zcent) < pp.zw) &&
+                             ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw));
+        const unsigned m = __ballot_sync(FULL, in_slab);
+        if (m) {                                              // one counter bump per warp: inside the slab every lane qualifies
+          int base = 0;
+          if (lane == __ffs(m) - 1) base = atomicAdd(slab_count, __popc(m));
+          base = __shfl_sync(FULL, base, __ffs(m) - 1);
+          if (in_slab) {
+            atomicOr(slab_bits + (idv >> 5), 1u << (idv & 31));
+            slab_list[base + __popc(m & ((1u << lane) - 1u))] = d;
+          }
         }
       }
       if (key_out) {

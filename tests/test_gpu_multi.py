@@ -94,8 +94,8 @@ def _worker_slab(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         uid = mrg.broadcast_unique_id(rank)
-        p = U.make_parm(12, 8, 32, Ez00=0.0)       # Ez00 = 0: the kick draws its random numbers but changes nothing,
-        ppc = 10                                   # so the particles do not depend on which rank owns them (Q4)
+        p = U.make_parm(12, 8, 48, Ez00=0.0)       # Ez00 = 0: the kick draws its random numbers but changes nothing,
+        ppc = 8                                    # so the particles do not depend on which rank owns them (Q4)
         sp, ranfb = U.load_species(p, ppc)
         npr = len(sp[1][0])
         ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, rank=rank, nranks=world, device=rank)
