@@ -322,8 +322,8 @@ k_correct_quad(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
 // transposing butterfly, shared-memory moment tile, one red.global.add.f64 per touched value).
 // ---------------------------------------------------------------------------
 constexpr int QPRED_SMEM_BYTES =
-    (QT_TAB_D + 6 * TILE_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + 256 + QP_NST * 6 * STAGE_D)) * 8 + (PR_WARPS * QP_NST + 1) * 8;
-static_assert(PR_WARPS * (32 * PR_W_STRIDE + 256) >= 6 * QT_ROW_D, "staged field rows alias the park area");
+    (QT_TAB_D + 6 * TILE_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + PR_Q_D + QP_NST * 6 * STAGE_D)) * 8 + (PR_WARPS * QP_NST + 1) * 8;
+static_assert(PR_WARPS * (32 * PR_W_STRIDE + PR_Q_D) >= 6 * QT_ROW_D, "staged field rows alias the park area");
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_QPRED_MINB)
 k_predict_quad(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
                const int* __restrict__ cell_end, double* __restrict__ wk_out, int group_min) {
@@ -332,7 +332,7 @@ k_predict_quad(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
   double* sM = sT + QT_TAB_D;                                  // [6][TILE_ACC_D] moment accumulators
   double* smW = sM + 6 * TILE_ACC_D;                           // [warps][32*PR_W_STRIDE]; during set-up: staged field rows
   double* smQ = smW + PR_WARPS * 32 * PR_W_STRIDE;             // [warps][256]
-  double* sRing = smQ + PR_WARPS * 256;                        // [warps][QP_NST*6*STAGE_D]
+  double* sRing = smQ + PR_WARPS * PR_Q_D;                        // [warps][QP_NST*6*STAGE_D]
   unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sRing + PR_WARPS * QP_NST * 6 * STAGE_D);
   unsigned long long& bar = sBar[PR_WARPS * QP_NST];
   double* sF = smW;
@@ -349,7 +349,7 @@ k_predict_quad(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
   quad_build_table(sF, sT, t.ncell);
   __syncthreads();                                             // sF is dead from here on: the park area takes over
   double* W = smW + w * (32 * PR_W_STRIDE);
-  double* Q = smQ + w * 256;
+  double* Q = smQ + w * PR_Q_D;
   const Target<true> tg(g, M4, sM, t.n0_first, t.ncell, lane);
   double acc[18];
 #pragma unroll
@@ -362,11 +362,11 @@ k_predict_quad(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
     P6 c;
     st.next(P, it, lane, c);
     const bool valid = st.a + 32 * it + lane < st.b;
+    int key = -1;
     {
       bool generic;
       const Kick k = quad_gather_rotate(g, pp, t, sT, F6, lane, valid, c, generic);
       double qvy[8], wxz[9];
-      int key = -1;
       if (valid) {
         wx += k.wx; wh += k.wh;
         Predicted o;
@@ -387,7 +387,8 @@ k_predict_quad(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6
       park_factors(W, Q, lane, qvy, wxz, key);
     }
     __syncwarp();
-    deposit_parked<true>(W, Q, lane, acc, cur, group_min, tg);
+    deposit_parked<true>(reinterpret_cast<const double2*>(W + (lane >> 2) * PR_W_STRIDE),
+                         reinterpret_cast<const double2*>(Q) + (lane & 3) * PR_Q_ROW + (lane >> 2), key, lane, acc, cur, group_min, tg);
     __syncwarp();
   }
   if (cur >= 0) flush_quad<true>(acc, cur, tg);

@@ -100,6 +100,11 @@ struct Target {
 
 constexpr int PR_WARPS = 4;        // warps per block
 constexpr int PR_W_STRIDE = 10;    // doubles per particle in the W slab: wxz[9] + key
+// Q slab: four rows (one per lane role q) of 32 double2.  Rows are 34 double2 apart: in the phase-B read the 8 lanes
+// of a quarter-warp are 4 roles x 2 particles, and a 32-double2 (512-byte) row stride would put the four roles on
+// the same banks (a 4-way conflict, 16 wavefronts per LDS.128 -- measured); 34 spreads them over all 32 banks.
+constexpr int PR_Q_ROW = 34;       // double2 per row
+constexpr int PR_Q_D = 4 * PR_Q_ROW * 2;   // doubles per warp
 
 // Sum the quad-distributed accumulators over the warp with a transposing
 // butterfly (18 -> 9 -> 4+1 -> 2+1 values per lane) and add the 72 totals of
@@ -128,7 +133,7 @@ __device__ __forceinline__ void park_factors(double* W, double* Q, int lane, con
   Wp[4] = make_double2(wxz[8], __longlong_as_double((long long)key));
   double2* Qp = reinterpret_cast<double2*>(Q);
 #pragma unroll
-  for (int qq = 0; qq < 4; qq++) Qp[qq * 32 + lane] = make_double2(qvy[2 * qq], qvy[2 * qq + 1]);
+  for (int qq = 0; qq < 4; qq++) Qp[qq * PR_Q_ROW + lane] = make_double2(qvy[2 * qq], qvy[2 * qq + 1]);
 }
 
 // phase B: four sub-iterations of 8 particles; a QUAD of lanes serves one
@@ -138,19 +143,23 @@ __device__ __forceinline__ void park_factors(double* W, double* Q, int lane, con
 // key; a group that continues the current cell, is large, or reaches the last
 // lane is summed in registers across (sub-)iterations, other groups (strays)
 // go straight to the target.
+//
+// own_key is the key of the lane's OWN particle (still in a register from
+// phase A): one ballot against the current cell tells which sub-iterations
+// may take the fast path, so that path reads no key and votes nothing.  Wq/Qq
+// are the lane's read pointers into the parked factors (particle pl = lane/4
+// of sub-iteration 0); they advance by a constant per sub-iteration.
 template <bool TILED>
-__device__ __forceinline__ void deposit_parked(const double* W, const double* Q, int lane, double* acc, int& cur,
+__device__ __forceinline__ void deposit_parked(const double2* Wq, const double2* Qq, int own_key, int lane, double* acc, int& cur,
                                                int group_min, const Target<TILED>& tg) {
-  const int q = lane & 3, pl = lane >> 2;
+  const int q = lane & 3;
+  unsigned bad = __ballot_sync(FULL, own_key >= 0 && own_key != cur);   // bit p: particle p does not continue the current cell
 #pragma unroll 1
-  for (int sub = 0; sub < 4; sub++) {
-    const int p = sub * 8 + pl;
-    const double2* Wp = reinterpret_cast<const double2*>(W + p * PR_W_STRIDE);
-    const double2 w01 = Wp[0], w23 = Wp[1], w45 = Wp[2], w67 = Wp[3], w8k = Wp[4];
-    const double2 qv = reinterpret_cast<const double2*>(Q)[q * 32 + p];
-    const int key = (int)__double_as_longlong(w8k.y);
+  for (int sub = 0; sub < 4; sub++, Wq += 8 * PR_W_STRIDE / 2, Qq += 8, bad >>= 8) {
+    const double2 w01 = Wq[0], w23 = Wq[1], w45 = Wq[2], w67 = Wq[3], w8k = Wq[4];
+    const double2 qv = Qq[0];
     const double wxz[9] = {w01.x, w01.y, w23.x, w23.y, w45.x, w45.y, w67.x, w67.y, w8k.x};
-    if (__all_sync(FULL, (key == cur) || (key < 0))) {
+    if ((bad & 0xffu) == 0u) {
 #pragma unroll
       for (int r = 0; r < 9; r++) {
         acc[r] = fma(qv.x, wxz[r], acc[r]);
@@ -158,6 +167,7 @@ __device__ __forceinline__ void deposit_parked(const double* W, const double* Q,
       }
       continue;
     }
+    const int key = (int)__double_as_longlong(w8k.y);
     const bool valid = key >= 0;
     unsigned remaining = __ballot_sync(FULL, valid);
     while (remaining) {
@@ -189,6 +199,8 @@ __device__ __forceinline__ void deposit_parked(const double* W, const double* Q,
       }
       remaining &= ~grp;
     }
+    // the current cell may have changed: the remaining sub-iterations are judged against the new one
+    bad = __ballot_sync(FULL, own_key >= 0 && own_key != cur) >> (8 * sub);
   }
 }
 
@@ -201,13 +213,15 @@ __global__ void __launch_bounds__(PR_WARPS * 32)
 k_predict_run(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6, double* __restrict__ M4,
               double* __restrict__ wk_partial, int group_min) {
   __shared__ __align__(16) double smW[PR_WARPS][32 * PR_W_STRIDE];
-  __shared__ __align__(16) double smQ[PR_WARPS][4 * 32 * 2];
+  __shared__ __align__(16) double smQ[PR_WARPS][PR_Q_D];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   double* W = smW[w];
   double* Q = smQ[w];
   const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const long long base = warp * (32LL * ITERS);
   const Target<false> tg(g, M4, nullptr, 0, 0, lane);
+  const double2* Wq = reinterpret_cast<const double2*>(W + (lane >> 2) * PR_W_STRIDE);
+  const double2* Qq = reinterpret_cast<const double2*>(Q) + (lane & 3) * PR_Q_ROW + (lane >> 2);
   double wx = 0.0, wh = 0.0;
   double acc[18];
 #pragma unroll
@@ -217,9 +231,9 @@ k_predict_run(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6,
   for (int it = 0; it < ITERS; it++) {
     const long long t = base + 32LL * it + lane;
     if (base + 32LL * it >= P.n) break;                     // warp-uniform
+    int key = -1;
     {
       double qvy[8], wxz[9];
-      int key = -1;
       if (t < P.n) {
         const Predicted o = predict_one(g, pp, P, t, F6, wx, wh);
         key = scatter_factors(g, pp.qmult, o, qvy, wxz);
@@ -232,7 +246,7 @@ k_predict_run(GP g, PushParams pp, ParticleSoA P, const double* __restrict__ F6,
       park_factors(W, Q, lane, qvy, wxz, key);
     }
     __syncwarp();
-    deposit_parked<false>(W, Q, lane, acc, cur, group_min, tg);
+    deposit_parked<false>(Wq, Qq, key, lane, acc, cur, group_min, tg);
     __syncwarp();
   }
   if (cur >= 0) flush_quad<false>(acc, cur, tg);
@@ -532,7 +546,7 @@ __device__ __forceinline__ void warp_wk_atomic(double wx, double wh, double* __r
 constexpr int PNS = MRG_PRED_NSTAGE, CNS = MRG_CORR_NSTAGE;
 constexpr int PRED_ACC_D = MRG_PRED_SMEM_TILE ? 6 * TILE_ACC_D : 0;      // the accumulator tile exists only when it is used
 constexpr int PRED_RING_BYTES = PR_WARPS * PNS * TSTAGE_P;               // first in the carve-up: tensor TMA wants 128-byte aligned boxes
-constexpr int PRED_SMEM_BYTES = PRED_RING_BYTES + (6 * TILE_ROW_D + PRED_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + 256)) * 8 +
+constexpr int PRED_SMEM_BYTES = PRED_RING_BYTES + (6 * TILE_ROW_D + PRED_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + PR_Q_D)) * 8 +
                                 (PR_WARPS * PNS + 1) * 8;
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_PRED_MINB)
 k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, const double* __restrict__ F6, double* __restrict__ M4,
@@ -544,8 +558,8 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
   double* sF = reinterpret_cast<double*>(smem_pred + PRED_RING_BYTES);   // [6][TILE_ROW_D]  staged fields
   double* sM = sF + 6 * TILE_ROW_D;                            // [6][TILE_ACC_D]      moment accumulators (optional)
   double* smW = sM + PRED_ACC_D;                               // [warps][32*PR_W_STRIDE]
-  double* smQ = smW + PR_WARPS * 32 * PR_W_STRIDE;             // [warps][256]
-  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smQ + PR_WARPS * 256);   // [warps][PNS] + 1
+  double* smQ = smW + PR_WARPS * 32 * PR_W_STRIDE;             // [warps][PR_Q_D]
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smQ + PR_WARPS * PR_Q_D);   // [warps][PNS] + 1
   unsigned long long& bar = sBar[PR_WARPS * PNS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const Tile t = tile_of(g, cell_end, blockIdx.x);
@@ -563,7 +577,9 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     double* W = smW + w * (32 * PR_W_STRIDE);
-    double* Q = smQ + w * 256;
+    double* Q = smQ + w * PR_Q_D;
+    const double2* Wq = reinterpret_cast<const double2*>(W + (lane >> 2) * PR_W_STRIDE);
+    const double2* Qq = reinterpret_cast<const double2*>(Q) + (lane & 3) * PR_Q_ROW + (lane >> 2);
     // MRG_PRED_SMEM_TILE = 0: cell-run totals go straight to global memory with red.global.add.f64 (fire and
     // forget; shared-memory fp64 atomics are compare-and-swap loops on sm_100a)
     const Target<(MRG_PRED_SMEM_TILE != 0)> tg(g, M4, sM, t.n0_first, t.ncell, lane);
@@ -581,9 +597,9 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
       stream_read<PNS, TSTAGE_P>(st, it, lane, c);
       const int p = st.a + 32 * it + lane;
       const bool valid = p >= st.lo && p < st.b;
+      int key = -1;
       {
         double qvy[8], wxz[9];
-        int key = -1;
         if (!valid) c = safe;                                 // idle lanes push a harmless copy (results masked)
         const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
         Predicted o;
@@ -615,7 +631,7 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
         }
       }
       __syncwarp();
-      deposit_parked<(MRG_PRED_SMEM_TILE != 0)>(W, Q, lane, acc, cur, group_min, tg);
+      deposit_parked<(MRG_PRED_SMEM_TILE != 0)>(Wq, Qq, key, lane, acc, cur, group_min, tg);
       __syncwarp();
     }
     if (cur >= 0) flush_quad<(MRG_PRED_SMEM_TILE != 0)>(acc, cur, tg);
