@@ -482,10 +482,14 @@ template <int NS>
 __device__ __forceinline__ void stream_wait(const Stream& st, int it) {
   mbar_wait(st.bar + it % NS, (unsigned)((it / NS) & 1));
 }
-// lane's particle of iteration `it` (whose stage has been waited for)
+// lane's particle of iteration `it` (whose stage has been waited for).  A lane outside [lo, b) -- the first / last
+// iteration of a slice may be partial -- reads the nearest particle of the slice instead (a shared-memory broadcast):
+// it then runs the same arithmetic on finite data and takes the same gather path as its neighbour; its results are masked.
 template <int NS, int STAGE>
 __device__ __forceinline__ void stream_read(const Stream& st, int it, int lane, P6& o) {
-  const double* src = reinterpret_cast<const double*>(st.ring + (it % NS) * STAGE) + lane;
+  const int first = st.a + 32 * it;
+  const int le = min(max(first + lane, st.lo), st.b - 1) - first;
+  const double* src = reinterpret_cast<const double*>(st.ring + (it % NS) * STAGE) + le;
   o.x = src[0]; o.y = src[32]; o.z = src[64];
   o.vx = src[96]; o.vy = src[128]; o.vz = src[160];
 }
@@ -588,7 +592,6 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     for (int n = 0; n < 18; n++) acc[n] = 0.0;
     int cur = -1;
     const double ah = pp.aimpl * pp.hh, hh2 = 0.5 * pp.hh;
-    const P6 safe = {0.0, 0.5 * g.hy, 0.0, 0.0, 0.0, 0.0};
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
@@ -600,7 +603,6 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
       int key = -1;
       {
         double qvy[8], wxz[9];
-        if (!valid) c = safe;                                 // idle lanes push a harmless copy (results masked)
         const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
         Predicted o;
         o.vxj = fma(ah, k.dvx, c.vx);                         // F:1300-1302
@@ -689,7 +691,6 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     stage_fields(g, t, F6, sF, &bar);
     mbar_wait(&bar, 0);
     const double hh2 = 0.5 * pp.hh;
-    const P6 safe = {0.0, 0.5 * g.hy, 0.0, 0.0, 0.0, 0.0};
     int cb = 0, crk = 0;         // claim of the current iteration: base (in the run's head lane), rank in the run
     int rlo = 0x7fffffff, rhi = -0x7fffffff;   // range of next-pass gather planes seen by this lane, relative to t.k
     if (st.nit > 0) stream_wait<CNS>(st, 0);                  // warp-uniform; a warp of a thin tile may have no iteration
@@ -720,7 +721,6 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
           if (head) nb = atomicAdd(cursor + pk1, cnt);
         }
       }
-      if (!valid) c = safe;                                   // idle lanes push a harmless copy (nothing is stored)
       const Kick k = gather_rotate(g, pp, t, sF, F6, c.x, c.y, c.z, c.vx, c.vy, c.vz);
       double x = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x);      // F:1289-1291
       double y = fma(pp.dt, fma(hh2, k.dvy, c.vy), c.y);
