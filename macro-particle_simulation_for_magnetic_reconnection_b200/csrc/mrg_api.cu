@@ -182,6 +182,7 @@ struct mrg_ctx {
   int* sort_key = nullptr; long long sort_key_cap = 0;
   int* hist = nullptr; int* cursor = nullptr; long long ncell = 0;
   int* scan_tiles = nullptr; long long scan_tiles_cap = 0;
+  unsigned* lcg_tab = nullptr;   // lambda^(j * 2048^t), t = 0..2, j < 2048 (lcg_pow_tab)
   unsigned* slab_bits = nullptr; int* slab_words = nullptr; long long slab_words_cap = 0;
   int* slab_list = nullptr; long long slab_list_cap = 0;
   int* slab_count = nullptr;
@@ -633,6 +634,17 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   }
   CK(cudaMalloc((void**)&c->F6, gb * 6));
   CK(cudaMalloc((void**)&c->wk2, 2 * sizeof(double)));
+  {
+    std::vector<unsigned> tab(3 * 2048);
+    unsigned step = 48828125u;                     // lambda^(2048^t)
+    for (int t = 0; t < 3; t++) {
+      unsigned v = 1u;
+      for (int j = 0; j < 2048; j++) { tab[t * 2048 + j] = v; v *= step; }
+      step = v;                                    // = step^2048
+    }
+    CK(cudaMalloc((void**)&c->lcg_tab, tab.size() * sizeof(unsigned)));
+    CK(cudaMemcpy(c->lcg_tab, tab.data(), tab.size() * sizeof(unsigned), cudaMemcpyHostToDevice));
+  }
   CK(cudaMalloc((void**)&c->slab_count, sizeof(int)));
   CK(cudaMalloc((void**)&c->hist, (size_t)(c->ncell + 1) * sizeof(int)));
   CK(cudaMalloc((void**)&c->cursor, (size_t)(c->ncell + 1) * sizeof(int)));
@@ -659,6 +671,7 @@ int mrg_destroy(mrg_ctx* c) {
     for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
   }
   cudaFree(c->wk_partial); cudaFree(c->wk2); cudaFree(c->sort_key); cudaFree(c->hist); cudaFree(c->cursor);
+  cudaFree(c->lcg_tab);
   cudaFree(c->scan_tiles); cudaFree(c->slab_bits); cudaFree(c->slab_words); cudaFree(c->slab_list); cudaFree(c->slab_count);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->wk_pinned) cudaFreeHost(c->wk_pinned);
@@ -1123,7 +1136,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         if (rc) return rc;
         k_kick<<<grid_for(slab_n, 256), 256, 0, c->stream>>>(g, soa(s), c->F6, c->slab_bits, c->slab_words, c->slab_list,
                                                               c->slab_count, (unsigned)*ranfb, p->Ez00, p->ycent1,
-                                                              p->ycent2, 0.05 * g.ymax); CKL(c);
+                                                              p->ycent2, 0.05 * g.ymax, c->lcg_tab); CKL(c);
         *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)slab_n);
       }
     }

@@ -573,17 +573,24 @@ __global__ void k_popc(const unsigned* __restrict__ bits, long long nwords, int*
   if (t < nwords) out[t] = __popc(bits[t]);
 }
 
+// lambda^n mod 2^32 for n < 2^33 from three 2048-entry tables of lambda^(j * 2048^t) (built by the host): the kick
+// needs one skip-ahead per slab particle, and the square-and-multiply loop of lcg_skip was most of k_kick.
+__device__ __forceinline__ unsigned lcg_pow_tab(const unsigned* __restrict__ tab, unsigned long long n) {
+  return __ldg(tab + (unsigned)(n & 2047ull)) * __ldg(tab + 2048 + (unsigned)((n >> 11) & 2047ull)) *
+         __ldg(tab + 4096 + (unsigned)((n >> 22) & 2047ull));
+}
+
 __global__ void k_kick(GP g, ParticleSoA P, const double* __restrict__ F6, const unsigned* __restrict__ bits,
                        const int* __restrict__ word_off, const int* __restrict__ slab_list,
                        const int* __restrict__ slab_count, unsigned state0, double Ez00, double ycent1,
-                       double ycent2, double yw2) {
+                       double ycent2, double yw2, const unsigned* __restrict__ lcg_tab) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= *slab_count) return;
   const int slot = slab_list[e];
   const int id = P.id ? P.id[slot] : slot;
   const unsigned w = bits[id >> 5];
   const int rank = word_off[id >> 5] + __popc(w & ((1u << (id & 31)) - 1u));
-  const unsigned ir = lcg_skip(state0, (unsigned long long)rank + 1ull);
+  const unsigned ir = (lcg_pow_tab(lcg_tab, (unsigned long long)rank + 1ull) * state0) & 0x7fffffffu;   // = lcg_skip(state0, rank + 1)
   const double u = (double)ir * (1.0 / 2147483648.0);     // F:9302
   if (u > 0.999) {                                          // F:1353
     const double x = P.x[slot], y = P.y[slot], z = P.z[slot];
