@@ -188,6 +188,15 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                z slab prepares its slab instead of the whole replicated
  *                grid.  -1 (default) = on when nranks > 1, 0 = off, 1 = on.
  *                Needs |vz|*dt < hz (like partbc, which wraps once)
+ *   "compact"    rank sum of the moments for ranks that own z slabs: -1
+ *                (default) = when every rank's deposits stay within 6 planes
+ *                of its own block of mz/nranks planes (decided from the
+ *                recorded planes and agreed between the ranks in the
+ *                preceding ipc == 0 call), each rank adds its two neighbours'
+ *                boundary strips (ncclSend/Recv) and the complete blocks are
+ *                all-gathered in place -- half the bytes of the whole-grid
+ *                allreduce, same sums; 0 = always ncclAllReduce.  Every rank
+ *                must use the same setting
  *   "defer"      1 = mrg_fulmov(ipc >= 1) returns once its work is queued: the
  *                NCCL moment sum and the fold run on a second stream and
  *                overlap the next species' particle kernel.  *wkix, *wkih are
@@ -212,9 +221,10 @@ int mrg_last_kernel_ms(mrg_ctx* ctx, double* ms);
  * that kernel only); usable in deferred mode.                               */
 int mrg_pass_ms(mrg_ctx* ctx, int32_t ksp, int32_t ipc, double* ms);
 
-/* Field preparations since the last reset: [0] runs of section 0,
- * [1] of which restricted to a plane set, [2] planes finalized by those.    */
-int mrg_get_prep_stats(mrg_ctx* ctx, int64_t out[3], int32_t reset);
+/* Since the last reset: [0] runs of section 0 (field preparation), [1] of
+ * which restricted to a plane set, [2] planes finalized by those, [3] rank
+ * sums of the moments done slab-wise instead of by a whole-grid allreduce.  */
+int mrg_get_prep_stats(mrg_ctx* ctx, int64_t out[4], int32_t reset);
 
 /* Host-only helper behind option "planes" (no GPU needed; exported so the
  * dependency analysis can be tested on its own): occ[kp], kp = 0..mz, marks

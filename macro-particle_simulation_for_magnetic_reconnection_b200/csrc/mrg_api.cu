@@ -53,6 +53,12 @@ struct NcclApi {
   int (*GetUniqueId)(void*) = nullptr;
   int (*CommInitRank)(void**, int, Uid, int) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
@@ -80,6 +86,12 @@ int nccl_load() {
   g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
   g_nccl.CommInitRank = (int (*)(void**, int, Uid, int))dlsym(h, "ncclCommInitRank");
   g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclAllReduce");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+  g_nccl.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclBroadcast");
+  g_nccl.Send = (int (*)(const void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclSend");
+  g_nccl.Recv = (int (*)(void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclRecv");
+  g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
   g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
   g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
   if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
@@ -125,6 +137,9 @@ struct Species {
   unsigned* kocc = nullptr;
   std::vector<unsigned> kocc_host;
   bool hull_valid = false, kocc_pending = false;
+  // every rank found (and the ranks agreed, in the last corrector call) that this species deposits only within
+  // HALO_H planes of the rank's own z block: the next ipc>=1 call may exchange slabs instead of allreducing the grid
+  bool compact_ok = false;
   int kz0 = 0, nkz = 0;
   // deferred completion (option "defer"): the moment sum, fold and wkix/wkih of the last ipc>=1 call run on the
   // communication stream; done marks their end, wk_user receives wkix/wkih when the host next waits for them
@@ -170,7 +185,7 @@ struct mrg_ctx {
   bool prep_full = true;
   std::vector<char> prep_planes;
   int* plane_lists = nullptr;    // device copy of the three plane lists of a restricted preparation
-  long long prep_count = 0, prep_restricted_count = 0, prep_planes_sum = 0;
+  long long prep_count = 0, prep_restricted_count = 0, prep_planes_sum = 0, compact_count = 0;
   // species
   Species sp[MRG_MAX_SPECIES];
   double* alt[6] = {};     // shared spare particle buffer (sort / download)
@@ -197,6 +212,8 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_compact = -1;  // slab-wise moment exchange instead of the whole-grid allreduce: -1 = when possible, 0 = never
+  double* halo_rx[2] = {nullptr, nullptr};   // staging of the two neighbour halos of the slab-wise exchange
   int opt_slab_n = 0, opt_slab_i = 0;   // "slab_of"/"slab_index": mrg_loadpt loads slab i of n whatever nranks is (sizing aid)
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
@@ -296,6 +313,7 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   s.fresh = false;
   s.zocc_valid = false;
   s.hull_valid = false;
+  s.compact_ok = false;
   if (!s.cell_end) {
     CK(cudaMalloc((void**)&s.cell_end, (size_t)(c->ncell + 1) * sizeof(int)));
     CK(cudaMalloc((void**)&s.cell_end2, (size_t)(c->ncell + 1) * sizeof(int)));
@@ -454,6 +472,66 @@ void plane_sets(int mz, const std::vector<char>& occ, PlaneSets& ps) {
     if (ps.G[e]) ps.listG.push_back(e);
     else if ((e > 0 && ps.G[e - 1]) || (e + 1 < nz && ps.G[e + 1])) ps.listG.push_back(e | PLANE_GUARD);
   }
+}
+
+// ---- slab-wise moment exchange ---------------------------------------------------
+// With z-slab ownership a rank deposits only near its own block of L = mz/N planes, so the rank sum of the raw
+// moments (F:2379-2384, 2533) needs no whole-grid allreduce: every rank adds the two HALO-wide strips its ring
+// neighbours deposited into its block (ncclSend/ncclRecv), then the complete blocks are all-gathered in place and
+// the four z ghost planes broadcast by the ranks that own them -- about half the bytes of the allreduce.  Ghost
+// planes are ordinary planes of the raw arrays (deposits next to the periodic seam go to k = -1 or k = mz, the
+// fold maps them later), but a particle that crossed the seam deposits next to plane 0 although its rank owns the
+// last block, so the "upper" strip of rank N-1 is the bottom of the array and the "lower" strip of rank 0 its top.
+// Eligibility is decided from the recorded gather planes (a deposit lies within 2 planes of the gather plane for
+// |vz| dt < hz) and agreed between the ranks in the preceding corrector call.
+constexpr int HALO_H = 6;                 // planes beyond the own block a rank may deposit into
+constexpr int HALO_PLANES = HALO_H + 2;   // strip width: + the two ghost planes at the seam
+bool compact_possible(const mrg_ctx* c) {
+  const int N = c->nranks, mz = c->g.mz;
+  return N > 1 && c->opt_compact != 0 && tracking(c) && mz % N == 0 && mz / N >= 2 * HALO_PLANES && g_nccl.AllGather &&
+         g_nccl.Broadcast && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
+}
+bool compact_eligible(const mrg_ctx* c, const Species& s, double hdt) {
+  if (s.n == 0) return true;
+  if (!(s.zocc_valid && s.zocc_lookahead == hdt)) return false;
+  const int N = c->nranks, mz = c->g.mz, L = mz / N, lo = c->rank * L, hi = lo + L - 1;
+  std::vector<char> occ(mz + 1, 0);
+  add_occupancy(s, mz, occ);
+  for (int kp = 0; kp < mz; kp++) {
+    if (!occ[kp] || (kp >= lo && kp <= hi)) continue;
+    const int d = std::min(((lo - kp) % mz + mz) % mz, ((kp - hi) % mz + mz) % mz);
+    if (d > HALO_H - 2) return false;
+  }
+  if (occ[mz] && c->rank != 0 && c->rank != N - 1) return false;
+  return true;
+}
+// the exchange itself, on stream ms; M4 = raw moments [nz planes][nxy][4] + (wkix, wkih)
+int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
+  const GP& g = c->g;
+  const int N = c->nranks, r = c->rank, L = g.mz / N;
+  const size_t P = (size_t)g.nxy * 4;                       // doubles per plane
+  const size_t cnt = (size_t)HALO_PLANES * P;
+  const int up = (r + 1) % N, dn = (r + N - 1) % N;
+  for (int k = 0; k < 2; k++)
+    if (!c->halo_rx[k]) CK(cudaMalloc((void**)&c->halo_rx[k], cnt * sizeof(double)));
+  const size_t send_up = (r < N - 1) ? (size_t)(2 + (r + 1) * L) : 0;                            // first plane of each strip
+  const size_t send_dn = (r > 0) ? (size_t)(2 + r * L - HALO_PLANES) : (size_t)(g.mz + 4 - HALO_PLANES);
+  const size_t add_lo = (r > 0) ? (size_t)(2 + r * L) : 0;
+  const size_t add_hi = (r < N - 1) ? (size_t)(2 + (r + 1) * L - HALO_PLANES) : (size_t)(g.mz + 4 - HALO_PLANES);
+  int n = g_nccl.GroupStart();
+  if (!n) n = g_nccl.Send(M4 + send_up * P, cnt, kNcclFloat64, up, c->comm, ms);
+  if (!n) n = g_nccl.Send(M4 + send_dn * P, cnt, kNcclFloat64, dn, c->comm, ms);
+  if (!n) n = g_nccl.Recv(c->halo_rx[0], cnt, kNcclFloat64, dn, c->comm, ms);   // the lower neighbour's upward strip
+  if (!n) n = g_nccl.Recv(c->halo_rx[1], cnt, kNcclFloat64, up, c->comm, ms);   // the upper neighbour's downward strip
+  const int e = g_nccl.GroupEnd();
+  if (n || e) return fail(MRG_ERR_NCCL, "halo exchange: " + nccl_err(n ? n : e));
+  k_add_strips<<<grid_for((long long)cnt, 256), 256, 0, ms>>>(M4 + add_lo * P, c->halo_rx[0], M4 + add_hi * P, c->halo_rx[1], (long long)cnt); CKL(c);
+  n = g_nccl.AllGather(M4 + (size_t)(2 + r * L) * P, M4 + 2 * P, (size_t)L * P, kNcclFloat64, c->comm, ms);
+  if (!n) n = g_nccl.Broadcast(M4, M4, 2 * P, kNcclFloat64, 0, c->comm, ms);
+  if (!n) n = g_nccl.Broadcast(M4 + (size_t)(g.mz + 2) * P, M4 + (size_t)(g.mz + 2) * P, 2 * P, kNcclFloat64, N - 1, c->comm, ms);
+  if (!n) n = g_nccl.AllReduce(M4 + (size_t)g.ntot * 4, M4 + (size_t)g.ntot * 4, 2, kNcclFloat64, kNcclSum, c->comm, ms);
+  if (n) return fail(MRG_ERR_NCCL, "slab exchange: " + nccl_err(n));
+  return MRG_OK;
 }
 
 // F:1127-1148 on the device, cached on (fields version, aimpl, dc, ifil*).
@@ -633,7 +711,7 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
     CK(cudaMemsetAsync(c->A6[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T1[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T2[k], 0, gb, c->stream));
   }
   CK(cudaMalloc((void**)&c->F6, gb * 6));
-  CK(cudaMalloc((void**)&c->wk2, 2 * sizeof(double)));
+  CK(cudaMalloc((void**)&c->wk2, 3 * sizeof(double)));   // wkix, wkih + the ranks' vote on the slab-wise exchange
   {
     std::vector<unsigned> tab(3 * 2048);
     unsigned step = 48828125u;                     // lambda^(2048^t)
@@ -671,7 +749,7 @@ int mrg_destroy(mrg_ctx* c) {
     for (int k = 0; k < 4; k++) cudaFree(s.out4[k]);
   }
   cudaFree(c->wk_partial); cudaFree(c->wk2); cudaFree(c->sort_key); cudaFree(c->hist); cudaFree(c->cursor);
-  cudaFree(c->lcg_tab);
+  cudaFree(c->lcg_tab); cudaFree(c->halo_rx[0]); cudaFree(c->halo_rx[1]);
   cudaFree(c->scan_tiles); cudaFree(c->slab_bits); cudaFree(c->slab_words); cudaFree(c->slab_list); cudaFree(c->slab_count);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->wk_pinned) cudaFreeHost(c->wk_pinned);
@@ -985,8 +1063,14 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     }
     if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
-      int n = g_nccl.AllReduce(s.M4, s.M4, (size_t)g.ntot * 4 + 2, kNcclFloat64, kNcclSum, c->comm, ms);
-      if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
+      if (s.compact_ok && compact_possible(c) && (s.n == 0 || (s.zocc_valid && s.zocc_lookahead == p->hdt))) {
+        rc = compact_sum(c, s.M4, ms);
+        if (rc) return rc;
+        c->compact_count++;
+      } else {
+        int n = g_nccl.AllReduce(s.M4, s.M4, (size_t)g.ntot * 4 + 2, kNcclFloat64, kNcclSum, c->comm, ms);
+        if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
+      }
     }
     Ptr4 o; for (int k = 0; k < 4; k++) o.p[k] = s.out4[k];
     k_fold_unpack<<<grid_for(g.ntot, 256), 256, 0, ms>>>(g, s.M4, o, 1); CKL(c);   // F:2398, 2544
@@ -1030,7 +1114,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CK(cudaMemsetAsync(c->slab_bits, 0, (size_t)nwords * sizeof(unsigned), c->stream));
       CK(cudaMemsetAsync(c->slab_count, 0, sizeof(int), c->stream));
     }
-    CK(cudaMemsetAsync(c->wk2, 0, 2 * sizeof(double), c->stream));
+    CK(cudaMemsetAsync(c->wk2, 0, 3 * sizeof(double), c->stream));
     s.keys_valid = false;
     s.fresh = false;
     bool fused_scatter = false;
@@ -1120,12 +1204,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       s.prekeys_valid = false;
       if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c); }
     }
-    if (c->nranks > 1) {                                           // F:1312-1315
-      if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
-      int n = g_nccl.AllReduce(c->wk2, c->wk2, 2, kNcclFloat64, kNcclSum, c->comm, c->stream);
-      if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
-    }
-    CK(cudaMemcpyAsync(wk_host, c->wk2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    double wk3[3] = {0.0, 0.0, 0.0};
     if (pp.drive_on && s.n > 0) {
       CK(cudaMemcpyAsync(&slab_n, c->slab_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
@@ -1140,7 +1219,26 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)slab_n);
       }
     }
-    CK(cudaStreamSynchronize(c->stream));
+    if (c->nranks > 1) {                                           // F:1312-1315
+      if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
+      // third word: this rank's vote on exchanging slabs instead of allreducing the grid in the next ipc>=1 call of
+      // the species (0 = my deposits will stay near my block); the planes were recorded by the kernel above
+      const bool vote = compact_possible(c);
+      if (vote) {
+        CK(cudaStreamSynchronize(c->stream));                      // the recorded planes are on the host now
+        const double veto = compact_eligible(c, s, p->hdt) ? 0.0 : 1.0;
+        CK(cudaMemcpyAsync(c->wk2 + 2, &veto, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      }
+      int n = g_nccl.AllReduce(c->wk2, c->wk2, 3, kNcclFloat64, kNcclSum, c->comm, c->stream);
+      if (n != 0) return fail(MRG_ERR_NCCL, "ncclAllReduce: " + nccl_err(n));
+      CK(cudaMemcpyAsync(wk3, c->wk2, 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+      s.compact_ok = vote && wk3[2] == 0.0;
+    } else {
+      CK(cudaMemcpyAsync(wk3, c->wk2, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+    wk_host[0] = wk3[0]; wk_host[1] = wk3[1];
     if (fused_scatter) kocc_finish(c, s);   // planes of the order the particles are in now
   }
   c->pass_timed[ksp - 1][ipc != 0] = s.n > 0;
@@ -1319,7 +1417,11 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
   } else if (n == "planes") {
     if (value < -1 || value > 1) return fail(MRG_ERR_ARG, "planes must be -1 (when nranks > 1), 0 (never) or 1 (always)");
     c->opt_planes = (int)value;
-    for (auto& sp : c->sp) sp.zocc_valid = false;
+    for (auto& sp : c->sp) { sp.zocc_valid = false; sp.compact_ok = false; }
+  } else if (n == "compact") {
+    if (value < -1 || value > 0) return fail(MRG_ERR_ARG, "compact must be -1 (slab-wise moment exchange when the ranks agree it is possible) or 0 (always allreduce)");
+    c->opt_compact = (int)value;
+    for (auto& sp : c->sp) sp.compact_ok = false;
   } else if (n == "defer") {
     if (!value) { for (int k = 0; k < c->nspecies; k++) { int rc = complete_moments(c, k); if (rc) return rc; } }
     c->opt_defer = value != 0;
@@ -1397,10 +1499,10 @@ int mrg_plane_sets(int32_t mz, const uint8_t* occ, int32_t* listB, int32_t* list
   return MRG_OK;
 }
 
-int mrg_get_prep_stats(mrg_ctx* c, int64_t out[3], int32_t reset) {
+int mrg_get_prep_stats(mrg_ctx* c, int64_t out[4], int32_t reset) {
   if (!c || !out) return fail(MRG_ERR_ARG, "null argument");
-  out[0] = c->prep_count; out[1] = c->prep_restricted_count; out[2] = c->prep_planes_sum;
-  if (reset) { c->prep_count = 0; c->prep_restricted_count = 0; c->prep_planes_sum = 0; }
+  out[0] = c->prep_count; out[1] = c->prep_restricted_count; out[2] = c->prep_planes_sum; out[3] = c->compact_count;
+  if (reset) { c->prep_count = 0; c->prep_restricted_count = 0; c->prep_planes_sum = 0; c->compact_count = 0; }
   return MRG_OK;
 }
 

@@ -169,6 +169,15 @@ __global__ void k_finalize(GP g, CPtr6 A, CPtr6 T, double* __restrict__ F6, doub
   o[2] = make_double2(out[4], out[5]);
 }
 
+// slab-wise moment exchange: add the two neighbour strips into the rank's own block
+__global__ void k_add_strips(double* __restrict__ lo, const double* __restrict__ rx_lo, double* __restrict__ hi,
+                             const double* __restrict__ rx_hi, long long n) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  lo[t] += rx_lo[t];
+  hi[t] += rx_hi[t];
+}
+
 // packed F6 -> six reference-layout arrays (mrg_get_prepared_fields)
 __global__ void k_unpack6(GP g, const double* __restrict__ F6, Ptr6 out) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;

@@ -173,9 +173,9 @@ class MrgContext:
         return ms.value
 
     def prep_stats(self, reset=False):
-        out = (C.c_int64 * 3)()
+        out = (C.c_int64 * 4)()
         check(self.lib.mrg_get_prep_stats(self.h, out, 1 if reset else 0))
-        return {"preps": out[0], "restricted": out[1], "planes": out[2]}
+        return {"preps": out[0], "restricted": out[1], "planes": out[2], "compact_sums": out[3]}
 
     def moments(self, ksp, folded=True, out=None):
         arrs = out if out is not None else [np.zeros(self.n_grid) for _ in range(4)]
