@@ -188,6 +188,17 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                z slab prepares its slab instead of the whole replicated
  *                grid.  -1 (default) = on when nranks > 1, 0 = off, 1 = on.
  *                Needs |vz|*dt < hz (like partbc, which wraps once)
+ *   "kick"       random numbers of the E x B drive kick (F:1342-1364).  0 = the
+ *                reference's: every rank draws ranfp once per owned particle
+ *                inside the slab, in l order (bit-exact with the reference for
+ *                its round-robin ownership, any nranks).  1 = the particle with
+ *                original local index id takes draw id+1 of the stream starting
+ *                at *ranfb, and *ranfb advances by the number of owned
+ *                particles per call: same LCG, same kick probability, no serial
+ *                order -- the kick then happens inside the tiled corrector
+ *                instead of through an index bitmap, a scan and a second
+ *                kernel.  -1 (default) = 1 when "shard" = 1 (z-slab ownership
+ *                has no reference stream to reproduce), else 0
  *   "compact"    rank sum of the moments for ranks that own z slabs: -1
  *                (default) = when every rank's deposits stay within 6 planes
  *                of its own block of mz/nranks planes (decided from the

@@ -212,6 +212,7 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_kick = -1;     // drive-kick draws: -1 = by particle index when "shard" = 1 (no reference stream exists), else the reference's serial order; 0 / 1 force
   int opt_compact = -1;  // slab-wise moment exchange instead of the whole-grid allreduce: -1 = when possible, 0 = never
   double* halo_rx[2] = {nullptr, nullptr};   // staging of the two neighbour halos of the slab-wise exchange
   int opt_slab_n = 0, opt_slab_i = 0;   // "slab_of"/"slab_index": mrg_loadpt loads slab i of n whatever nranks is (sizing aid)
@@ -992,6 +993,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
   pp.zcent = p->zcent; pp.ycent1 = p->ycent1; pp.ycent2 = p->ycent2;
   pp.zw = 0.15 * g.zmax; pp.yw = 0.025 * g.ymax;                   // F:1343-1345
   pp.drive_on = (ipc == 0 && p->drive_on) ? 1 : 0;
+  pp.kick_inline = 0; pp.kick_state = 0u; pp.Ez00 = p->Ez00; pp.yw2 = 0.05 * g.ymax;
   const ParticleSoA P = soa(s);
   double wk_host[2] = {0.0, 0.0};
 
@@ -1098,8 +1100,13 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     CK(cudaStreamSynchronize(c->stream));
   } else {
     int slab_n = 0;
-    if (pp.drive_on) {
-      if (!ranfb) return fail(MRG_ERR_ARG, "ranfb state pointer is required when the drive kick is on");
+    if (pp.drive_on && !ranfb) return fail(MRG_ERR_ARG, "ranfb state pointer is required when the drive kick is on");
+    {
+      const bool want = c->opt_kick == 1 || (c->opt_kick < 0 && c->opt_shard == 1 && (c->nranks > 1 || c->opt_slab_n > 1));
+      const bool tile1 = c->opt_tile == 1 && s.index_valid && s.layout == 0;   // the kernel that can kick on its own
+      if (pp.drive_on && want && tile1 && s.n > 0) { pp.kick_inline = 1; pp.kick_state = (unsigned)*ranfb; }
+    }
+    if (pp.drive_on && !pp.kick_inline) {
       const long long nwords = (s.n + 31) / 32 + 1;
       if (c->slab_words_cap < nwords) {
         if (c->slab_bits) CK(cudaFree(c->slab_bits));
@@ -1180,7 +1187,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         for (int k = 0; k < 6; k++) D.src_rw[k] = s.d[k];
         k_correct_tile<<<blocks, B, 0, c->stream>>>(gl, pp, tmP, tmId, tmKey, s.id ? 1 : 0, c->F6, s.cell_end, c->wk_partial,
                                                     c->slab_bits, c->slab_list, c->slab_count, key_out, s.hist, p->hdt,
-                                                    scatter ? 1 : 0, s.cell_end2, D, zocc);
+                                                    scatter ? 1 : 0, s.cell_end2, D, zocc, c->lcg_tab);
         s.hist_valid = !scatter;
         fused_scatter = scatter;
       } else {
@@ -1205,7 +1212,9 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c); }
     }
     double wk3[3] = {0.0, 0.0, 0.0};
-    if (pp.drive_on && s.n > 0) {
+    if (pp.kick_inline) {
+      *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)s.n);   // every particle owns one draw of the call
+    } else if (pp.drive_on && s.n > 0) {
       CK(cudaMemcpyAsync(&slab_n, c->slab_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       CK(cudaStreamSynchronize(c->stream));
       if (slab_n > 0) {
@@ -1418,6 +1427,9 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value < -1 || value > 1) return fail(MRG_ERR_ARG, "planes must be -1 (when nranks > 1), 0 (never) or 1 (always)");
     c->opt_planes = (int)value;
     for (auto& sp : c->sp) { sp.zocc_valid = false; sp.compact_ok = false; }
+  } else if (n == "kick") {
+    if (value < -1 || value > 1) return fail(MRG_ERR_ARG, "kick must be -1, 0 (the reference's serial draw order) or 1 (draw by particle index)");
+    c->opt_kick = (int)value;
   } else if (n == "compact") {
     if (value < -1 || value > 0) return fail(MRG_ERR_ARG, "compact must be -1 (slab-wise moment exchange when the ranks agree it is possible) or 0 (always allreduce)");
     c->opt_compact = (int)value;

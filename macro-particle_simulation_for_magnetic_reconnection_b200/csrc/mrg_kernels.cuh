@@ -232,6 +232,14 @@ struct PushParams {
   // drive-kick slab (F:1343-1345): |z-zcent| < zw and (|y-ycent2| < yw or |y-ycent1| < yw)
   double zcent, ycent1, ycent2, zw, yw;
   int drive_on;
+  // drive kick inside the tiled corrector (kick_inline): the particle whose original local index is id draws
+  // ranfp number id + 1 of the stream that starts at kick_state, instead of the draw its position among the rank's
+  // slab particles in l order selects (F:1342-1364 with a serial stream).  Only for ownerships the reference does
+  // not have (z slabs): there is no reference stream to reproduce, and the serial order costs a bitmap over the
+  // particle indices, a scan and a second kernel -- mostly on the ranks that own the slab.
+  int kick_inline;
+  unsigned kick_state;
+  double Ez00, yw2;
 };
 
 struct ParticleSoA {

@@ -673,7 +673,8 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
                const __grid_constant__ CUtensorMap tmKey, int have_id, const double* __restrict__ F6,
                const int* __restrict__ cell_end, double* __restrict__ wk_partial, unsigned* __restrict__ slab_bits,
                int* __restrict__ slab_list, int* __restrict__ slab_count, int* __restrict__ key_out, int* __restrict__ hist,
-               double lookahead, int scatter, int* __restrict__ cursor, SortArrays D, unsigned* __restrict__ zocc) {
+               double lookahead, int scatter, int* __restrict__ cursor, SortArrays D, unsigned* __restrict__ zocc,
+               const unsigned* __restrict__ lcg_tab) {
   __shared__ __align__(128) unsigned char sRing[PR_WARPS][CNS * TSTAGE_PIK];
   __shared__ __align__(128) double sF[6 * TILE_ROW_D];
   __shared__ __align__(8) unsigned long long sBar[PR_WARPS][CNS];
@@ -739,6 +740,18 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
         kq = kq > hmz ? kq - g.mz : (kq < -hmz ? kq + g.mz : kq);
         if (valid) { rlo = min(rlo, kq); rhi = max(rhi, kq); }
       }
+      if (pp.drive_on && pp.kick_inline) {                    // E x B drive kick with a per-particle draw, F:1343-1364
+        if (valid && (fabs(z - pp.zcent) < pp.zw) && ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw))) {
+          const unsigned ir = (lcg_pow_tab(lcg_tab, (unsigned long long)(unsigned)idv + 1ull) * pp.kick_state) & 0x7fffffffu;
+          if ((double)ir * (1.0 / 2147483648.0) > 0.999) {    // F:1353
+            int ip, jp, kp;
+            cell_of(g, x, y, z, ip, jp, kp);                  // F:1347-1349
+            const double vy0 = __ddiv_rn(pp.Ez00, F6[(size_t)node_of(g, ip, jp, kp) * 6 + 3]);   // F:1354
+            if (fabs(y - pp.ycent2) < pp.yw2) vy = __dsub_rn(vy, vy0);
+            else if (fabs(y - pp.ycent1) < pp.yw2) vy = __dadd_rn(vy, vy0);
+          }
+        }
+      }
       int d = p;                                              // slot the updated particle is written to
       if (scatter) {
         d = __shfl_sync(FULL, cb, lane - crk) + crk;          // claimed one iteration ago
@@ -760,7 +773,7 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
           key_out[p] = kcell;
         }
       }
-      if (pp.drive_on) {                                      // slab of the E x B drive kick, F:1343-1345
+      if (pp.drive_on && !pp.kick_inline) {                   // slab of the E x B drive kick, F:1343-1345 (kicked by k_kick)
         const bool in_slab = valid && (fabs(z - pp.zcent) < pp.zw) &&
                              ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw));
         const unsigned m = __ballot_sync(FULL, in_slab);

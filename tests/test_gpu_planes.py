@@ -205,3 +205,44 @@ def test_bind_fields_device_is_zero_copy_and_identical(mrg):
         np.testing.assert_array_equal(got[c], a6c[c])
     assert ctx.counters()["h2d_bytes"] == 0
     ctx.close()
+
+
+def test_inline_drive_kick_by_particle_index(mrg):
+    """Option "kick" = 1 (what z-slab ownership uses): particle id draws ranfp number id+1 of the stream at *ranfb and
+    is kicked inside the tiled corrector.  Checked against the oracle's corrector without kick (Ez00 = 0) plus the
+    kick of F:1342-1364 applied here with that draw rule; *ranfb advances by the number of particles."""
+    p = U.make_parm(16, 12, 16, Ez00=0.25)                 # a large Ez00 makes a missed or spurious kick obvious
+    p0 = U.make_parm(16, 12, 16, Ez00=0.0)
+    sp, ranfb = U.load_species(p, 40)
+    f12 = U.smooth_fields(p, seed=21)
+    a6 = O.field_prep(p, f12)
+    bxa = a6[3]
+    ksp = 2
+    q, w = U.QSPEC[ksp], U.WSPEC[ksp]
+    ref = [a.copy() for a in sp[ksp]]
+    O.fulmov(p0, a6, *ref, q, w, 0, nranks=1)
+    n = len(ref[0])
+    x, y, z, vy = ref[0], ref[1], ref[2], ref[4]
+    in_slab = (np.abs(z - p.zcent) < 0.15 * p.zmax) & ((np.abs(y - p.ycent2) < 0.025 * p.ymax) | (np.abs(y - p.ycent1) < 0.025 * p.ymax))
+    nk = 0
+    for l in np.nonzero(in_slab)[0]:
+        u = O.lcg_skip(ranfb, int(l) + 1) / 2147483648.0
+        if u > 0.999:
+            ip, jp, kp = int(p.hxi * x[l] + 0.500000001), int(p.hyi * y[l] + 0.000000001), int(p.hzi * z[l] + 0.500000001)
+            vy0 = p.Ez00 / bxa[U.idx(p, ip, jp, kp)]
+            if abs(y[l] - p.ycent2) < 0.05 * p.ymax:
+                vy[l] -= vy0
+            elif abs(y[l] - p.ycent1) < 0.05 * p.ymax:
+                vy[l] += vy0
+            nk += 1
+    assert nk >= 2, nk
+    ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax)
+    ctx.set_option("kick", 1)
+    ctx.set_fields(f12)
+    ctx.upload(ksp, *sp[ksp])
+    ctx.sort(ksp, p.hdt)
+    _, _, st = ctx.fulmov(ksp, q, w, 0, params_of(mrg, p), ranfb)
+    got = ctx.download(ksp, n)
+    assert U.particle_err(got, ref, p.hx, U.vth(ksp)) < PTOL
+    assert st == O.lcg_skip(ranfb, n)
+    ctx.close()

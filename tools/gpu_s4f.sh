@@ -4,12 +4,12 @@ mkdir -p gpurun_out
 cd "$(dirname "$0")/.."
 T0=$(date +%s)
 nvidia-smi -L > gpurun_out/s4f_box.txt
-for N in 8 4 2; do
+for N in ${SWEEP:-8 4 2}; do
   timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2954$N bench.py --gpus $N --steps 6 --warmup 3 --no-cpu --no-e2e > gpurun_out/s4f_bench_$N.log 2>&1
   echo "N=$N t=$(( $(date +%s) - T0 ))"
 done
 timeout 120 python bench.py --gpus 1 --steps 6 --warmup 3 --no-cpu --no-e2e > gpurun_out/s4f_bench_1.log 2>&1
-timeout 200 python -m pytest tests/test_gpu_multi.py -m gpu -x -q --timeout 150 > gpurun_out/s4f_pytest_multi.log 2>&1; tail -2 gpurun_out/s4f_pytest_multi.log
+[ -n "$SKIPTEST" ] || timeout 200 python -m pytest tests/test_gpu_multi.py -m gpu -x -q --timeout 150 > gpurun_out/s4f_pytest_multi.log 2>&1; tail -2 gpurun_out/s4f_pytest_multi.log
 python - <<'PY'
 import json
 base=None
