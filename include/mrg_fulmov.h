@@ -246,6 +246,17 @@ int mrg_get_prep_stats(mrg_ctx* ctx, int64_t out[4], int32_t reset);
 int mrg_plane_sets(int32_t mz, const uint8_t* occ, int32_t* listB,
                    int32_t* listGI, int32_t* listG, int32_t n[3]);
 
+/* Host-only helper behind option "compact" (no GPU needed; exported so the
+ * exchange pattern can be tested on its own).  out[0] = 1 when a grid of mz
+ * planes can be exchanged slab-wise by nranks ranks; out[1..4] = first
+ * extended plane (k+2) of the strips rank sends to its upper / lower ring
+ * neighbour and of the regions where it adds what it receives from the lower
+ * / upper neighbour; out[5] = strip width in planes; out[6] = 1 when a rank
+ * whose gather cells lie on the planes occ[kp], kp = 0..mz (may be NULL), is
+ * eligible.                                                                 */
+int mrg_compact_layout(int32_t mz, int32_t nranks, int32_t rank,
+                       const uint8_t* occ, int32_t out[7]);
+
 /* Device-side stopwatch on the library's stream (where every kernel of this
  * context is launched): record marks slot 0..7, elapsed gives the CUDA-event
  * time between two recorded slots in milliseconds (synchronises on b).       */

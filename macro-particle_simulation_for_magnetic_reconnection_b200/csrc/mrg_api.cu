@@ -487,6 +487,26 @@ void plane_sets(int mz, const std::vector<char>& occ, PlaneSets& ps) {
 // |vz| dt < hz) and agreed between the ranks in the preceding corrector call.
 constexpr int HALO_H = 6;                 // planes beyond the own block a rank may deposit into
 constexpr int HALO_PLANES = HALO_H + 2;   // strip width: + the two ghost planes at the seam
+// first extended plane (k+2) of the four HALO_PLANES-wide strips of rank r: sent to the upper / lower ring neighbour,
+// and where the strips received from the lower / upper neighbour are added
+void compact_layout(int mz, int N, int r, int lay[4]) {
+  const int L = mz / N;
+  lay[0] = (r < N - 1) ? 2 + (r + 1) * L : 0;
+  lay[1] = (r > 0) ? 2 + r * L - HALO_PLANES : mz + 4 - HALO_PLANES;
+  lay[2] = (r > 0) ? 2 + r * L : 0;
+  lay[3] = (r < N - 1) ? 2 + (r + 1) * L - HALO_PLANES : mz + 4 - HALO_PLANES;
+}
+// may rank r of N, whose (widened) gather planes are occ[0..mz], take part in the slab-wise exchange?
+bool compact_planes_ok(int mz, int N, int r, const std::vector<char>& occ) {
+  const int L = mz / N, lo = r * L, hi = lo + L - 1;
+  for (int kp = 0; kp < mz; kp++) {
+    if (!occ[kp] || (kp >= lo && kp <= hi)) continue;
+    const int d = std::min(((lo - kp) % mz + mz) % mz, ((kp - hi) % mz + mz) % mz);
+    if (d > HALO_H - 2) return false;
+  }
+  if (occ[mz] && r != 0 && r != N - 1) return false;
+  return true;
+}
 bool compact_possible(const mrg_ctx* c) {
   const int N = c->nranks, mz = c->g.mz;
   return N > 1 && c->opt_compact != 0 && tracking(c) && mz % N == 0 && mz / N >= 2 * HALO_PLANES && g_nccl.AllGather &&
@@ -495,16 +515,10 @@ bool compact_possible(const mrg_ctx* c) {
 bool compact_eligible(const mrg_ctx* c, const Species& s, double hdt) {
   if (s.n == 0) return true;
   if (!(s.zocc_valid && s.zocc_lookahead == hdt)) return false;
-  const int N = c->nranks, mz = c->g.mz, L = mz / N, lo = c->rank * L, hi = lo + L - 1;
+  const int mz = c->g.mz;
   std::vector<char> occ(mz + 1, 0);
   add_occupancy(s, mz, occ);
-  for (int kp = 0; kp < mz; kp++) {
-    if (!occ[kp] || (kp >= lo && kp <= hi)) continue;
-    const int d = std::min(((lo - kp) % mz + mz) % mz, ((kp - hi) % mz + mz) % mz);
-    if (d > HALO_H - 2) return false;
-  }
-  if (occ[mz] && c->rank != 0 && c->rank != N - 1) return false;
-  return true;
+  return compact_planes_ok(mz, c->nranks, c->rank, occ);
 }
 // the exchange itself, on stream ms; M4 = raw moments [nz planes][nxy][4] + (wkix, wkih)
 int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
@@ -515,10 +529,9 @@ int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
   const int up = (r + 1) % N, dn = (r + N - 1) % N;
   for (int k = 0; k < 2; k++)
     if (!c->halo_rx[k]) CK(cudaMalloc((void**)&c->halo_rx[k], cnt * sizeof(double)));
-  const size_t send_up = (r < N - 1) ? (size_t)(2 + (r + 1) * L) : 0;                            // first plane of each strip
-  const size_t send_dn = (r > 0) ? (size_t)(2 + r * L - HALO_PLANES) : (size_t)(g.mz + 4 - HALO_PLANES);
-  const size_t add_lo = (r > 0) ? (size_t)(2 + r * L) : 0;
-  const size_t add_hi = (r < N - 1) ? (size_t)(2 + (r + 1) * L - HALO_PLANES) : (size_t)(g.mz + 4 - HALO_PLANES);
+  int lay[4];
+  compact_layout(g.mz, N, r, lay);
+  const size_t send_up = lay[0], send_dn = lay[1], add_lo = lay[2], add_hi = lay[3];   // first plane of each strip
   int n = g_nccl.GroupStart();
   if (!n) n = g_nccl.Send(M4 + send_up * P, cnt, kNcclFloat64, up, c->comm, ms);
   if (!n) n = g_nccl.Send(M4 + send_dn * P, cnt, kNcclFloat64, dn, c->comm, ms);
@@ -1508,6 +1521,17 @@ int mrg_plane_sets(int32_t mz, const uint8_t* occ, int32_t* listB, int32_t* list
   std::copy(ps.listGI.begin(), ps.listGI.end(), listGI);
   std::copy(ps.listG.begin(), ps.listG.end(), listG);
   n[0] = (int32_t)ps.listB.size(); n[1] = (int32_t)ps.listGI.size(); n[2] = (int32_t)ps.listG.size();
+  return MRG_OK;
+}
+
+int mrg_compact_layout(int32_t mz, int32_t nranks, int32_t rank, const uint8_t* occ, int32_t out[7]) {
+  if (mz < 4 || nranks < 2 || rank < 0 || rank >= nranks || !out) return fail(MRG_ERR_ARG, "bad argument");
+  out[0] = (mz % nranks == 0 && mz / nranks >= 2 * HALO_PLANES) ? 1 : 0;     // can this grid be exchanged slab-wise at all
+  int lay[4] = {0, 0, 0, 0};
+  if (out[0]) compact_layout(mz, nranks, rank, lay);
+  for (int k = 0; k < 4; k++) out[1 + k] = lay[k];
+  out[5] = HALO_PLANES;
+  out[6] = (out[0] && occ) ? (compact_planes_ok(mz, nranks, rank, std::vector<char>(occ, occ + mz + 1)) ? 1 : 0) : 0;
   return MRG_OK;
 }
 
