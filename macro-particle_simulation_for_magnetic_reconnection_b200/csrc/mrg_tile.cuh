@@ -5,19 +5,18 @@
 //   k_predict_tile  same deposition, but a CTA owns a pencil of TILE_CELLS
 //                   cells along x: the 6 stencil rows of the six prepared
 //                   fields are staged in shared memory with 1-D bulk TMA
-//                   (cp.async.bulk + mbarrier), moments are accumulated in a
-//                   shared-memory tile and flushed once per CTA with
-//                   red.global.add.f64.
-//   k_correct_tile  corrector with the same TMA-staged gather; optionally
-//                   emits next step's sort keys + cell histogram.
+//                   (cp.async.bulk + mbarrier), the particles stream through a
+//                   ring of 2-D tensor-TMA stages, cell-run totals leave with
+//                   red.global.add.f64; also emits the next order's sort keys.
+//   k_correct_tile  corrector with the same staging; scatters the updated
+//                   particles straight into the next cell order (fused sort),
+//                   records the z planes of the next gather, applies the drive
+//                   kick inline under slab ownership.
 //
-// Both tiled kernels stream a warp's contiguous slice of the tile's particles
-// with the NEXT 32 particles prefetched into registers while the current 32
-// are pushed (the passes are fp64-issue bound; the HBM latency must not be
-// exposed).  The tiled kernels need the cell index built by mrg_sort
-// (cell_end[]); a particle whose stencil is not inside its CTA's tile takes
-// the L1 / global atomic path, so results never depend on how well the order
-// fits.  F:n = /root/reference/@mrg37-080A.f03 line n.
+// The tiled kernels need the cell index built by mrg_sort (cell_end[]); a
+// particle whose stencil is not inside its CTA's tile takes the L1 / global
+// atomic path, so results never depend on how well the order fits.
+// F:n = /root/reference/@mrg37-080A.f03 line n.
 #pragma once
 #include <cuda.h>   // CUtensorMap (type only; the descriptors are encoded on the host in mrg_api.cu)
 #include "mrg_kernels.cuh"
@@ -527,14 +526,6 @@ __device__ __forceinline__ int run_rank(int key, bool valid, int lane, int& coun
   const int end = above ? (__ffs(above) - 1) : (32 - __clz(vmask));   // first lane of the next run / one past the last valid lane
   count = end - start;
   return lane - start;
-}
-
-// A streaming int load the compiler must issue where it is written (asm volatile is not sunk towards its
-// first use, which is what happens to a plain load under register pressure).
-__device__ __forceinline__ int ld_early(const int* p) {
-  int v;
-  asm volatile("ld.global.cs.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
 }
 
 // wkix/wkih of the warp -> two global accumulators (zeroed by the host before the launch)
