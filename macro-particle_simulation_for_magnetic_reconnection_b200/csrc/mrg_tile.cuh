@@ -408,6 +408,36 @@ constexpr int STAGE_BYTES = STAGE_D * 8;
 constexpr int TSTAGE_P = 6 * 32 * 8;              // particle box of a stage
 constexpr int TSTAGE_PIK = TSTAGE_P + 128 + 128;  // + ids + keys
 
+// The stream keeps 32-bit shared-window addresses of its ring and barriers (computed once per warp): converting a
+// generic pointer for every PTX operand costs an S2R + LEA pair each time.
+__device__ __forceinline__ void mbar_expect_tx_s(unsigned bar_s, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_s(unsigned bar_s, unsigned phase) {
+  unsigned ok = 0;
+#pragma unroll 1
+  for (int spin = 0; spin < (1 << 22); spin++) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar_s), "r"(phase)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();   // a lost TMA completion must not hang the GPU
+}
+__device__ __forceinline__ void tma_box_2d_s(unsigned dst_s, const CUtensorMap* tm, int c0, int c1, unsigned bar_s) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst_s),
+      "l"(tm), "r"(c0), "r"(c1), "r"(bar_s), "l"(0x12F0000000000000ull)   // evict-first, as bulk_g2s_stream
+      : "memory");
+}
+__device__ __forceinline__ void tma_box_1d_s(unsigned dst_s, const CUtensorMap* tm, int c0, unsigned bar_s) {
+  asm volatile(
+      "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2}], [%3], %4;" ::"r"(dst_s),
+      "l"(tm), "r"(c0), "r"(bar_s), "l"(0x12F0000000000000ull)
+      : "memory");
+}
 __device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
@@ -430,6 +460,7 @@ struct Stream {
   int issued;       // iterations whose copies have been issued
   unsigned char* ring;       // [NS][STAGE]
   unsigned long long* bar;   // [NS]
+  unsigned ring_s, bar_s;    // the same two as shared-window addresses
 };
 // the descriptors of a launch: particles always; ids / keys may be absent (nullptr)
 struct StreamMaps { const CUtensorMap* p; const CUtensorMap* id; const CUtensorMap* key; };
@@ -440,12 +471,12 @@ __device__ __forceinline__ void stream_issue(const StreamMaps& M, Stream& st, in
     if (lane == 0) {
       const int slot = st.issued % NS;
       const int e = st.a + 32 * st.issued;
-      unsigned char* dst = st.ring + slot * STAGE;
-      unsigned long long* bar = st.bar + slot;
-      mbar_expect_tx(bar, (unsigned)TSTAGE_P + (M.id ? 128u : 0u) + (M.key ? 128u : 0u));
-      tma_box_2d(dst, M.p, e, 0, bar);
-      if (M.id) tma_box_1d(dst + TSTAGE_P, M.id, e, bar);
-      if (M.key) tma_box_1d(dst + TSTAGE_P + 128, M.key, e, bar);
+      const unsigned dst = st.ring_s + slot * STAGE;
+      const unsigned bar = st.bar_s + slot * 8;
+      mbar_expect_tx_s(bar, (unsigned)TSTAGE_P + (M.id ? 128u : 0u) + (M.key ? 128u : 0u));
+      tma_box_2d_s(dst, M.p, e, 0, bar);
+      if (M.id) tma_box_1d_s(dst + TSTAGE_P, M.id, e, bar);
+      if (M.key) tma_box_1d_s(dst + TSTAGE_P + 128, M.key, e, bar);
     }
     st.issued++;
   }
@@ -465,6 +496,8 @@ __device__ __forceinline__ void stream_open(const StreamMaps& M, const Tile& t, 
   st.issued = 0;
   st.ring = ring;
   st.bar = bar;
+  st.ring_s = smem_u32(ring);
+  st.bar_s = smem_u32(bar);
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
@@ -479,7 +512,7 @@ struct P6 { double x, y, z, vx, vy, vz; };
 
 template <int NS>
 __device__ __forceinline__ void stream_wait(const Stream& st, int it) {
-  mbar_wait(st.bar + it % NS, (unsigned)((it / NS) & 1));
+  mbar_wait_s(st.bar_s + (it % NS) * 8, (unsigned)((it / NS) & 1));
 }
 // lane's particle of iteration `it` (whose stage has been waited for).  A lane outside [lo, b) -- the first / last
 // iteration of a slice may be partial -- reads the nearest particle of the slice instead (a shared-memory broadcast):
