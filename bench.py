@@ -115,7 +115,10 @@ def cpu_reference_rate(steps, warmup, nthreads=None, grid=(32, 32, 32), ppc=64):
     MPI rank with private particle arrays) on a bounded sample of the same workload.
     Returns (particle-pushes/s, per-step seconds list, description)."""
     from oracle import pyoracle as O
-    nthreads = nthreads or min(O.num_threads(), 64)
+    if not nthreads:      # all the host cores this process may use, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        nthreads = min(len(os.sched_getaffinity(0)), 64)
+    O.set_num_threads(nthreads)
+    nthreads = min(O.num_threads(), nthreads)
     mx, my, mz = grid
     p = O.make_parm(mx, my, mz, HX * mx, HY * my, HZ * mz, DT, AIMPL, WCE, EZ00)
     sp = {}

@@ -26,6 +26,15 @@
 
 int64_t orc_mxyzA(const orc_parm* p) { return NX(p) * NY(p) * NZ(p); }
 
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline legs of bench.py set the count explicitly */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -122,6 +122,7 @@ double orc_time_step(const orc_parm* p, const double* const a6p[6], const double
                      int nranks, double* t_pred, double* t_corr);
 
 int orc_num_threads(void);
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

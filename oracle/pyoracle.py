@@ -200,6 +200,11 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    """OpenMP threads of the simulated ranks (torchrun exports OMP_NUM_THREADS=1 to its workers)."""
+    lib().orc_set_num_threads(int(n))
+
+
 def time_step(p, a6p, a6c, arrs, qmult, wmult, nranks):
     """Seconds for one species' predictor + corrector pass by `nranks` threads
     (each with private particle arrays, like the reference's MPI ranks)."""
