@@ -9,8 +9,10 @@
  * PARITY UNPINNED: the reference (one Fortran 2003 file) ships no tests, no
  * golden vectors and no fixtures for this path, and neither this container
  * nor the GPU box has a Fortran compiler or MPI, so oracle/_ref cannot be
- * built.  The pin is this restatement plus the analytic invariants in
- * tests/test_oracle_invariants.py.
+ * built.  The pin is this restatement, the analytic invariants in
+ * tests/test_oracle_invariants.py, and bit-for-bit agreement with a second,
+ * independent transcription of the same Fortran (oracle/np_restatement.py,
+ * tests/test_oracle_crosscheck.py).
  *
  * Citation shorthand: F:n = /root/reference/@mrg37-080A.f03 line n.
  * Arrays use the reference layout real(C_DOUBLE)(-2:mx+1,-1:my+1,-2:mz+1),
