@@ -426,16 +426,19 @@ __device__ __forceinline__ void mbar_wait_s(unsigned bar_s, unsigned phase) {
   }
   __trap();   // a lost TMA completion must not hang the GPU
 }
+#ifndef MRG_STREAM_HINT
+#define MRG_STREAM_HINT 0x12F0000000000000ull   // L2 evict-first (0x14F0... = evict-last, 0x10F0... = normal)
+#endif
 __device__ __forceinline__ void tma_box_2d_s(unsigned dst_s, const CUtensorMap* tm, int c0, int c1, unsigned bar_s) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(dst_s),
-      "l"(tm), "r"(c0), "r"(c1), "r"(bar_s), "l"(0x12F0000000000000ull)   // evict-first, as bulk_g2s_stream
+      "l"(tm), "r"(c0), "r"(c1), "r"(bar_s), "l"(MRG_STREAM_HINT)
       : "memory");
 }
 __device__ __forceinline__ void tma_box_1d_s(unsigned dst_s, const CUtensorMap* tm, int c0, unsigned bar_s) {
   asm volatile(
       "cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2}], [%3], %4;" ::"r"(dst_s),
-      "l"(tm), "r"(c0), "r"(bar_s), "l"(0x12F0000000000000ull)
+      "l"(tm), "r"(c0), "r"(bar_s), "l"(MRG_STREAM_HINT)
       : "memory");
 }
 __device__ __forceinline__ void tma_box_2d(void* dst, const CUtensorMap* tm, int c0, int c1, unsigned long long* bar) {
