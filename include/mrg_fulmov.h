@@ -187,7 +187,8 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                planes and their stencil neighbours only; a rank that owns a
  *                z slab prepares its slab instead of the whole replicated
  *                grid.  -1 (default) = on when nranks > 1, 0 = off, 1 = on.
- *                Needs |vz|*dt < hz (like partbc, which wraps once)
+ *                Needs |vz|*dt < hz (true for |v| < c when c*dt < hz; the
+ *                reference runs hz = 7.5, dt = 1.2)
  *   "kick"       random numbers of the E x B drive kick (F:1342-1364).  0 = the
  *                reference's: every rank draws ranfp once per owned particle
  *                inside the slab, in l order (bit-exact with the reference for

@@ -555,8 +555,9 @@ int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
 // (set G, extended index k+2), the filters run on the interior planes of G (x and y sweeps stay inside a
 // plane), the z sweep needs the blend two planes either side (periodic, F:7365-7395), and the ghost planes
 // k = -1, mz, mz+1 of G need the blend of their periodic images (F:3088-3148).  The planes just outside G are
-// filled with NaN.  Precondition (shared with partbc, which wraps once): no particle moves more than one cell
-// in z per step.
+// filled with NaN.  The recorded planes are those of the gather positions themselves, whatever the speeds; only
+// the drive kick's nearest-node look-up at the NEW position (F:1347-1354) relies on |vz| hdt < hz to stay
+// inside the widened set -- true for |v| < c when c dt < hz (the reference runs hz = 7.5, dt = 1.2).
 int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
   if (p->ifilx < 0 || p->ifily < 0 || p->ifilz < 0) return fail(MRG_ERR_ARG, "negative filter count");
