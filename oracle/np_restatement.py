@@ -240,3 +240,64 @@ def vmesh(p, a):
     for k in (mz, mz + 1):
         a[k - mz + 2, J, I] = a[k + 2, J, I]
     return a
+
+
+def loadpt(p, ppc, vth, vdr, vbeam, ranfa=3021, ranfb=7331):
+    """F:8885-8909 (table fv2) + F:8937-9040, one species; `ppc` particles per cell stand for the source's
+    hard-coded 32 (F:8941).  Returns ([x, y, z, vx, vy, vz], ranfa_state, ranfb_state)."""
+    import math
+    mx, my, mz = p.mx, p.my, p.mz
+    # inverse-CDF table of exp(-v^2) (v + vrg1), Simpson's rule, 100 intervals x 1000 sub-steps
+    vrg1 = vdr / vth
+    fun2 = lambda v: math.exp(-v ** 2) * (v + vrg1)
+    vv = max(-3.0, -vrg1)
+    dv = (3.0 - vv) / 100.0
+    v2 = vv * vth
+    dv2 = dv * vth
+    fv2 = [0.0] * 102                                         # fv2(1..101), fv2(1) = 0
+    for j in range(1, 101):
+        s = 0.0
+        sdv = dv / 1000.0
+        for _ in range(500):
+            vv = vv + 2.0 * sdv
+            s = s + 4.0 * fun2(vv - sdv) + 2.0 * fun2(vv)
+        s = (s + 4.0 * fun2(vv + sdv) + fun2(vv + 2.0 * sdv)) * sdv / 3.0
+        fv2[j + 1] = fv2[j] + s
+    top = fv2[101]
+    for j in range(1, 102):
+        fv2[j] = fv2[j] / top
+    npr = mx * my * mz * ppc
+    x, y, z = np.empty(npr), np.empty(npr), np.empty(npr)
+    vx, vy, vz = np.empty(npr), np.empty(npr), np.empty(npr)
+    sb = ranfb
+    for l in range(npr):                                      # positions: three ranfp draws per particle
+        sb, u = ranfp_next(sb); x[l] = p.xmax * u - p.hx / 2
+        sb, u = ranfp_next(sb); y[l] = p.ymax * u
+        sb, u = ranfp_next(sb); z[l] = p.zmax * u - p.hz / 2
+    sa = ranfa
+    zcent, dzcent, dzsmt = 0.50 * p.zmax, 0.125 * p.zmax, 0.15 * p.zmax
+    ycent1, ycent2, dycent = 0.30 * p.ymax, 0.70 * p.ymax, 0.05 * p.ymax
+    rrz, rry = 0.25 * p.zmax, 0.075 * p.ymax
+    for l in range(npr):                                      # velocities: four ranf draws per particle (same LCG)
+        sa, eps = ranfp_next(sa)
+        k2 = 100
+        for k in range(1, 101):
+            k2 = k
+            if fv2[k] > eps:
+                break
+        y1, y2 = fv2[k2 - 1], fv2[k2]
+        x2 = (eps - y2) / (y2 - y1) + k2
+        vmag = v2 + dv2 * (x2 - 1.0) + vdr
+        sa, u = ranfp_next(sa); vxo = vmag * (u - 0.5)
+        sa, u = ranfp_next(sa); vyo = vmag * (u - 0.5)
+        sa, u = ranfp_next(sa); vzo = vmag * (u - 0.5)
+        az = abs(z[l] - zcent)
+        if az < dzcent or az < dzsmt:
+            ycnt1, ycnt2 = ycent1 + dycent, ycent2 - dycent
+        else:
+            ycnt1, ycnt2 = ycent1, ycent2
+        vdrift = 0.0
+        if az <= rrz and (abs(y[l] - ycnt1) <= rry or abs(y[l] - ycnt2) <= rry):
+            vdrift = vbeam
+        vx[l], vy[l], vz[l] = vxo + vdrift, vyo, vzo
+    return [x, y, z, vx, vy, vz], sa, sb

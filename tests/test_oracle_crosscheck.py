@@ -82,3 +82,17 @@ def test_predictor_moments_bit_identical(case, ksp):
     # what the fold does (Q1): interior planes next to the seams are overwritten, not accumulated
     f = folded[3].reshape(p.mz + 4, p.my + 3, p.mx + 4)
     assert np.all(f[2:p.mz + 2, 1:p.my + 2, 1 + 2] == 0.0) and np.all(f[2:p.mz + 2, 1:p.my + 2, p.mx - 2 + 2] == 0.0)
+
+
+@pytest.mark.parametrize("ksp", [1, 2])
+def test_loadpt_bit_identical(ksp):
+    """The synthetic two-flux-bundle load (positions from ranfp, speeds from the tabulated inverse CDF and ranf,
+    beam drift inside the bundles): the C oracle, which bench.py and the device loader are checked against, and the
+    numpy transcription of F:8885-9040 give the same particles and leave both LCGs in the same state."""
+    p = U.make_parm(6, 5, 8)
+    a, sa, sb = O.loadpt(p, 7, U.vth(ksp), 0.0, U.VBEAM[ksp])
+    b, ta, tb = N.loadpt(p, 7, U.vth(ksp), 0.0, U.VBEAM[ksp])
+    assert (sa, sb) == (ta, tb)
+    for c in range(6):
+        np.testing.assert_array_equal(a[c], b[c], err_msg="component %d" % c)
+    assert np.count_nonzero(a[3] != b[3] - 0.0) == 0 and np.any(np.abs(a[3]) > 0)
