@@ -158,8 +158,9 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                (ballot/shuffle) per 32 particles then atomics, 2 = cell-run
  *                register accumulation + warp pre-reduction (default)
  *   "tile"       1 (default) = after mrg_sort, particle passes run on
- *                TMA-staged shared-memory field tiles with shared-memory
- *                moment accumulators; 0 = gather through L1 only; 2 = two
+ *                TMA-staged shared-memory field tiles, particles stream
+ *                through tensor-TMA stages, cell-run totals of the moments
+ *                leave with red.global.add.f64; 0 = gather through L1 only; 2 = two
  *                particles per thread; 3 = register-stationary lane pairs on
  *                an interleaved tile layout; 4 = quad-cooperative polynomial
  *                gather (2-4 are experimental)
