@@ -319,8 +319,10 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "kernel": dominant, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "predictor": {"ms_per_launch": tp, "algorithmic_bytes": bytes_pred, "gbs": gb_pred, "frac": gb_pred / peak},
-                "corrector": {"ms_per_launch": tc, "algorithmic_bytes": bytes_corr, "gbs": gb_corr, "frac": gb_corr / peak},
+                "predictor": {"ms_per_launch": tp, "algorithmic_bytes": bytes_pred, "gbs": gb_pred, "frac": gb_pred / peak,
+                              "particle_passes_per_s": n_sp / (tp * 1e-3)},
+                "corrector": {"ms_per_launch": tc, "algorithmic_bytes": bytes_corr, "gbs": gb_corr, "frac": gb_corr / peak,
+                              "particle_passes_per_s": n_sp / (tc * 1e-3)},
                 "whole_step": {"algorithmic_bytes": step_bytes, "gbs": step_bytes * args.steps / (ms * 1e-3) / 1e9 if world == 1 else None,
                                "frac": step_bytes * args.steps / (ms * 1e-3) / 1e9 / peak if world == 1 else None}}
 
