@@ -1,0 +1,184 @@
+"""ctypes binding of oracle/_ref/libmrg_ref.so: the reference's own routines (F = @mrg37-080A.f03), translated to C
+by oracle/f03c.py and compiled by oracle/build_ref.py.  TEST INFRASTRUCTURE: only tests/, bench.py's CPU legs and the
+golden-vector generators use it.
+
+    with RefRun(mx, my, mz, np0, nranks=4) as R:      # param_080A.h sizes; one thread per simulated MPI rank
+        R.set("parm2", "dt", 1.2)                     # COMMON members by the name the reference gives them
+        ex = R.arr("fields", "ex", rank=0)            # numpy view of rank 0's COMMON /fields/ ex(-2:mx+1,-1:my+1,-2:mz+1)
+        R.call("fulmov", x, y, z, vx, vy, vz, qmult, wmult, npr, ipc, ksp, IPAR, SIZE)
+
+`call` runs the unit on every rank at once (the ranks meet in the simulated mpi_allreduce).  Arguments: numpy arrays are
+passed as they are (shared by the ranks unless a list of per-rank arrays is given), Python floats / ints become
+by-reference temporaries, IPAR stands for rank+1 and SIZE for the number of ranks (F:219).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build_ref
+
+_lib = None
+IPAR, SIZE = object(), object()
+
+
+def available():
+    return build_ref.available() or build_ref.can_build()
+
+
+def load():
+    global _lib
+    if _lib is None:
+        path = build_ref.build()
+        if not path or not os.path.exists(path):
+            raise RuntimeError("oracle/_ref/libmrg_ref.so is missing and /root/reference is not here to build it from")
+        L = C.CDLL(path)
+        L.ref_set_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_long]
+        L.ref_param.argtypes = [C.c_char_p]
+        L.ref_param.restype = C.c_long
+        L.ref_pool_start.argtypes = [C.c_int]
+        L.ref_common.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_int)]
+        L.ref_common.restype = C.c_void_p
+        L.ref_call.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.ref_has_unit.argtypes = [C.c_char_p]
+        L.ref_collective_seconds.argtypes = [C.c_int, C.c_int]
+        L.ref_collective_seconds.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+_NP = {1: np.int32, 2: np.float32, 3: np.float64}
+
+
+class RefRun:
+    """One run of the translated reference: sizes of param_080A.h + a pool of simulated MPI ranks.  Only one can be
+    alive at a time (the reference's sizes are process-wide, as its PARAMETERs are)."""
+
+    def __init__(self, mx, my, mz, np0, nranks=1, npc=None):
+        self.L = load()
+        self.L.ref_pool_stop()
+        npc = npc or nranks
+        if self.L.ref_set_params(npc, mx, my, mz, np0):
+            raise RuntimeError("ref_set_params failed")
+        if self.L.ref_pool_start(nranks):
+            raise RuntimeError("ref_pool_start failed")
+        self.mx, self.my, self.mz, self.np0, self.nranks = mx, my, mz, np0, nranks
+        self.last_secs = [0.0] * nranks
+
+    def close(self):
+        self.L.ref_pool_stop()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def param(self, name):
+        return self.L.ref_param(name.encode())
+
+    def has(self, unit):
+        return self.L.ref_has_unit(unit.encode()) >= 0
+
+    # -- COMMON ----------------------------------------------------------------------------------
+    def arr(self, block, name, rank=0, unit=None):
+        """numpy view (flat, Fortran storage order) of a COMMON member of one rank"""
+        cnt, typ = C.c_long(), C.c_int()
+        p = self.L.ref_common(rank, block.encode(), unit.encode() if unit else None, name.encode(), C.byref(cnt), C.byref(typ))
+        if not p:
+            raise KeyError("COMMON /%s/ %s (unit %s)" % (block, name, unit))
+        ct = {1: C.c_int32, 2: C.c_float, 3: C.c_double}[typ.value]
+        return np.ctypeslib.as_array((ct * cnt.value).from_address(p))
+
+    def set(self, block, name, value, unit=None):
+        for r in range(self.nranks):
+            self.arr(block, name, r, unit)[...] = value
+
+    def get(self, block, name, rank=0, unit=None):
+        a = self.arr(block, name, rank, unit)
+        return a[0] if a.size == 1 else a.copy()
+
+    # -- calls -----------------------------------------------------------------------------------
+    def call(self, unit, *args):
+        n = self.L.ref_has_unit(unit.encode())
+        if n < 0:
+            raise KeyError("unit %r is not in the translated reference" % unit)
+        if n != len(args):
+            raise TypeError("%s takes %d arguments, %d given" % (unit, n, len(args)))
+        keep, table = [], (C.c_void_p * (self.nranks * max(n, 1)))()
+        for r in range(self.nranks):
+            for i, a in enumerate(args):
+                if a is IPAR:
+                    a = r + 1
+                elif a is SIZE:
+                    a = self.nranks
+                elif isinstance(a, (list, tuple)):
+                    a = a[r]
+                if isinstance(a, np.ndarray):
+                    assert a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
+                    table[r * n + i] = a.ctypes.data
+                    keep.append(a)
+                elif isinstance(a, (int, np.integer)):
+                    b = C.c_int32(int(a))
+                    keep.append(b)
+                    table[r * n + i] = C.addressof(b)
+                elif isinstance(a, (float, np.floating)):
+                    b = C.c_double(float(a))
+                    keep.append(b)
+                    table[r * n + i] = C.addressof(b)
+                elif isinstance(a, (C.c_int32, C.c_double)):
+                    keep.append(a)
+                    table[r * n + i] = C.addressof(a)
+                else:
+                    raise TypeError("argument %d of %s: %r" % (i + 1, unit, type(a)))
+        ret = (C.c_double * self.nranks)()
+        secs = (C.c_double * self.nranks)()
+        rc = self.L.ref_call(unit.encode(), table, ret, secs)
+        if rc:
+            raise RuntimeError("ref_call(%s) -> %d" % (unit, rc))
+        self.last_secs = list(secs)
+        return list(ret)
+
+    def collective_seconds(self, reset=True):
+        return [self.L.ref_collective_seconds(r, 1 if reset else 0) for r in range(self.nranks)]
+
+
+# ------------------------------------------------------------------------------------------------
+# Conveniences shared by the pin tests, the golden-vector generator and bench.py's reference leg
+# ------------------------------------------------------------------------------------------------
+def setup_run(R, xmax, ymax, zmax, dt=1.2, aimpl=0.6, wce_by_wpe=0.2, Ez00=0.25e-2, veth=0.2, te_by_ti=1.0,
+              qspec=(1.0, -1.0), wspec=(100.0, 1.0), vbeam=(0.35e-2, -0.35e-2), vdr=(0.0, 0.0), nha=5, io_pe=0):
+    """What `program` does before `init` (F:184-374): the namelist values of rec_3d80A into COMMON, filters forced to 1."""
+    for name, v in (("xmax", xmax), ("ymax", ymax), ("zmax", zmax), ("dt", dt), ("aimpl", aimpl), ("wce_by_wpe", wce_by_wpe),
+                    ("veth", veth), ("te_by_ti", te_by_ti), ("pi", 3.141592653589), ("thb", 90.0), ("rwd", 50.0),
+                    ("epsln1", 1e-5)):
+        R.set("parm2", name, v, unit="fulmov")
+    for r in range(R.nranks):
+        R.arr("parm2", "qspec", r, "fulmov")[:2] = qspec
+        R.arr("parm2", "wspec", r, "fulmov")[:2] = wspec
+        R.arr("parm2", "vbeam", r, "fulmov")[:2] = vbeam
+        R.arr("parm2", "vdr", r, "fulmov")[:2] = vdr
+    R.set("profl", "ez00", Ez00, unit="fulmov")
+    for name, v in (("ifilx", 1), ("ifily", 1), ("ifilz", 1), ("nha", nha), ("it", 0), ("ldec", 1), ("iloadp", 0)):   # F:368-370
+        R.set("parm1", name, v, unit="fulmov")
+    R.set("iope66", "io_pe", io_pe, unit="fulmov")
+
+
+def ref_init(R):
+    """call the reference's own init (F:8244-8731) on every rank: tables, constants, loadpt of both species, xe = xi.
+    Returns per-rank particle arrays {ksp: [x,y,z,vx,vy,vz]} (every rank loads ALL particles, F:121-122)."""
+    n = R.np0
+    parts = []
+    for r in range(R.nranks):
+        parts.append({k: [np.zeros(n) for _ in range(6)] for k in (1, 2)})
+    args = []
+    for k in (1, 2):
+        args += [[parts[r][k][c] for r in range(R.nranks)] for c in range(6)]
+        args += [0.0, 0.0]
+    qm = [[C.c_double(), C.c_double(), C.c_double(), C.c_double()] for _ in range(R.nranks)]
+    npr = [C.c_int32(0) for _ in range(R.nranks)]
+    a = ([[parts[r][1][c] for r in range(R.nranks)] for c in range(6)] + [[q[0] for q in qm], [q[1] for q in qm]]
+         + [[parts[r][2][c] for r in range(R.nranks)] for c in range(6)] + [[q[2] for q in qm], [q[3] for q in qm]]
+         + [npr, 0])
+    R.call("init", *a)
+    return parts, npr[0].value, [(q[0].value, q[1].value, q[2].value, q[3].value) for q in qm][0]
