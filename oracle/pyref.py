@@ -182,3 +182,67 @@ def ref_init(R):
          + [npr, 0])
     R.call("init", *a)
     return parts, npr[0].value, [(q[0].value, q[1].value, q[2].value, q[3].value) for q in qm][0]
+
+
+FIELD_NAMES = ("ex", "ey", "ez", "bx", "by", "bz", "ex0", "ey0", "ez0", "bx0", "by0", "bz0")
+MOMENT_NAMES = {1: ("qix", "qiy", "qiz", "qi"), 2: ("qex", "qey", "qez", "qe")}
+
+
+def reference_steps(grid, box, particles, field_sets, nranks=1, ranfb_in=None, qspec=(1.0, -1.0), wspec=(100.0, 1.0),
+                    dt=1.2, aimpl=0.6, wce_by_wpe=0.2, Ez00=0.25e-2, nha=5, it0=1):
+    """The reference's own call sequence of trans (F:749-807) around the particle path, with the field solve replaced by
+    given fields: for every (f_pred, f_corr) in field_sets
+        COMMON /fields/ <- f_pred;  fulmov(ions, ipc=1); fulmov(electrons, ipc=1)      -> folded moments, wkix/wkih
+        COMMON /fields/ <- f_corr;  fulmov(ions, ipc=0); fulmov(electrons, ipc=0)      -> particles, ranfb
+    executed by `nranks` simulated MPI ranks (every rank holds all particles, touches l = rank+1, rank+1+nranks, ...).
+    particles = {ksp: [x,y,z,vx,vy,vz]} (not modified).  Returns a dict of per-step results and the final state
+    (owned subsets merged back into one set of arrays).  `init` runs first, so every COMMON constant is the reference's."""
+    mx, my, mz = grid
+    n = len(particles[1][0])
+    np0 = max(n, 32 * mx * my * mz)           # init's loadpt loads 32 per cell into arrays of np0 (F:8941, Q6)
+    out = {"mom": [], "wk_pred": [], "wk_corr": []}
+    with RefRun(mx, my, mz, np0, nranks=nranks) as R:
+        setup_run(R, box[0], box[1], box[2], dt=dt, aimpl=aimpl, wce_by_wpe=wce_by_wpe, Ez00=Ez00, qspec=qspec, wspec=wspec, nha=nha)
+        parts, _, _ = ref_init(R)
+        ranfb_after_init = int(R.get("ranfb", "ir", unit="ranfp"))
+        if ranfb_in is None:
+            ranfb_in = ranfb_after_init
+        for r in range(nranks):
+            R.arr("ranfb", "ir", r, "ranfp")[0] = ranfb_in
+            for k in (1, 2):
+                for c in range(6):
+                    parts[r][k][c][:n] = particles[k][c]
+        it = it0
+        for f_pred, f_corr in field_sets:
+            R.set("parm1", "it", it, unit="fulmov")
+            for name, a in zip(FIELD_NAMES, f_pred):
+                R.set("fields", name, a, unit="fulmov")
+            mom, wk = {}, {}
+            for k in (1, 2):
+                xs = [[parts[r][k][c] for r in range(nranks)] for c in range(6)]
+                R.call("fulmov", *xs, float(qspec[k - 1]), float(wspec[k - 1]), n, 1, k, IPAR, SIZE)
+                mom[k] = [R.get("srimp7", nm, unit="fulmov") for nm in MOMENT_NAMES[k]]
+                wk[k] = (float(R.get("wkinel", "wkix", unit="fulmov")), float(R.get("wkinel", "wkih", unit="fulmov")))
+            out["mom"].append(mom)
+            out["wk_pred"].append(wk)
+            for name, a in zip(FIELD_NAMES, f_corr):
+                R.set("fields", name, a, unit="fulmov")
+            wk = {}
+            for k in (1, 2):
+                xs = [[parts[r][k][c] for r in range(nranks)] for c in range(6)]
+                R.call("fulmov", *xs, float(qspec[k - 1]), float(wspec[k - 1]), n, 0, k, IPAR, SIZE)
+                wk[k] = (float(R.get("wkinel", "wkix", unit="fulmov")), float(R.get("wkinel", "wkih", unit="fulmov")))
+            out["wk_corr"].append(wk)
+            it += 1
+        final = {}
+        for k in (1, 2):
+            final[k] = [np.empty(n) for _ in range(6)]
+            for r in range(nranks):
+                for c in range(6):
+                    final[k][c][r::nranks] = parts[r][k][c][:n][r::nranks]
+        out["final"] = final
+        out["ranfb"] = [int(R.get("ranfb", "ir", rank=r, unit="ranfp")) for r in range(nranks)]
+        out["ranfb_in"] = ranfb_in
+        out["edec"] = R.get("parm2", "edec", unit="fulmov")
+        out["consts"] = {nm: float(R.get("parm2", nm, unit="fulmov")) for nm in ("hxi", "hyi", "hzi", "xmaxe", "zmaxe", "adt", "hdt", "bxc")}
+    return out

@@ -142,7 +142,7 @@ static pthread_t g_thr[REF_MAX_RANKS];
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cv_job = PTHREAD_COND_INITIALIZER, g_cv_done = PTHREAD_COND_INITIALIZER;
 static job_t *g_job = NULL;
-static long g_job_seq = 0;
+static long g_job_seq = 0, g_start_seq = 0;
 static int g_done = 0, g_quit = 0, g_running = 0;
 static char *g_cm[REF_MAX_RANKS][CM_COUNT];
 static long g_cm_bytes[CM_COUNT];
@@ -168,7 +168,7 @@ static double call_unit(const ref_unit_t *u, void **a) {
 static void *worker(void *arg) {
   t_rank = (int)(long)arg;
   for (int b = 0; b < CM_COUNT; b++) ref_cm[b] = g_cm[t_rank][b];
-  long seen = 0;
+  long seen = g_start_seq;      /* jobs posted before this pool started are not ours */
   for (;;) {
     pthread_mutex_lock(&g_mu);
     while (!g_quit && g_job_seq == seen) pthread_cond_wait(&g_cv_job, &g_mu);
@@ -217,6 +217,8 @@ int ref_pool_start(int nranks) {
     for (int r = 0; r < nranks; r++) g_cm[r][b] = (char *)calloc((size_t)total + 64, 1);
   }
   for (int r = 0; r < nranks; r++) g_t_allreduce[r] = 0.0;
+  g_start_seq = g_job_seq;
+  g_job = NULL;
   for (int r = 0; r < nranks; r++) pthread_create(&g_thr[r], NULL, worker, (void *)(long)r);
   g_running = 1;
   return 0;

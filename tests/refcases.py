@@ -1,0 +1,72 @@
+"""Seeded inputs shared by the reference-pin tests, the golden-vector generator and the GPU parity tests.
+Nothing here touches the reference; the cases are run through oracle/pyref (the translated reference), the C oracle and
+the CUDA path by their respective tests."""
+import numpy as np
+
+from oracle import pyoracle as O
+from tests import util as U
+
+
+def loader_case(mx, my, mz, ppc, steps, seed0=100):
+    """two-flux-bundle load of the oracle's loader (pinned bit for bit to the reference's loadpt) + `steps` pairs of
+    smooth field sets (before / after the field solve)"""
+    p = U.make_parm(mx, my, mz)
+    sp, ranfb = U.load_species(p, ppc)
+    fsets = [(U.smooth_fields(p, seed=seed0 + 2 * s), U.smooth_fields(p, seed=seed0 + 2 * s + 1)) for s in range(steps)]
+    return p, sp, ranfb, fsets
+
+
+def edge_case(mx=8, my=6, mz=8, n=2048, seed=42):
+    """particles on / next to the periodic seams, the walls and cell boundaries, fast enough to
+    wrap and reflect; same construction as tests/test_gpu_parity.py::test_edge_particles"""
+    p = U.make_parm(mx, my, mz)
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(-p.hx / 2, p.xmax - p.hx / 2, n)
+    y = rng.uniform(0, p.ymax, n)
+    z = rng.uniform(-p.hz / 2, p.zmax - p.hz / 2, n)
+    v = [rng.normal(scale=0.3, size=n) for _ in range(3)]
+    sx = [np.nextafter(-p.hx / 2, 1), np.nextafter(p.xmax - p.hx / 2, 0), 0.5 * p.hx, np.nextafter(0.5 * p.hx, 0),
+          np.nextafter(0.5 * p.hx, 1), 0.0, 1.5 * p.hx, -p.hx / 2, p.xmax - p.hx / 2]
+    for q, val in enumerate(sx):
+        x[q] = val
+        z[q + 16] = val * p.hz / p.hx
+    y[32:42] = [np.nextafter(0, 1), np.nextafter(p.ymax, 0), p.hy, np.nextafter(p.hy, 0), np.nextafter(p.hy, 1),
+                p.ymax - 1e-9, 1e-9, (p.my - 1) * p.hy, 0.0, p.ymax]
+    v[1][32] = -0.5; v[1][33] = 0.5; v[1][37] = 0.5; v[1][38] = -0.5
+    v[0][0] = -0.5; v[0][1] = 0.5; v[2][16] = -0.5; v[2][17] = 0.5
+    v[1][40] = 0.0; v[1][41] = 0.0          # exactly on the walls with no motion: the jp >= my branch of F:1191 / F:2285
+    # a few particles inside the drive slab so that the kick draws (F:1343-1353)
+    k0 = 64
+    m = 400
+    z[k0:k0 + m] = p.zcent + rng.uniform(-0.14, 0.14, m) * p.zmax
+    y[k0:k0 + m] = np.where(rng.uniform(size=m) < 0.5, p.ycent1, p.ycent2) + rng.uniform(-0.02, 0.02, m) * p.ymax
+    for c in range(3):
+        v[c][k0:k0 + m] *= 0.05
+    arrs = [np.ascontiguousarray(a) for a in [x, y, z] + v]
+    sp = {1: arrs, 2: [a.copy() for a in arrs]}
+    fsets = [(U.smooth_fields(p, seed=7), U.smooth_fields(p, seed=8))]
+    return p, sp, 7331, fsets
+
+
+def oracle_steps(p, sp, ranfb, fsets, nranks):
+    """the same call sequence as pyref.reference_steps through the C oracle"""
+    arrs = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.full(nranks, ranfb, dtype=np.int32)
+    out = {"mom": [], "wk_pred": [], "wk_corr": []}
+    for f_pred, f_corr in fsets:
+        a6 = O.field_prep(p, f_pred)
+        mom, wk = {}, {}
+        for k in (1, 2):
+            r = O.fulmov(p, a6, *arrs[k], U.QSPEC[k], U.WSPEC[k], 1, nranks=nranks, ranfb=st)
+            mom[k], wk[k] = r["mom"], (r["wkix"], r["wkih"])
+        out["mom"].append(mom)
+        out["wk_pred"].append(wk)
+        a6 = O.field_prep(p, f_corr)
+        wk = {}
+        for k in (1, 2):
+            r = O.fulmov(p, a6, *arrs[k], U.QSPEC[k], U.WSPEC[k], 0, nranks=nranks, ranfb=st)
+            wk[k] = (r["wkix"], r["wkih"])
+        out["wk_corr"].append(wk)
+    out["final"] = arrs
+    out["ranfb"] = [int(v) for v in st]
+    return out

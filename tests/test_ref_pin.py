@@ -1,0 +1,169 @@
+"""The oracle is pinned to the reference's own code.
+
+oracle/_ref/libmrg_ref.so is /root/reference/@mrg37-080A.f03 itself -- init, loadpt, fulmov, partbc, partbcEST, srimp1,
+srimp2, outmesh3, filt3e, vmesh3, vmesh1, ranf, ranfp, iwrt -- translated statement by statement to C by oracle/f03c.py
+(the image has no Fortran compiler) and run by simulated MPI ranks.  Two layers:
+
+  * live   (needs oracle/_ref, i.e. this container or a snapshot that carries the prebuilt library): the C oracle and
+           the translated reference run the same seeded cases and must agree BIT FOR BIT -- loads, folded moments,
+           wkix/wkih, corrector output with the drive kick, every rank's ranfp state;
+  * golden (always): tests/golden/ref_*.npz were written by the translated reference (tests/golden/make_golden_ref.py);
+           the oracle must reproduce them bit for bit.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as O
+from oracle import pyref as PR
+from tests import refcases as RC
+from tests import util as U
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+needs_ref = pytest.mark.skipif(not PR.available(), reason="oracle/_ref is not built and /root/reference is not here")
+
+
+def digest(arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a, dtype=np.float64).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8)
+
+
+def assert_same(ref, orc, nsteps):
+    for s in range(nsteps):
+        for k in (1, 2):
+            for c in range(4):
+                np.testing.assert_array_equal(ref["mom"][s][k][c], orc["mom"][s][k][c])
+            assert tuple(ref["wk_pred"][s][k]) == tuple(orc["wk_pred"][s][k])
+            assert tuple(ref["wk_corr"][s][k]) == tuple(orc["wk_corr"][s][k])
+    for k in (1, 2):
+        for c in range(6):
+            np.testing.assert_array_equal(ref["final"][k][c], orc["final"][k][c])
+    assert list(ref["ranfb"]) == list(orc["ranfb"])
+
+
+@needs_ref
+def test_reference_init_and_loadpt_match_oracle_loader():
+    """init (F:8244-8731) with its two loadpt calls and ipleql vs the oracle's loader, 32 per cell as the source has it"""
+    mx, my, mz = 8, 6, 8
+    p = U.make_parm(mx, my, mz)
+    with PR.RefRun(mx, my, mz, 32 * mx * my * mz, nranks=1) as R:
+        PR.setup_run(R, p.xmax, p.ymax, p.zmax)
+        parts, npr, _ = PR.ref_init(R)
+        consts = {nm: float(R.get("parm2", nm, unit="fulmov")) for nm in ("hxi", "hyi", "hzi", "xmaxe", "zmaxe", "adt", "hdt", "bxc")}
+        profl = [float(R.get("profl", nm, unit="fulmov")) for nm in ("zcent", "ycent1", "ycent2")]
+        ranfb = int(R.get("ranfb", "ir", unit="ranfp"))
+        hx, hz = float(R.get("ptable", "hx", unit="fulmov")), float(R.get("ptable", "hz", unit="fulmov"))
+    assert npr == 32 * mx * my * mz
+    sp, st = U.load_species(p, 32)
+    for k in (1, 2):
+        for c in range(6):
+            np.testing.assert_array_equal(parts[0][k][c], sp[k][c])
+    assert ranfb == st
+    assert consts == {"hxi": p.hxi, "hyi": p.hyi, "hzi": p.hzi, "xmaxe": p.xmaxe, "zmaxe": p.zmaxe, "adt": p.adt, "hdt": p.hdt, "bxc": p.bxc}
+    assert profl == [p.zcent, p.ycent1, p.ycent2] and (hx, hz) == (p.hx, p.hz)
+
+
+@needs_ref
+@pytest.mark.parametrize("grid,ppc,steps,nranks", [((6, 4, 6), 32, 3, 1), ((6, 4, 6), 32, 3, 4), ((8, 6, 8), 20, 2, 3),
+                                                     ((12, 5, 8), 7, 2, 8), ((16, 12, 16), 16, 1, 2)])
+def test_fulmov_sequence_bit_identical(grid, ppc, steps, nranks):
+    p, sp, ranfb, fsets = RC.loader_case(*grid, ppc, steps)
+    ref = PR.reference_steps(grid, (p.xmax, p.ymax, p.zmax), sp, fsets, nranks=nranks, ranfb_in=ranfb)
+    orc = RC.oracle_steps(p, sp, ranfb, fsets, nranks)
+    assert_same(ref, orc, steps)
+
+
+@needs_ref
+@pytest.mark.parametrize("nranks", [1, 2, 5])
+def test_edge_particles_bit_identical(nranks):
+    """seams, walls (incl. y == 0 and y == ymax exactly: the jp >= my branches of F:1191 and F:2285), cell boundaries
+    +-1 ulp, drive-slab particles"""
+    p, sp, ranfb, fsets = RC.edge_case()
+    ref = PR.reference_steps((p.mx, p.my, p.mz), (p.xmax, p.ymax, p.zmax), sp, fsets, nranks=nranks, ranfb_in=ranfb)
+    orc = RC.oracle_steps(p, sp, ranfb, fsets, nranks)
+    assert_same(ref, orc, 1)
+    assert not np.array_equal(ref["final"][1][4], sp[1][4])        # something was kicked / reflected
+
+
+@needs_ref
+def test_large_dt_heavy_species_bit_identical():
+    """BASELINE configs[4] regime: dt*wce > 10 and a heavy positive species (q = +1, m = 1600) through the ksp = 1 slot"""
+    p, sp, ranfb, fsets = RC.loader_case(6, 4, 6, 8, 1)
+    kw = dict(dt=1.2, wce_by_wpe=9.0, wspec=(1600.0, 1.0))
+    ref = PR.reference_steps((6, 4, 6), (p.xmax, p.ymax, p.zmax), sp, fsets, nranks=2, ranfb_in=ranfb, **kw)
+    pp = O.make_parm(6, 4, 6, p.xmax, p.ymax, p.zmax, 1.2, 0.6, 9.0, 0.25e-2)
+    W = {1: 1600.0, 2: 1.0}
+    arrs = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.full(2, ranfb, dtype=np.int32)
+    a6 = O.field_prep(pp, fsets[0][0])
+    for k in (1, 2):
+        r = O.fulmov(pp, a6, *arrs[k], U.QSPEC[k], W[k], 1, nranks=2, ranfb=st)
+        for c in range(4):
+            np.testing.assert_array_equal(ref["mom"][0][k][c], r["mom"][c])
+    a6 = O.field_prep(pp, fsets[0][1])
+    for k in (1, 2):
+        O.fulmov(pp, a6, *arrs[k], U.QSPEC[k], W[k], 0, nranks=2, ranfb=st)
+        for c in range(6):
+            np.testing.assert_array_equal(ref["final"][k][c], arrs[k][c])
+    assert ref["ranfb"] == [int(v) for v in st]
+
+
+@needs_ref
+def test_history_rows_written_by_the_reference():
+    """edec(ldec,5..8) <- wkix/wkih when mod(it,nha) == 0 on io_pe == 1 (F:1320-1328): the rows the host mirrors fill"""
+    p, sp, ranfb, fsets = RC.loader_case(6, 4, 6, 4, 1)
+    mx, my, mz = 6, 4, 6
+    with PR.RefRun(mx, my, mz, 32 * mx * my * mz, nranks=1) as R:
+        PR.setup_run(R, p.xmax, p.ymax, p.zmax, nha=5, io_pe=1)
+        parts, _, _ = PR.ref_init(R)
+        n = len(sp[1][0])
+        for k in (1, 2):
+            for c in range(6):
+                parts[0][k][c][:n] = sp[k][c]
+        for name, a in zip(PR.FIELD_NAMES, fsets[0][0]):
+            R.set("fields", name, a, unit="fulmov")
+        R.set("parm1", "it", 10, unit="fulmov")
+        R.set("parm1", "ldec", 3, unit="fulmov")
+        wk = {}
+        for k in (1, 2):
+            R.call("fulmov", *parts[0][k], U.QSPEC[k], U.WSPEC[k], n, 1, k, 1, 1)
+            wk[k] = (float(R.get("wkinel", "wkix", unit="fulmov")), float(R.get("wkinel", "wkih", unit="fulmov")))
+        edec = R.get("parm2", "edec", unit="fulmov").reshape(12, 3000)      # edec(3000,12), column-major
+        assert (edec[4, 2], edec[5, 2], edec[6, 2], edec[7, 2]) == (wk[1][0], wk[1][1], wk[2][0], wk[2][1])
+        R.set("parm1", "it", 11, unit="fulmov")
+        R.set("parm1", "ldec", 4, unit="fulmov")
+        R.call("fulmov", *parts[0][1], U.QSPEC[1], U.WSPEC[1], n, 1, 1, 1, 1)
+        assert R.get("parm2", "edec", unit="fulmov").reshape(12, 3000)[4, 3] == 0.0
+
+
+# ---- committed reference output -------------------------------------------------------------------------
+CASES = {"loader_4r": lambda: RC.loader_case(6, 4, 6, 32, 3), "loader_1r": lambda: RC.loader_case(6, 4, 6, 32, 2),
+         "edge_2r": RC.edge_case}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_reproduces_reference_golden(name):
+    G = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
+    p, sp, ranfb, fsets = CASES[name]()
+    nranks, steps, sample = int(G["nranks"][0]), int(G["steps"][0]), int(G["sample"][0])
+    assert [p.mx, p.my, p.mz] == [int(v) for v in G["grid"]] and ranfb == int(G["ranfb_in"][0])
+    for k in (1, 2):
+        if "in_%d" % k in G.files:            # stored inputs: use them (and check the generator still makes the same)
+            np.testing.assert_array_equal(np.stack(sp[k]), G["in_%d" % k])
+        np.testing.assert_array_equal(digest(sp[k]), G["in_sha_%d" % k])
+    consts = [p.hxi, p.hyi, p.hzi, p.xmaxe, p.zmaxe, p.adt, p.hdt, p.bxc]
+    np.testing.assert_array_equal(np.array(consts), G["consts"])
+    orc = RC.oracle_steps(p, sp, ranfb, fsets, nranks)
+    for s in range(steps):
+        for k in (1, 2):
+            np.testing.assert_array_equal(np.stack(orc["mom"][s][k]), G["mom_%d_%d" % (s, k)])
+            wk = list(orc["wk_pred"][s][k]) + list(orc["wk_corr"][s][k])
+            np.testing.assert_array_equal(np.array(wk), G["wk_%d_%d" % (s, k)])
+    for k in (1, 2):
+        np.testing.assert_array_equal(np.stack([a[::sample] for a in orc["final"][k]]), G["out_%d" % k])
+        np.testing.assert_array_equal(digest(orc["final"][k]), G["out_sha_%d" % k])     # every particle, not only the sample
+    assert orc["ranfb"] == [int(v) for v in G["ranfb_out"]]
