@@ -160,10 +160,8 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *   "tile"       1 (default) = after mrg_sort, particle passes run on
  *                TMA-staged shared-memory field tiles, particles stream
  *                through tensor-TMA stages, cell-run totals of the moments
- *                leave with red.global.add.f64; 0 = gather through L1 only; 2 = two
- *                particles per thread; 3 = register-stationary lane pairs on
- *                an interleaved tile layout; 4 = quad-cooperative polynomial
- *                gather (2-4 are experimental)
+ *                leave with red.global.add.f64; 0 = gather through L1 only
+ *                (any particle order)
  *   "fused_sort" 1 (default) = the tiled predictor emits the cell keys of the
  *                next order and the tiled corrector writes the updated
  *                particles straight into that order, so mrg_sort(ksp, hdt)
@@ -264,6 +262,26 @@ int mrg_compact_layout(int32_t mz, int32_t nranks, int32_t rank,
  * time between two recorded slots in milliseconds (synchronises on b).       */
 int mrg_event_record(mrg_ctx* ctx, int32_t slot);
 int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
+
+/* Cheap invariants of the resident state, for callers that want to check a
+ * run without a CPU reference (bench.py prints them with every line):
+ *   sums[0..3]  sums over the extended grid of the RAW (rank-summed, unfolded)
+ *               qjx,qjy,qjz,q of the last ipc>=1 call.  The scatter weights of
+ *               srimp1/srimp2 are a partition of unity (F:2296-2308), so
+ *               sums[3] = qmult * (particles of all ranks) up to rounding and
+ *               sums[0..2] = qmult * sum of the predicted velocities;
+ *   counts[0]   resident particles; counts[1] end slot of the last cell of
+ *               the cell index (= counts[0] when every particle is owned by a
+ *               cell); counts[2], counts[3] sum and sum of squares (mod 2^64)
+ *               of the slots' original local indices -- n(n-1)/2 and
+ *               (n-1)n(2n-1)/6 mod 2^64 while the slots hold a permutation,
+ *               i.e. no particle was lost or duplicated by the fused sort.    */
+int mrg_self_check(mrg_ctx* ctx, int32_t ksp, double sums[4], int64_t counts[4]);
+
+/* Measured fp64 FMA rate of this GPU (thread-level DFMA per second, 8
+ * independent chains per thread, all SMs): the denominator of the second
+ * roofline bench.py reports next to the HBM one.                             */
+int mrg_dfma_peak(mrg_ctx* ctx, double* dfma_per_s);
 
 /* Block the host until all work queued by this context has finished.        */
 int mrg_synchronize(mrg_ctx* ctx);

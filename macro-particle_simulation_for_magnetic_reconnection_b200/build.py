@@ -35,7 +35,7 @@ def _stale(target, sources):
 
 
 def cuda_sources():
-    srcs = [os.path.join(CSRC, f) for f in ("mrg_api.cu", "mrg_kernels.cuh", "mrg_tile.cuh", "mrg_pair.cuh", "mrg_lane.cuh", "mrg_quad.cuh", "mrg_device.cuh")]
+    srcs = [os.path.join(CSRC, f) for f in ("mrg_api.cu", "mrg_kernels.cuh", "mrg_tile.cuh", "mrg_device.cuh")]
     srcs.append(os.path.join(ROOT, "include", "mrg_fulmov.h"))
     return srcs
 

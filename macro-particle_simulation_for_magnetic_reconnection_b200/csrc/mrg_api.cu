@@ -5,9 +5,6 @@
 #include "../../include/mrg_fulmov.h"
 #include "mrg_kernels.cuh"
 #include "mrg_tile.cuh"
-#include "mrg_pair.cuh"
-#include "mrg_lane.cuh"
-#include "mrg_quad.cuh"
 
 #include <cuda.h>
 #include <dlfcn.h>
@@ -65,15 +62,6 @@ struct NcclApi {
 NcclApi g_nccl;
 constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 
-// warps per CTA of the pair kernels (shared-memory budget: see PredSmem / CorrSmem)
-#ifndef MRG_PRED_NW
-#define MRG_PRED_NW 6
-#endif
-#ifndef MRG_CORR_NW
-#define MRG_CORR_NW 4
-#endif
-constexpr int PRED_NW = MRG_PRED_NW, CORR_NW = MRG_CORR_NW;
-
 int nccl_load() {
   if (g_nccl.h) return MRG_OK;
   const char* names[] = {"libnccl.so.2", "libnccl.so"};
@@ -118,12 +106,11 @@ struct Species {
   bool prekeys_valid = false;
   bool fresh = false; double fresh_lookahead = 0.0;
   int* cell_end2 = nullptr;
-  int layout = 0;              // 0 = slots in cell order; 1 = 16-cell tiles stored as 16 interleaved runs (mrg_lane.cuh)
   // next-sort keys emitted by the corrector (fused_keys) + their histogram
   int* key = nullptr; long long key_cap = 0;
   int* hist = nullptr;
   bool keys_valid = false;
-  bool hist_valid = false;     // s.hist matches s.key (the pair corrector emits keys only)
+  bool hist_valid = false;     // s.hist matches s.key
   double keys_lookahead = 0.0;
   // z planes kp of the gather cells of the next pass (bit kp, kp = 0..mz), tracked by the tiled corrector and the
   // sort; valid for passes whose hdt equals zocc_lookahead.  Lets ensure_prep prepare only the planes in use.
@@ -208,7 +195,6 @@ struct mrg_ctx {
   cudaEvent_t ev_kernel = nullptr;
   double* wk_pinned = nullptr;      // [MRG_MAX_SPECIES][2] wkix/wkih landing zone of the deferred mode
   // options / counters
-  int lane_grid[3] = {148 * 8, 148 * 8, 148 * 8};   // persistent warps of k_lane<0>, k_lane<1>, k_lane_deposit (SMs x resident CTAs)
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
@@ -308,7 +294,6 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   if (s.id) { CK(cudaFree(s.id)); s.id = nullptr; }
   s.n = n;
   s.index_valid = false;
-  s.layout = 0;
   s.keys_valid = false;
   s.prekeys_valid = false;
   s.fresh = false;
@@ -693,20 +678,7 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   g.xhi_h = hi32(g.xhi); g.xlo_h = hi32(g.xlo); g.ymax_h = hi32(g.ymax); g.zhi_h = hi32(g.zhi); g.zlo_h = hi32(g.zlo);
   g.kz0 = 0; g.nkz = mz;
   c->ncell = (long long)mx * my * mz;
-  {
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    int nb[3] = {8, 8, 8};
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[0], k_lane<0>, 32, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[1], k_lane<1>, 32, 0));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb[2], k_lane_deposit, 32, 0));
-    for (int k = 0; k < 3; k++) c->lane_grid[k] = prop.multiProcessorCount * std::max(nb[k], 1);
-  }
   CK(cudaFuncSetAttribute(k_predict_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, PRED_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_predict_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, QPRED_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_correct_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, QCORR_SMEM_BYTES));
-  CK(cudaFuncSetAttribute(k_predict_pair<PRED_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PredSmem<PRED_NW>::bytes));
-  CK(cudaFuncSetAttribute(k_correct_pair<CORR_NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CorrSmem<CORR_NW>::bytes));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   {
     int lo = 0, hi = 0;
@@ -1017,33 +989,20 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     const int B = 128;
     if (s.n > 0) {
       const int iters = (c->opt_deposit == 2) ? c->opt_iters : 1;
-      const bool lane = c->opt_tile == 3 && s.index_valid && s.layout == 1;
-      const bool quad = c->opt_tile == 4 && s.index_valid && s.layout == 0;
-      const bool tiled = !lane && !quad && c->opt_tile && c->opt_tile < 3 && c->opt_deposit == 2 && s.index_valid && s.layout == 0;
-      const bool pair = tiled && c->opt_tile == 2;
+      const bool tiled = c->opt_tile == 1 && c->opt_deposit == 2 && s.index_valid;
       s.prekeys_valid = false;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
       GP gl = g;                               // tiled launches cover only the z planes of the order that own slots
       if (tiled && s.hull_valid) { gl.kz0 = s.kz0; gl.nkz = s.nkz; }
       if (tiled) blocks = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * gl.nkz;
-      if (lane) blocks = ((g.mx + LT_CELLS - 1) / LT_CELLS) * g.my * g.mz;
-      if (quad) blocks = ((g.mx + QT_CELLS - 1) / QT_CELLS) * g.my * g.mz;
-      const int nparts = pair ? blocks * PRED_NW : (tiled ? 1 : blocks);   // pair kernels: one partial per warp; tiled: two atomic accumulators
+      const int nparts = tiled ? 1 : blocks;   // tiled: two atomic accumulators
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
-      if (tiled && !pair) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
-      if (lane) { rc = ensure_alt(c, s.cap, false); if (rc) return rc; }
+      if (tiled) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
       CK(cudaEventRecord(c->ev0, c->stream));
       const int gm = c->opt_group_min * 4;   // option counts particles; a particle is a quad of lanes
-      if (quad) k_predict_quad<<<blocks, PR_WARPS * 32, QPRED_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.M4, s.cell_end, s.M4 + (size_t)g.ntot * 4, gm);
-      else if (lane) {   // split predictor: push into the spare SoA set, then deposit from it
-        Six Q; for (int k = 0; k < 6; k++) Q.p[k] = c->alt[k];
-        k_lane<1><<<std::min(blocks, c->lane_grid[1]), 32, 0, c->stream>>>(g, pp, P, Q, c->F6, s.cell_end, s.M4 + (size_t)g.ntot * 4, Slab{nullptr, nullptr, nullptr}, nullptr, 0.0, blocks); CKL(c);
-        k_lane_deposit<<<std::min(blocks, c->lane_grid[2]), 32, 0, c->stream>>>(g, qmult, Q, s.M4, s.cell_end, blocks);
-      }
-      else if (pair) k_predict_pair<PRED_NW><<<blocks, PRED_NW * 32, PredSmem<PRED_NW>::bytes, c->stream>>>(gl, pp, P, c->F6, s.M4, s.cell_end, c->wk_partial);
-      else if (tiled) {
+      if (tiled) {
         int* prekey = nullptr;
         if (c->opt_fused_sort) {   // keys + histogram of the next order; the corrector scatters by them
           rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
@@ -1067,7 +1026,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       else return fail(MRG_ERR_ARG, "option iters must be 4, 8, 16 or 32");
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
-      if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c); }   // k_lane / k_*_quad sum wkix/wkih themselves
+      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c);
     }
     // moment sum + fold; in deferred mode they run on the communication stream, so the next call's particle
     // kernel overlaps them and the host does not wait here
@@ -1117,7 +1076,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     if (pp.drive_on && !ranfb) return fail(MRG_ERR_ARG, "ranfb state pointer is required when the drive kick is on");
     {
       const bool want = c->opt_kick == 1 || (c->opt_kick < 0 && c->opt_shard == 1 && (c->nranks > 1 || c->opt_slab_n > 1));
-      const bool tile1 = c->opt_tile == 1 && s.index_valid && s.layout == 0;   // the kernel that can kick on its own
+      const bool tile1 = c->opt_tile == 1 && s.index_valid;   // the kernel that can kick on its own
       if (pp.drive_on && want && tile1 && s.n > 0) { pp.kick_inline = 1; pp.kick_state = (unsigned)*ranfb; }
     }
     if (pp.drive_on && !pp.kick_inline) {
@@ -1140,23 +1099,18 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     s.fresh = false;
     bool fused_scatter = false;
     if (s.n > 0) {
-      const bool lane = c->opt_tile == 3 && s.index_valid && s.layout == 1;
-      const bool quad = c->opt_tile == 4 && s.index_valid && s.layout == 0;
-      const bool tiled = !lane && !quad && c->opt_tile && c->opt_tile < 3 && s.index_valid && s.layout == 0;
-      const bool pair = tiled && c->opt_tile == 2;
-      const int B = lane ? 32 : (pair ? CORR_NW * 32 : ((tiled || quad) ? 128 : 256));
+      const bool tiled = c->opt_tile == 1 && s.index_valid;
+      const int B = tiled ? 128 : 256;
       GP gl = g;
       if (tiled && s.hull_valid) { gl.kz0 = s.kz0; gl.nkz = s.nkz; }
-      const int blocks = lane ? ((g.mx + LT_CELLS - 1) / LT_CELLS) * g.my * g.mz
-                              : quad ? ((g.mx + QT_CELLS - 1) / QT_CELLS) * g.my * g.mz
-                              : (tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * gl.nkz : grid_for(s.n, B));
-      const int nparts = pair ? blocks * CORR_NW : (tiled ? 1 : blocks);
+      const int blocks = tiled ? ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my * gl.nkz : grid_for(s.n, B);
+      const int nparts = tiled ? 1 : blocks;
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
-      if (tiled && !pair) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
+      if (tiled) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
       int* key_out = nullptr;
       // fused sort: the tiled predictor left the keys of the next order in s.key and their histogram in s.hist
-      const bool scatter = tiled && !pair && s.prekeys_valid && c->opt_fused_sort;
+      const bool scatter = tiled && s.prekeys_valid && c->opt_fused_sort;
       SortArrays D{};
       if (scatter) {   // cell starts of the next order; the kernel advances them to the ends
         rc = ensure_alt(c, s.cap, true);
@@ -1168,29 +1122,17 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         for (int k = 0; k < 6; k++) { D.src[k] = s.d[k]; D.dst[k] = c->alt[k]; }
         D.id_src = s.id; D.id_dst = c->alt_id;
       }
-      if ((tiled || lane || quad) && c->opt_fused_keys && !scatter) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
+      if (tiled && c->opt_fused_keys && !scatter) {   // emit next step's sort keys (cell of x + hdt*v); the old kernel also builds their histogram
         rc = ensure(c, (void**)&s.key, &s.key_cap, s.n + 2, sizeof(int));
         if (rc) return rc;
-        if (!pair && !lane && !quad) CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
+        CK(cudaMemsetAsync(s.hist, 0, (size_t)(c->ncell + 1) * sizeof(int), c->stream));
         key_out = s.key;
       }
       unsigned* zocc = nullptr;
-      if (tiled && !pair) { rc = zocc_begin(c, s, &zocc); if (rc) return rc; }
+      if (tiled) { rc = zocc_begin(c, s, &zocc); if (rc) return rc; }
       else s.zocc_valid = false;
       CK(cudaEventRecord(c->ev0, c->stream));
-      if (quad) {
-        Slab sl{c->slab_bits, c->slab_list, c->slab_count};
-        k_correct_quad<<<blocks, B, QCORR_SMEM_BYTES, c->stream>>>(g, pp, P, c->F6, s.cell_end, c->wk2, sl, key_out, p->hdt);
-        s.hist_valid = false;
-      } else if (lane) {
-        Slab sl{c->slab_bits, c->slab_list, c->slab_count};
-        k_lane<0><<<std::min(blocks, c->lane_grid[0]), 32, 0, c->stream>>>(g, pp, P, Six{}, c->F6, s.cell_end, c->wk2, sl, key_out, p->hdt, blocks);
-        s.hist_valid = false;
-      } else if (pair) {
-        Slab sl{c->slab_bits, c->slab_list, c->slab_count};
-        k_correct_pair<CORR_NW><<<blocks, B, CorrSmem<CORR_NW>::bytes, c->stream>>>(gl, pp, P, c->F6, s.cell_end, c->wk_partial, sl, key_out, p->hdt);
-        s.hist_valid = false;
-      } else if (tiled) {
+      if (tiled) {
         CUtensorMap tmP, tmId, tmKey;
         memset(&tmId, 0, sizeof(tmId));
         memset(&tmKey, 0, sizeof(tmKey));
@@ -1223,7 +1165,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         s.fresh_lookahead = p->hdt;
       }
       s.prekeys_valid = false;
-      if (!lane && !quad) { k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c); }
+      k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c);
     }
     double wk3[3] = {0.0, 0.0, 0.0};
     if (pp.kick_inline) {
@@ -1376,25 +1318,19 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
   }
   if (zocc) { rc = zocc_fetch(c, s, lookahead, false); if (rc) return rc; }   // completed by the synchronize below
   s.keys_valid = false;
-  const bool lane_layout = c->opt_tile == 3;
-  rc = scan_excl(c, s.hist, lane_layout ? c->cursor : s.cell_end, c->ncell + 1, nullptr);
+  rc = scan_excl(c, s.hist, s.cell_end, c->ncell + 1, nullptr);
   if (rc) return rc;
   s.kocc_pending = false;
-  if (!lane_layout) { rc = kocc_begin(c, s, s.cell_end); if (rc) return rc; }
+  rc = kocc_begin(c, s, s.cell_end);
+  if (rc) return rc;
   SortArrays A;
   for (int k = 0; k < 6; k++) { A.src[k] = s.d[k]; A.dst[k] = c->alt[k]; }
   A.id_src = s.id; A.id_dst = c->alt_id;
   // the scatter advances cell_end[c] from the start to the end slot of cell c
-  if (lane_layout) {   // c->cursor keeps the cell starts (tile base / size of the interleaved layout)
-    CK(cudaMemcpyAsync(s.cell_end, c->cursor, (size_t)(c->ncell + 1) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
-    k_sort_scatter_lane<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, c->g.mx, s.key, c->cursor, s.cell_end, A); CKL(c);
-  } else {
-    k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.cell_end, A); CKL(c);
-  }
+  k_sort_scatter<<<grid_for(s.n, B), B, 0, c->stream>>>(s.n, s.key, s.cell_end, A); CKL(c);
   CK(cudaStreamSynchronize(c->stream));
   kocc_finish(c, s);
   s.index_valid = true;
-  s.layout = lane_layout ? 1 : 0;
   // the spare buffer becomes the species' storage and vice versa
   for (int k = 0; k < 6; k++) std::swap(s.d[k], c->alt[k]);
   int* old_id = s.id;
@@ -1421,7 +1357,7 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value != 4 && value != 8 && value != 16 && value != 32) return fail(MRG_ERR_ARG, "iters must be 4, 8, 16 or 32");
     c->opt_iters = (int)value;
   } else if (n == "tile") {
-    if (value < 0 || value > 4) return fail(MRG_ERR_ARG, "tile must be 0..4");
+    if (value < 0 || value > 1) return fail(MRG_ERR_ARG, "tile must be 0 (gather through L1, any particle order) or 1 (TMA-staged tiles)");
     c->opt_tile = (int)value;
   } else if (n == "fused_keys") {
     c->opt_fused_keys = value != 0;
@@ -1511,6 +1447,67 @@ int mrg_pass_ms(mrg_ctx* c, int32_t ksp, int32_t ipc, double* ms) {
   float f = 0.f;
   CK(cudaEventElapsedTime(&f, e[0], e[1]));
   *ms = f;
+  return MRG_OK;
+}
+
+int mrg_self_check(mrg_ctx* c, int32_t ksp, double sums[4], int64_t counts[4]) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (!sums || !counts) return fail(MRG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  Species& s = c->sp[ksp - 1];
+  rc = complete_moments(c, ksp - 1);
+  if (rc) return rc;
+  double* d4 = nullptr;
+  CK(cudaMalloc((void**)&d4, 4 * sizeof(double) + 2 * sizeof(unsigned long long)));
+  CK(cudaMemsetAsync(d4, 0, 4 * sizeof(double) + 2 * sizeof(unsigned long long), c->stream));
+  unsigned long long* d2 = reinterpret_cast<unsigned long long*>(d4 + 4);
+  for (int k = 0; k < 4; k++) sums[k] = 0.0;
+  if (s.have_moments) { k_moment_sums<<<592, 256, 0, c->stream>>>(s.M4, c->g.ntot, d4); CKL(c); }
+  unsigned long long h2[2] = {0ull, 0ull};
+  if (s.id && s.n > 0) { k_id_sums<<<592, 256, 0, c->stream>>>(s.id, s.n, d2); CKL(c); }
+  int last = -1;
+  if (s.index_valid && s.cell_end) CK(cudaMemcpyAsync(&last, s.cell_end + (c->ncell - 1), sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(sums, d4, 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(h2, d2, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  CK(cudaFree(d4));
+  const unsigned long long n = (unsigned long long)s.n;
+  if (!s.id) {      // identity order
+    h2[0] = n ? n * (n - 1) / 2 : 0ull;
+    const unsigned __int128 t = n ? (unsigned __int128)(n - 1) * n * (2 * n - 1) / 6 : 0;
+    h2[1] = (unsigned long long)t;
+  }
+  counts[0] = s.n;
+  counts[1] = s.index_valid ? (int64_t)last : (int64_t)s.n;
+  counts[2] = (int64_t)h2[0];
+  counts[3] = (int64_t)h2[1];
+  return MRG_OK;
+}
+
+int mrg_dfma_peak(mrg_ctx* c, double* dfma_per_s) {
+  if (!c || !dfma_per_s) return fail(MRG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  const int blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; rep++) {
+    CK(cudaEventRecord(e0, c->stream));
+    k_dfma_peak<<<blocks, 256, 0, c->stream>>>(c->wk2, iters, 1.0000001, 1e-9); CKL(c);
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double rate = (double)blocks * 256.0 * 8.0 * iters / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  CK(cudaEventDestroy(e0));
+  CK(cudaEventDestroy(e1));
+  *dfma_per_s = best;
   return MRG_OK;
 }
 

@@ -557,6 +557,62 @@ __global__ void k_sort_scatter(long long n, const int* __restrict__ key, int* __
   A.id_dst[d] = A.id_src ? A.id_src[t] : (int)t;
 }
 
+// ---------------------------------------------------------------------------
+// Self-checks (mrg_self_check): sums of the raw moments over the extended grid
+// (srimp1/srimp2 weights are a partition of unity, F:2296-2308, so the raw q sums
+// to qmult * N exactly up to rounding), and sum / sum of squares (mod 2^64) of the
+// slots' original indices (a permutation of 0..n-1 after any number of sorts).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_moment_sums(const double* __restrict__ M4, long long ntot, double* __restrict__ out4) {
+  double a[4] = {0.0, 0.0, 0.0, 0.0};
+  const double2* m = reinterpret_cast<const double2*>(M4);
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < ntot; t += (long long)gridDim.x * blockDim.x) {
+    const double2 u = m[2 * t], v = m[2 * t + 1];
+    a[0] += u.x; a[1] += u.y; a[2] += v.x; a[3] += v.y;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const double w = warp_sum(a[c]);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out4 + c, w);
+  }
+}
+__global__ void __launch_bounds__(256) k_id_sums(const int* __restrict__ id, long long n, unsigned long long* __restrict__ out2) {
+  unsigned long long s1 = 0ull, s2 = 0ull;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+    const unsigned long long v = (unsigned long long)(unsigned)id[t];
+    s1 += v; s2 += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(out2, s1); atomicAdd(out2 + 1, s2); }
+}
+
+// Dependent-free DFMA stream for the second roofline (mrg_dfma_peak): 8 independent chains per thread.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* __restrict__ out, int iters, double a, double b) {
+  double v[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) v[q] = (double)(threadIdx.x + q);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int q = 0; q < 8; q++) v[q] = fma(v[q], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) s += v[q];
+  if (s == 123.456) out[0] = s;      // never true: keeps the chains alive
+}
+
+// histogram of existing sort keys (mrg_sort, when the keys came without one)
+__global__ void k_key_hist(long long n, const int* __restrict__ key, int* __restrict__ hist) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const bool valid = t < n;
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  if (!valid) return;
+  const int kcell = key[t];
+  const unsigned m = __match_any_sync(act, kcell);
+  if ((threadIdx.x & 31) == __ffs(m) - 1) atomicAdd(hist + kcell, __popc(m));
+}
+
 // out[id[slot]] = in[slot]  (download in original order)
 __global__ void k_unpermute(long long n, const int* __restrict__ id, const double* __restrict__ in, double* __restrict__ out) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;

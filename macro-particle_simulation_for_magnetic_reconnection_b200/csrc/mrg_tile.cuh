@@ -402,9 +402,6 @@ __device__ __forceinline__ Kick gather_rotate(const GP& g, const PushParams& pp,
 #ifndef MRG_CORR_NSTAGE
 #define MRG_CORR_NSTAGE 4
 #endif
-constexpr int NSTAGE = 3;          // ring depth of the experimental families (mrg_pair.cuh, mrg_quad.cuh)
-constexpr int STAGE_D = 34;        // their stage: 34 doubles per array (1-D bulk copies start on an even slot)
-constexpr int STAGE_BYTES = STAGE_D * 8;
 constexpr int TSTAGE_P = 6 * 32 * 8;              // particle box of a stage
 constexpr int TSTAGE_PIK = TSTAGE_P + 128 + 128;  // + ids + keys
 

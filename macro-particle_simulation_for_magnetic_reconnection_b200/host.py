@@ -206,6 +206,24 @@ class MrgContext:
     def synchronize(self):
         check(self.lib.mrg_synchronize(self.h))
 
+    def self_check(self, ksp):
+        """invariants of the resident state (mrg_self_check): raw moment sums, particle count, cell-index end,
+        and whether the slots still hold a permutation of the original indices"""
+        sums = (C.c_double * 4)()
+        cnt = (C.c_int64 * 4)()
+        check(self.lib.mrg_self_check(self.h, ksp, sums, cnt))
+        n = cnt[0]
+        m64 = (1 << 64) - 1
+        want1 = (n * (n - 1) // 2) & m64
+        want2 = ((n - 1) * n * (2 * n - 1) // 6) & m64 if n > 0 else 0
+        return {"sums": list(sums), "n": n, "cell_end_last": cnt[1],
+                "permutation_ok": (cnt[2] & m64) == want1 and ((cnt[3] & m64) == want2 or n <= 0)}
+
+    def dfma_peak(self):
+        v = C.c_double()
+        check(self.lib.mrg_dfma_peak(self.h, C.byref(v)))
+        return v.value
+
     def event_record(self, slot):
         check(self.lib.mrg_event_record(self.h, slot))
 

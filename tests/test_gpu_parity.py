@@ -68,7 +68,7 @@ def test_prepared_fields_bit_exact(mrg, case, ifil):
 
 # ---- C1: corrector ------------------------------------------------------------
 @pytest.mark.parametrize("ksp", [1, 2])
-@pytest.mark.parametrize("sort,tile", [(False, 2), (True, 2), (True, 1), (True, 0), (True, 3), ("adt", 3), (True, 4), ("adt", 4)])
+@pytest.mark.parametrize("sort,tile", [(False, 1), (True, 1), (True, 0), ("adt", 1)])
 def test_corrector_particles(mrg, case, ksp, sort, tile):
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
@@ -94,15 +94,11 @@ def test_corrector_particles(mrg, case, ksp, sort, tile):
 @pytest.mark.parametrize("ksp", [1, 2])
 @pytest.mark.parametrize("deposit,iters,sort,tile", [(0, 8, False, 0), (1, 8, False, 0), (1, 8, True, 0), (2, 4, True, 0),
                                                      (2, 8, True, 0), (2, 8, False, 0), (2, 32, True, 0),
-                                                     (2, 8, True, 1), (2, 8, "adt", 1), (2, 8, "stale", 1),
-                                                     (2, 8, True, 2), (2, 8, "adt", 2), (2, 8, "stale", 2),
-                                                     (2, 8, True, 3), (2, 8, "adt", 3), (2, 8, "stale", 3),
-                                                     (2, 8, True, 4), (2, 8, "adt", 4), (2, 8, "stale", 4)])
+                                                     (2, 8, True, 1), (2, 8, "adt", 1), (2, 8, "stale", 1)])
 def test_predictor_moments(mrg, case, ksp, deposit, iters, sort, tile):
     """sort: False = load order; True = sorted by the gather cell (x + hdt*v); "adt" = sorted by another
     key (many particles gather outside their tile); "stale" = sorted, then moved by a corrector step
-    without re-sorting.  tile=1 runs the TMA-staged shared-memory kernels, tile=2 the two-particles-per-thread
-    kernels, tile=3 the register-stationary lane-pair kernels on the interleaved tile layout."""
+    without re-sorting.  tile=1 runs the TMA-staged shared-memory kernels."""
     p, sp, ranfb, f12, a6 = case
     q, w = U.QSPEC[ksp], U.WSPEC[ksp]
     orig = [a.copy() for a in sp[ksp]]
@@ -187,9 +183,9 @@ def test_step_sequence(mrg, case):
 
 
 # ---- C4: seams, walls, cell boundaries ----------------------------------------------
-@pytest.mark.parametrize("tile", [None, 1, 3, 4])
+@pytest.mark.parametrize("tile", [None, 1])
 def test_edge_particles(mrg, case, tile):
-    """tile=None: load order (any-order kernels); 1 / 3: sorted, tiled / lane-pair kernels"""
+    """tile=None: load order (any-order kernels); 1: sorted, tiled kernels"""
     p, sp, ranfb, f12, a6 = case
     rng = np.random.default_rng(42)
     n = 4096
@@ -232,10 +228,10 @@ def test_edge_particles(mrg, case, tile):
         ctx.close()
 
 
-# ---- lane-pair kernels on a grid whose x size is not a multiple of the 16-cell tile --------------
-@pytest.mark.parametrize("tile", [3, 4])
-@pytest.mark.parametrize("mx,ppc", [(40, 7), (17, 33), (8, 70)])
-def test_lane_kernels_ragged_tiles(mrg, mx, ppc, tile):
+# ---- tiled kernels on grids whose x size is not a multiple of the 32-cell tile, thin and fat cells ---------
+@pytest.mark.parametrize("tile", [1])
+@pytest.mark.parametrize("mx,ppc", [(40, 7), (17, 33), (8, 70), (70, 3)])
+def test_tiled_kernels_ragged_tiles(mrg, mx, ppc, tile):
     p = U.make_parm(mx, 6, 8)
     sp, ranfb = U.load_species(p, ppc)
     f12 = U.smooth_fields(p, seed=11)
