@@ -443,9 +443,15 @@ def run_ours(args):
                        "wk_finite": all(np.isfinite(float(w[i].value if hasattr(w[i], "value") else w[i])) for w in state["wk"] for i in (0, 1))})
         if world == 1 and not args.no_check_direct:
             # the same predictor call through the simplest kernel of the library (one thread per particle, 72 red.global per
-            # particle, no tiles, no pre-reduction, no sort dependence) must give the same moments
-            tiled = {k: ctx.moments(k, folded=False) for k in (1, 2)}
-            ctx.set_option("tile", 0); ctx.set_option("deposit", 0); ctx.set_option("defer", 0)
+            # particle, no tiles, no pre-reduction, no sort dependence) must give the same moments as the tiled kernel: both run
+            # here, back to back, on the state the timed loop left behind
+            ctx.set_option("defer", 0)
+            ctx.bind_fields_device(fptr[0])
+            tiled = {}
+            for ksp in (1, 2):
+                ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"])
+                tiled[ksp] = ctx.moments(ksp, folded=False)
+            ctx.set_option("tile", 0); ctx.set_option("deposit", 0)
             worst = 0.0
             for ksp in (1, 2):
                 ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"])
@@ -454,6 +460,7 @@ def run_ours(args):
                     den = float(np.linalg.norm(direct[cidx]))
                     worst = max(worst, float(np.linalg.norm(tiled[ksp][cidx] - direct[cidx])) / (den if den > 0 else 1.0))
             ctx.set_option("tile", args.tile); ctx.set_option("deposit", args.deposit); ctx.set_option("defer", args.defer)
+            del tiled, direct
             parity["moments_tiled_vs_direct_rel_l2"] = worst
             parity["moments_ok"] = worst < 1e-10
         parity["ok"] = bool(parity["sum_q_ok"] and parity["particles_conserved"] and parity["wk_finite"] and parity.get("moments_ok", True))
