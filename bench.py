@@ -471,9 +471,27 @@ def run_ours(args):
     e2e = None
     host_ok = 0.0
     hsets = []
+    share = world > 1 and bool(args.share_moments)
+    lazy = world > 1 and bool(args.lazy_fields)
+    shm_keep = []
     if not args.no_e2e:
         def pinned(n):
             return torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+
+        def shared_pinned(name, n):
+            # one POSIX shared-memory array for all ranks of the node, page-locked in every process: COMMON /srimp7/ as the
+            # ranks of one node would share it (each rank delivers its own z block, option "sink_share")
+            path = "/dev/shm/mrg_bench_%s_%s" % (os.environ.get("MASTER_PORT", "0"), name)
+            if rank == 0:
+                with open(path, "wb") as f:
+                    f.truncate(n * 8)
+            dist.barrier()
+            t = torch.from_file(path, shared=True, size=n, dtype=torch.float64)
+            rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n * 8, 0)
+            if int(rc) != 0:
+                raise RuntimeError("cudaHostRegister failed: %r" % (rc,))
+            shm_keep.append((t, path))
+            return t.numpy()
         try:      # 32 page-locked grid arrays per rank (4.5 GB at 256^3): a host that cannot pin them loses this leg, not the line
             for fs in fsets:
                 hs = []
@@ -483,7 +501,7 @@ def run_ours(args):
                     hs.append(a)
                 hsets.append(hs)
             for name in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe"):
-                setattr(c, name, pinned(n_grid))
+                setattr(c, name, shared_pinned(name, n_grid) if share else pinned(n_grid))
         except (RuntimeError, MemoryError) as ex:
             host_ok = 1.0
             sys.stderr.write("bench: e2e leg skipped on rank %d: %r\n" % (rank, ex))
@@ -494,7 +512,7 @@ def run_ours(args):
     if not args.no_e2e and host_ok == 0.0:
         c.ranfb = state["ranfb"]
         fm = mrg.Fulmov(c, ipar=rank + 1, size=world, device=local, sort_interval=args.sort_every, ctx=ctx,
-                        hints=bool(args.hints), defer=bool(args.defer))
+                        hints=bool(args.hints), defer=bool(args.defer), lazy=lazy, share_moments=share)
         dummy = [np.zeros(1)] * 6
         npr = ntot_particles // 2
         FN = mrg.host.FIELD_NAMES
@@ -513,6 +531,8 @@ def run_ours(args):
             for ksp in (1, 2):
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 1, ksp)
             fm.finish_moments()
+            if share:
+                dist.barrier()          # every rank's block of the shared COMMON /srimp7/ arrays has landed (MPI_Barrier in a Fortran host)
             for i in (0, 1, 2):
                 setattr(c, FN[i], new[i])
             fm.fields_changed(fm.MASK_NEW)
@@ -539,11 +559,24 @@ def run_ours(args):
         te = float(tt[0])
         e2e = {"value": ntot_particles * ne / te, "unit": UNIT, "h2d_bytes_per_step": cnt_e["h2d_bytes"] // ne,
                "d2h_bytes_per_step": cnt_e["d2h_bytes"] // ne, "steps": ne, "ms_per_step": 1e3 * te / ne,
+               "pcie_gb_per_s_per_rank": (cnt_e["h2d_bytes"] + cnt_e["d2h_bytes"]) / te / 1e9,
+               "lazy_fields": lazy, "shared_moment_arrays": share,
                "note": "host fields in pinned memory -> mrg_set_fields (H2D), moments -> COMMON /srimp7/ arrays (D2H) every "
                        "step through the Fulmov mirror of the reference call; particles stay resident in HBM by design; "
+                       + ("each rank fetches only the z planes its field preparation reads (mrg_set_fields_lazy) and delivers only its "
+                          "own z block of the moments into host arrays shared by the ranks of the node (POSIX shm, option sink_share); "
+                          if (lazy or share) else "")
+                       +
                        + ("the host marks its field updates (prefld: bx..bz, emfild: ex..bz, renewal on the device)"
                           if args.hints else "no field hints: all of COMMON /fields/ is uploaded in both phases")}
         barrier()
+        for t, path in shm_keep:
+            torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+            if rank == 0:
+                try:
+                    os.unlink(path)
+                except OSError:
+                    pass
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -658,6 +691,8 @@ def main():
     ap.add_argument("--slab-of", type=int, nargs=2, default=None, metavar=("N", "I"),
                     help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
+    ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
+    ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -106,6 +106,23 @@ int mrg_set_fields_device(mrg_ctx* ctx, uint32_t mask,
  * solve that already owns ex..bz0 in HBM.                                   */
 int mrg_bind_fields_device(mrg_ctx* ctx, uint32_t mask,
                            const double* const f12_dev[12]);
+/* Lazy variant for HOST arrays: nothing is copied now.  The context keeps the
+ * pointers and, when a field preparation runs (F:1127-1148 inside the next
+ * mrg_fulmov / mrg_get_prepared_fields), fetches exactly the interior z planes
+ * that preparation reads and does not hold yet -- with option "planes" a rank
+ * that owns a z slab uploads its slab (+ filter halo) of the replicated
+ * COMMON /fields/ arrays instead of all of them.  The selected host arrays
+ * must stay valid and unchanged until the caller replaces them (another set /
+ * bind call for the same array) -- true for the reference, whose fields change
+ * only in prefld, emfild and the renewal loop.  With lazily held ex..bz the
+ * renewal must be mrg_renew_fields_host.                                     */
+int mrg_set_fields_lazy(mrg_ctx* ctx, uint32_t mask, const double* const f12[12]);
+/* mrg_renew_fields for lazily held fields: old6 = the host's ex0..bz0 arrays
+ * (which the host's own renewal loop has just filled with ex..bz); planes not
+ * yet on the device are later fetched from them.  old6 may be NULL when no
+ * field is held lazily.                                                      */
+int mrg_renew_fields_host(mrg_ctx* ctx, const double* const old6[6]);
+
 /* "Renewal: ex0 <- ex" of trans, F:796-807, on the device copies: after the
  * host has done that loop on its own arrays it calls this instead of
  * uploading ex0..bz0 again (they equal the ex..bz the device already has).  */
@@ -216,6 +233,14 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                mrg_fulmov(ipc >= 1) of the species, or mrg_synchronize (the
  *                pointers must stay valid until then).  0 (default) = every
  *                call completes before it returns
+ *   "sink_share" 1 = the host arrays given to mrg_set_moment_sink /
+ *                mrg_get_moments(folded = 1) are SHARED by the ranks of the
+ *                node (POSIX shared memory): every rank copies only its own
+ *                block of z planes (rank 0 and the last rank include the ghost
+ *                planes), the blocks tile each array exactly once, and the
+ *                caller synchronises the ranks (MPI_Barrier) before reading.
+ *                Removes the N-fold D2H of the replicated moments.  0 (default)
+ *                = every rank receives the whole arrays
  *   "iters"      particles per warp / 32 of the untiled predictor (4..32)
  *   "group_min"  smallest stray group (particles) that is pre-reduced        */
 int mrg_set_option(mrg_ctx* ctx, const char* name, int64_t value);

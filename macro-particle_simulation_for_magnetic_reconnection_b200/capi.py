@@ -22,7 +22,7 @@ SYMBOLS = [
     "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_sort", "mrg_set_option",
     "mrg_get_counters", "mrg_last_kernel_ms", "mrg_event_record", "mrg_event_elapsed_ms",
     "mrg_synchronize", "mrg_bind_fields_device", "mrg_renew_fields", "mrg_pass_ms", "mrg_get_prep_stats",
-    "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak",
+    "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak", "mrg_set_fields_lazy", "mrg_renew_fields_host",
 ]
 
 
@@ -79,6 +79,8 @@ def load(build_if_missing=True):
     L.mrg_set_fields_device.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
     L.mrg_bind_fields_device.argtypes = [vp, C.c_uint32, C.POINTER(vp)]
     L.mrg_renew_fields.argtypes = [vp]
+    L.mrg_set_fields_lazy.argtypes = [vp, C.c_uint32, C.POINTER(dp)]
+    L.mrg_renew_fields_host.argtypes = [vp, C.POINTER(dp)]
     L.mrg_compact_layout.argtypes = [i32, i32, i32, C.POINTER(C.c_uint8), C.POINTER(i32)]
     L.mrg_plane_sets.argtypes = [i32, C.POINTER(C.c_uint8), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
     L.mrg_set_moment_sink.argtypes = [vp, i32, dp, dp, dp, dp]

@@ -160,6 +160,11 @@ struct mrg_ctx {
   // fields
   double* f12[12] = {};
   const double* fcur[12] = {};   // what k_blend reads: f12[k], or the caller's device array after mrg_bind_fields_device
+  // lazily uploaded host fields (mrg_set_fields_lazy): the caller's host array and which interior z planes of it the
+  // device copy f12[k] already holds; ensure_prep fetches the planes a preparation reads and nothing else
+  const double* fhost[12] = {};
+  bool flazy[12] = {};
+  std::vector<char> fplane[12];
   double* A6[6] = {};
   double* T1[6] = {};
   double* T2[6] = {};
@@ -198,6 +203,7 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_sink_share = 0;   // deferred D2H of the folded moments copies only this rank's z block (ranks of a node share the host arrays)
   int opt_kick = -1;     // drive-kick draws: -1 = by particle index when "shard" = 1 (no reference stream exists), else the reference's serial order; 0 / 1 force
   int opt_compact = -1;  // slab-wise moment exchange instead of the whole-grid allreduce: -1 = when possible, 0 = never
   double* halo_rx[2] = {nullptr, nullptr};   // staging of the two neighbour halos of the slab-wise exchange
@@ -533,6 +539,19 @@ int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
   return MRG_OK;
 }
 
+// Option "sink_share": the ranks of a node share the host arrays the folded moments land in, so each rank copies only
+// its own block of extended z planes [e0, e1) -- rank 0 takes the two ghost planes below, the last rank the two above --
+// and the blocks tile the array exactly once.
+void sink_block(const mrg_ctx* c, size_t* off, size_t* cnt) {
+  const GP& g = c->g;
+  if (!c->opt_sink_share || c->nranks == 1) { *off = 0; *cnt = (size_t)g.ntot; return; }
+  const int N = c->nranks, r = c->rank;
+  const int k0 = (int)((long long)g.mz * r / N), k1 = (int)((long long)g.mz * (r + 1) / N);
+  const int e0 = (r == 0) ? 0 : k0 + 2, e1 = (r == N - 1) ? g.nz : k1 + 2;
+  *off = (size_t)e0 * g.nxy;
+  *cnt = (size_t)(e1 - e0) * g.nxy;
+}
+
 // F:1127-1148 on the device, cached on (fields version, aimpl, dc, ifil*).
 //
 // Restricted preparation: a particle whose gather cell lies on plane kp reads F6 on planes kp-1..kp+1 only
@@ -591,6 +610,21 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
     CK(cudaStreamSynchronize(c->stream));   // `all` is pageable and goes out of scope
     dB = c->plane_lists; dGI = c->plane_lists + (nz + 4); dG = c->plane_lists + 2 * (nz + 4);
     nB = (int)listB.size(); nGI = (int)listGI.size(); nG = (int)listG.size();
+  }
+  // lazily held host fields: fetch the interior planes the blend is about to read (F:1127-1139 reads k = 0..mz-1 only)
+  for (int a = 0; a < 12; a++) {
+    if (!c->flazy[a]) continue;
+    std::vector<char>& have = c->fplane[a];
+    auto need = [&](int k) { return restricted ? std::binary_search(listB.begin(), listB.end(), k) : true; };
+    for (int k = 0; k < mz;) {
+      if (have[k] || !need(k)) { k++; continue; }
+      int k1 = k;
+      while (k1 < mz && !have[k1] && need(k1)) { have[k1] = 1; k1++; }
+      const size_t off = (size_t)(k + 2) * g.nxy, cnt = (size_t)(k1 - k) * g.nxy;
+      CK(cudaMemcpyAsync(c->f12[a] + off, c->fhost[a] + off, cnt * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+      c->h2d += (long long)(cnt * sizeof(double));
+      k = k1;
+    }
   }
   const long long per = (long long)g.mx * (g.my + 1);
   CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->fcur[k];
@@ -920,6 +954,7 @@ static int set_fields_impl(mrg_ctx* c, uint32_t mask, const double* const f12[12
   for (int k = 0; k < 12; k++) {
     if (!((mask >> k) & 1u)) continue;
     if (!f12 || !f12[k]) return fail(MRG_ERR_ARG, "selected field pointer is null");
+    c->flazy[k] = false;
     if (kind == cudaMemcpyDefault) { c->fcur[k] = f12[k]; continue; }
     CK(cudaMemcpyAsync(c->f12[k], f12[k], gb, kind, c->stream));
     c->fcur[k] = c->f12[k];
@@ -939,20 +974,48 @@ int mrg_set_fields_device(mrg_ctx* c, uint32_t mask, const double* const f12[12]
 int mrg_bind_fields_device(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
   return set_fields_impl(c, mask, f12, cudaMemcpyDefault);
 }
+// Host fields held lazily: nothing is copied now; every preparation fetches the planes it reads (ensure_prep).
+int mrg_set_fields_lazy(mrg_ctx* c, uint32_t mask, const double* const f12[12]) {
+  if (!c) return fail(MRG_ERR_ARG, "null context");
+  if (mask >> 12) return fail(MRG_ERR_ARG, "mask has bits above 11");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < c->nspecies; k++)
+    if (c->sp[k].pending) CK(cudaStreamWaitEvent(c->stream, c->sp[k].done, 0));
+  for (int k = 0; k < 12; k++) {
+    if (!((mask >> k) & 1u)) continue;
+    if (!f12 || !f12[k]) return fail(MRG_ERR_ARG, "selected field pointer is null");
+    c->fhost[k] = f12[k];
+    c->flazy[k] = true;
+    c->fplane[k].assign(c->g.mz, 0);
+    c->fcur[k] = c->f12[k];
+  }
+  c->field_version++;
+  c->fields_set = true;
+  return MRG_OK;
+}
+
 // F:796-807 ("Renewal: ex0 <- ex") on the device copies of the fields.
-int mrg_renew_fields(mrg_ctx* c) {
+int mrg_renew_fields_host(mrg_ctx* c, const double* const old6[6]) {
   if (!c) return fail(MRG_ERR_ARG, "null context");
   if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
   CK(cudaSetDevice(c->device));
   const size_t gb = (size_t)c->g.ntot * sizeof(double);
   for (int k = 0; k < 6; k++) {
+    if (c->flazy[k] && !(old6 && old6[k]))
+      return fail(MRG_ERR_ARG, "lazily held fields need the host's ex0..bz0 arrays for the renewal (mrg_renew_fields_host)");
     CK(cudaMemcpyAsync(c->f12[k + 6], c->fcur[k], gb, cudaMemcpyDeviceToDevice, c->stream));
     c->fcur[k + 6] = c->f12[k + 6];
+    c->flazy[k + 6] = c->flazy[k];
+    if (c->flazy[k]) { c->fhost[k + 6] = old6[k]; c->fplane[k + 6] = c->fplane[k]; }   // same planes, same values (the host copied them too)
   }
   c->field_version++;
   return MRG_OK;
 }
-
+int mrg_renew_fields(mrg_ctx* c) {
+  if (c) for (int k = 0; k < 6; k++)
+    if (c->flazy[k]) return fail(MRG_ERR_STATE, "fields are held lazily: use mrg_renew_fields_host");
+  return mrg_renew_fields_host(c, nullptr);
+}
 int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc, const mrg_step_params* p,
                int32_t* ranfb, double* wkix, double* wkih) {
   int rc = check_species(c, ksp);
@@ -1054,10 +1117,12 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CK(cudaMemcpyAsync(c->wk_pinned + 2 * (ksp - 1), s.M4 + (size_t)g.ntot * 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, ms));
       s.sink_filled = false;
       if (s.sink[0] || s.sink[1] || s.sink[2] || s.sink[3]) {   // D2H of the moments overlaps the next particle kernel too
+        size_t off, cnt;
+        sink_block(c, &off, &cnt);
         for (int k = 0; k < 4; k++) {
           if (!s.sink[k]) continue;
-          CK(cudaMemcpyAsync(s.sink[k], s.out4[k], (size_t)g.ntot * sizeof(double), cudaMemcpyDeviceToHost, ms));
-          c->d2h += (long long)g.ntot * (long long)sizeof(double);
+          CK(cudaMemcpyAsync(s.sink[k] + off, s.out4[k] + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, ms));
+          c->d2h += (long long)(cnt * sizeof(double));
         }
         s.sink_filled = true;
       }
@@ -1236,12 +1301,15 @@ int mrg_get_moments(mrg_ctx* c, int32_t ksp, double* qjx, double* qjy, double* q
     k_fold_unpack<<<grid_for(c->g.ntot, 256), 256, 0, c->stream>>>(c->g, s.M4, o, 0); CKL(c);
     src = c->T2;
   }
+  size_t off = 0, cnt = (size_t)c->g.ntot;
+  if (folded) sink_block(c, &off, &cnt);      // shared host arrays: this rank's block only
   for (int k = 0; k < 4; k++) {
     if (!h[k]) continue;
     if (folded && s.sink_filled && h[k] == s.sink[k]) continue;   // already delivered by the deferred call
-    CK(cudaMemcpyAsync(h[k], src[k], gb, cudaMemcpyDeviceToHost, c->stream));
-    c->d2h += (long long)gb;
+    CK(cudaMemcpyAsync(h[k] + off, src[k] + off, cnt * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->d2h += (long long)(cnt * sizeof(double));
   }
+  (void)gb;
   CK(cudaStreamSynchronize(c->stream));
   return MRG_OK;
 }
@@ -1384,6 +1452,8 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value < -1 || value > 0) return fail(MRG_ERR_ARG, "compact must be -1 (slab-wise moment exchange when the ranks agree it is possible) or 0 (always allreduce)");
     c->opt_compact = (int)value;
     for (auto& sp : c->sp) sp.compact_ok = false;
+  } else if (n == "sink_share") {
+    c->opt_sink_share = value != 0;
   } else if (n == "defer") {
     if (!value) { for (int k = 0; k < c->nspecies; k++) { int rc = complete_moments(c, k); if (rc) return rc; } }
     c->opt_defer = value != 0;

@@ -21,6 +21,7 @@ struct HostState {
   bool auto_fields = true;
   unsigned dirty = 0xFFFu;     // members of COMMON /fields/ the device copy is stale for
   bool renew = false;          // ex0 <- ex still to be repeated on the device
+  bool it0 = false;            // the it = 0 pair of calls has been seen and emfld0 may have rewritten every field since
   int sort_interval = 1;
   bool exit_on_error = true;
   int status = 0;
@@ -75,7 +76,7 @@ int mrg_host_set_unique_id(const unsigned char id[128]) {
   return MRG_OK;
 }
 
-void fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz, double* qmult, double* wmult,
+void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz, double* qmult, double* wmult,
             int32_t* npr, int32_t* ipc, int32_t* ksp, int32_t* ipar, int32_t* size) {
   H.status = 0;
   if (!H.bound) { std::fprintf(stderr, "fulmov(gpu): mrg_host_bind was not called\n"); H.status = MRG_ERR_STATE; if (H.exit_on_error) std::exit(1); return; }
@@ -103,6 +104,12 @@ void fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz,
     H.resident[k - 1] = true;
   }
   if (H.auto_fields && k == 1) H.dirty = 0xFFFu;
+  // it = 0 (F:664-706): trans calls the pair with dt = 0, then emfld0 rewrites ALL of COMMON /fields/ on the host
+  // (F:691, 3384-3703) and the renewal loop runs -- none of which the three optional marks describe.  So the first
+  // call after the it = 0 pair uploads everything and drops the pending device renewal (it would copy the pre-emfld0
+  // ex..bz into ex0..bz0).
+  if (*v.it == 0) H.it0 = true;
+  else if (H.it0) { H.it0 = false; H.dirty = 0xFFFu; H.renew = false; }
   if (H.renew) {                                          // F:796-807 on the device copies
     rc = mrg_renew_fields(H.ctx);
     if (rc) return die("mrg_renew_fields", rc);

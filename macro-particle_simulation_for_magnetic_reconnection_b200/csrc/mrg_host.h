@@ -64,7 +64,7 @@ void mrg_host_set_exit_on_error(int32_t on);
 int mrg_host_status(void);
 
 /* The drop-in: same name and argument list as F:1044. */
-void fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz,
+void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, double* vz,
             double* qmult, double* wmult, int32_t* npr, int32_t* ipc, int32_t* ksp,
             int32_t* ipar, int32_t* size);
 

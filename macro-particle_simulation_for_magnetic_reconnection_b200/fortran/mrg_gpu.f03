@@ -54,7 +54,7 @@
 !
 !  The C++ drop-in with the argument list of F:1044 (all by reference).
         subroutine fulmov_gpu (x,y,z,vx,vy,vz,qmult,wmult,npr,ipc,ksp, &
-                               ipar,size) bind(C,name='fulmov')
+                               ipar,size) bind(C,name='mrg_host_fulmov')
           import :: C_DOUBLE, C_INT32_T
           real(C_DOUBLE) :: x(*),y(*),z(*),vx(*),vy(*),vz(*)
           real(C_DOUBLE) :: qmult,wmult

@@ -141,8 +141,16 @@ class MrgContext:
         arr = (C.c_void_p * 12)(*ptrs)
         check(self.lib.mrg_bind_fields_device(self.h, mask, arr))
 
-    def renew_fields(self):
-        check(self.lib.mrg_renew_fields(self.h))
+    def set_fields_lazy(self, f12, mask=0xFFF):
+        arr = (capi.dp * 12)(*[as_dp(a) for a in f12])
+        check(self.lib.mrg_set_fields_lazy(self.h, mask, arr))
+
+    def renew_fields(self, old6=None):
+        if old6 is None:
+            check(self.lib.mrg_renew_fields(self.h))
+        else:
+            arr = (capi.dp * 6)(*[as_dp(a) for a in old6])
+            check(self.lib.mrg_renew_fields_host(self.h, arr))
 
     def prepared_fields(self, params):
         out = [np.zeros(self.n_grid) for _ in range(6)]
@@ -258,7 +266,7 @@ class Fulmov:
     MASK_NEW, MASK_B, MASK_OLD, MASK_ALL = 0x03F, 0x038, 0xFC0, 0xFFF
 
     def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1, ctx=None, hints=False,
-                 defer=False):
+                 defer=False, lazy=False, share_moments=False):
         self.c = common
         self.ipar, self.size = ipar, size
         self.resident = {}
@@ -273,8 +281,14 @@ class Fulmov:
                     raise ValueError("size > 1 needs the NCCL unique id broadcast from rank 0")
                 self.ctx.comm_init(uid)
         self.hints = hints
+        # lazy: COMMON /fields/ is not uploaded when it changes; each field preparation fetches the planes it reads
+        # (a rank that owns a z slab then uploads its slab instead of the replicated arrays).  share_moments: the
+        # COMMON /srimp7/ arrays are shared by the ranks of the node and every rank delivers its own z block.
+        self.lazy = lazy
+        self.ctx.set_option("sink_share", 1 if share_moments else 0)
         self.dirty = self.MASK_ALL
         self.renew = False
+        self.it0 = False
         self.sort_interval = sort_interval
         self.ncorr = {1: 0, 2: 0}
         self.defer = defer
@@ -302,12 +316,19 @@ class Fulmov:
     def _push_fields(self, ksp):
         if not self.hints and ksp == 1:
             self.dirty = self.MASK_ALL
+        # it = 0 (F:664-706): after the dt = 0 pair, emfld0 rewrites all of COMMON /fields/ (F:691) and the renewal loop
+        # runs; the three optional marks do not describe that, so the first call afterwards uploads everything and drops
+        # the pending device renewal
+        if self.c.it == 0:
+            self.it0 = True
+        elif self.it0:
+            self.it0, self.dirty, self.renew = False, self.MASK_ALL, False
         if self.renew:
-            self.ctx.renew_fields()
+            self.ctx.renew_fields(self.c.fields()[6:] if self.lazy else None)
             self.renew = False
             self.dirty &= ~self.MASK_OLD
         if self.dirty:
-            self.ctx.set_fields(self.c.fields(), mask=self.dirty)
+            (self.ctx.set_fields_lazy if self.lazy else self.ctx.set_fields)(self.c.fields(), mask=self.dirty)
             self.dirty = 0
 
     def _record_wk(self, ksp, wkix, wkih):

@@ -38,7 +38,7 @@ def test_host_mirror_exports_reference_signature():
     import mrg_b200
     mrg_b200.build.build_host()
     lib = C.CDLL(mrg_b200.build.HOSTLIB)
-    for n in ("fulmov", "mrg_host_bind", "mrg_host_pull_particles", "mrg_host_particles_changed",
+    for n in ("mrg_host_fulmov", "mrg_host_bind", "mrg_host_pull_particles", "mrg_host_particles_changed",
               "mrg_host_fields_changed", "mrg_host_set_unique_id"):
         assert hasattr(lib, n), n
 

@@ -67,6 +67,45 @@ def test_python_fulmov_mirror(case):
         assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < PTOL
 
 
+def test_hints_survive_the_it0_sequence(case):
+    """at it = 0 trans calls the pair with dt = adt = hdt = 0, emfld0 then rewrites ALL of COMMON /fields/ and the
+    renewal loop runs (F:664-706) -- with only the three optional marks a mirror in hints mode would keep stale ex..bz and
+    copy them into ex0..bz0.  The mirrors treat the first call after the it = 0 pair as "everything changed"."""
+    import mrg_b200 as mrg
+    p, sp, ranfb, f_a, f_b = case
+    c = mrg.Common(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, dt=p.dt, aimpl=p.aimpl, wce_by_wpe=p.bxc, Ez00=p.Ez00)
+    c.ranfb, c.it = ranfb, 0
+    fm = mrg.Fulmov(c, ipar=1, size=1, hints=True)
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    npr = len(sp[1][0])
+    FN = mrg.host.FIELD_NAMES
+    for name, arr in zip(FN, f_a):
+        getattr(c, name)[:] = arr
+    dt, adt, hdt = c.dt, c.adt, c.hdt
+    c.dt = c.adt = c.hdt = 0.0                          # F:678-680
+    for k in (1, 2):
+        fm(*host[k], U.QSPEC[k], U.WSPEC[k], npr, 1, k)
+    c.dt, c.adt, c.hdt = dt, adt, hdt
+    for name, arr in zip(FN[:6], f_b[:6]):              # emfld0 (F:691): every field is new, no mark exists for it
+        getattr(c, name)[:] = arr
+    for i in range(6):                                  # renewal loop + its mark
+        getattr(c, FN[i + 6])[:] = getattr(c, FN[i])
+    fm.fields_renewed()
+    c.it = 1
+    f_c = U.smooth_fields(p, seed=23)
+    for i in (3, 4, 5):                                 # prefld + its mark
+        getattr(c, FN[i])[:] = f_c[i]
+    fm.fields_changed(fm.MASK_B)
+    a6 = O.field_prep(p, c.fields())
+    for k in (1, 2):
+        r = O.fulmov(p, a6, *[a.copy() for a in sp[k]], U.QSPEC[k], U.WSPEC[k], 1, nranks=1)
+        fm(*host[k], U.QSPEC[k], U.WSPEC[k], npr, 1, k)
+        got = (c.qix, c.qiy, c.qiz, c.qi) if k == 1 else (c.qex, c.qey, c.qez, c.qe)
+        for ci in range(4):
+            assert U.rel_l2(got[ci], r["mom"][ci]) < MTOL, (k, ci)
+    fm.ctx.close()
+
+
 _dp, _ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
 
 
@@ -89,8 +128,8 @@ def test_cpp_fulmov_mirror(case):
     mrg.build.build_host()
     lib = C.CDLL(mrg.build.HOSTLIB)
     dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
-    lib.fulmov.argtypes = [dp] * 8 + [ip] * 5
-    lib.fulmov.restype = None
+    lib.mrg_host_fulmov.argtypes = [dp] * 8 + [ip] * 5
+    lib.mrg_host_fulmov.restype = None
     lib.mrg_host_pull_particles.argtypes = [C.c_int32] + [dp] * 6 + [C.c_int32] * 3
     n = O.mxyzA(p)
     store = {}
@@ -126,7 +165,7 @@ def test_cpp_fulmov_mirror(case):
 
     def call(k, ipc):
         q, w = C.c_double(U.QSPEC[k]), C.c_double(U.WSPEC[k])
-        lib.fulmov(*[a.ctypes.data_as(dp) for a in host[k]], C.byref(q), C.byref(w), C.byref(npr),
+        lib.mrg_host_fulmov(*[a.ctypes.data_as(dp) for a in host[k]], C.byref(q), C.byref(w), C.byref(npr),
                    C.byref(C.c_int32(ipc)), C.byref(C.c_int32(k)), C.byref(one), C.byref(size))
         assert lib.mrg_host_status() == 0
 

@@ -246,3 +246,63 @@ def test_inline_drive_kick_by_particle_index(mrg):
     assert U.particle_err(got, ref, p.hx, U.vth(ksp)) < PTOL
     assert st == O.lcg_skip(ranfb, n)
     ctx.close()
+
+
+@pytest.mark.parametrize("planes", [0, 1])
+def test_lazy_host_fields_follow_the_trans_protocol(mrg, planes):
+    """mrg_set_fields_lazy + mrg_renew_fields_host through the Python mirror of fulmov, with the three field marks of trans
+    (prefld, emfild, renewal): a slab of particles steps three times; every result matches the oracle, which sees whole
+    arrays, and with restricted preparation the rank uploads well under the replicated arrays."""
+    p = U.make_parm(12, 10, 24)
+    sp_all, ranfb = U.load_species(p, 10)
+    sp = slab_subset(p, sp_all, 7.0, 12.0)
+    n = {k: len(sp[k][0]) for k in (1, 2)}
+    ref = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.array([ranfb], dtype=np.int32)
+    c = mrg.Common(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, dt=p.dt, aimpl=p.aimpl, wce_by_wpe=p.bxc, Ez00=p.Ez00)
+    c.ranfb, c.it = ranfb, 1
+    fm = mrg.Fulmov(c, ipar=1, size=1, hints=True, lazy=True)
+    fm.ctx.set_option("planes", planes)
+    FN = mrg.host.FIELD_NAMES
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    f_old = U.smooth_fields(p, seed=400, ghost_nan=False)
+    for name, a in zip(FN, f_old):
+        setattr(c, name, a.copy())
+    fm.ctx.counters(reset=True)
+    for step in range(3):
+        # prefld: new bx,by,bz (F:759)
+        f_b = U.smooth_fields(p, seed=410 + step, ghost_nan=False)
+        for i in (3, 4, 5):
+            setattr(c, FN[i], f_b[i].copy())
+        fm.fields_changed(fm.MASK_B)
+        a6 = O.field_prep(p, c.fields())
+        mom = {}
+        for k in (1, 2):
+            r = O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 1, nranks=1, ranfb=st)
+            fm(*host[k], U.QSPEC[k], U.WSPEC[k], n[k], 1, k)
+            got = (c.qix, c.qiy, c.qiz, c.qi) if k == 1 else (c.qex, c.qey, c.qez, c.qe)
+            for ci in range(4):
+                assert U.rel_l2(got[ci], r["mom"][ci]) < MTOL, (step, k, ci)
+        # emfild: new ex..bz (F:771)
+        f_n = U.smooth_fields(p, seed=420 + step, ghost_nan=False)
+        for i in range(6):
+            setattr(c, FN[i], f_n[i].copy())
+        fm.fields_changed(fm.MASK_NEW)
+        a6 = O.field_prep(p, c.fields())
+        for k in (1, 2):
+            O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 0, nranks=1, ranfb=st)
+            fm(*host[k], U.QSPEC[k], U.WSPEC[k], n[k], 0, k)
+        assert c.ranfb == int(st[0])
+        # renewal ex0 <- ex (F:796-807): the host copies, the mirror repeats it on the device
+        for i in range(6):
+            setattr(c, FN[i + 6], getattr(c, FN[i]).copy())
+        fm.fields_renewed()
+        c.it += 1
+    for k in (1, 2):
+        fm.pull(k, *host[k], n[k])
+        assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < 30 * PTOL, k
+    h2d = fm.ctx.counters()["h2d_bytes"]
+    full = 8 * O.mxyzA(p) * (12 + 3 * 9)              # eager protocol: 12 arrays once, then 9 per step
+    if planes:
+        assert h2d < 0.7 * full, (h2d, full)
+    fm.ctx.close()
