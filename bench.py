@@ -266,6 +266,128 @@ def workload_config(n, args):
             "cpu_sample": cpu_sample_text()}
 
 
+def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
+    """Small parity pass on ALL ranks of this job before the timed loop (so that a scaling record carries 2/4/8-rank
+    evidence): 16 x 12 x 16N grid, 8 ppc, two steps, both particle partitions.  Checker = the CPU oracle on rank 0
+    (pinned bit for bit to the reference's own fulmov, tests/test_ref_pin.py); it is not on any measured path.
+      roundrobin  the reference's partition and its serial per-rank kick streams: summed folded moments of step 1 and
+                  step 2 (step 2 sees the corrector and the kick of step 1) against the oracle run as N ranks;
+      slab        z-slab ownership, slab-wise exchange when the ranks agree: the same with the drive off (that
+                  ownership has no reference kick stream)."""
+    from oracle import pyoracle as O
+    mx, my, mz, ppc = 16, 12, 16 * world, 8
+    out = {}
+    for part in ("roundrobin", "slab"):
+        p = O.make_parm(mx, my, mz, HX * mx, HY * my, HZ * mz, DT, AIMPL, WCE, EZ00 if part == "roundrobin" else 0.0)
+        ctx = mrg.MrgContext(mx, my, mz, p.xmax, p.ymax, p.zmax, nspecies=2, rank=rank, nranks=world, device=local)
+        ctx.comm_init(mrg.broadcast_unique_id(rank, device=dev))
+        ctx.set_option("shard", 1 if part == "slab" else 0)
+        par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
+        st = 7331
+        for ksp in (1, 2):
+            _, st = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
+            ctx.sort(ksp, p.hdt)
+        if rank == 0:
+            sp = {}
+            for ksp in (1, 2):
+                sp[ksp], _, st_o = O.loadpt(p, ppc, vth(ksp), 0.0, VBEAM[ksp])
+            for cc in range(3):
+                sp[2][cc][:] = sp[1][cc]
+            nr = world if part == "roundrobin" else 1
+            sto = np.full(nr, st_o, dtype=np.int32)
+        # device loader: electrons share the ions' positions (ipleql, F:8657) by construction of the seeds
+        errs = []
+        for step in range(2):
+            fa = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 11 + 2 * step, dtype=np.float64)]
+            fb = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 12 + 2 * step, dtype=np.float64)]
+            ctx.set_fields(fa)
+            if rank == 0:
+                a6 = O.field_prep(p, fa)
+            for ksp in (1, 2):
+                ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, par, st)
+                mom = ctx.moments(ksp)
+                if rank == 0:
+                    r = O.fulmov(p, a6, *sp[ksp], QSPEC[ksp], WSPEC[ksp], 1, nranks=nr)
+                    errs.append(max(float(np.linalg.norm(mom[cc] - r["mom"][cc]) / np.linalg.norm(r["mom"][cc])) for cc in range(4)))
+            ctx.set_fields(fb)
+            if rank == 0:
+                a6 = O.field_prep(p, fb)
+            for ksp in (1, 2):
+                _, _, st = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, par, st)
+                ctx.sort(ksp, p.hdt)
+                if rank == 0:
+                    O.fulmov(p, a6, *sp[ksp], QSPEC[ksp], WSPEC[ksp], 0, nranks=nr, ranfb=sto)
+        stats = ctx.prep_stats()
+        rng_ok = True
+        if part == "roundrobin":          # every rank's ranfp state after the reference-order kicks
+            t = torch.tensor([float(st)], dtype=torch.float64, device=dev)
+            allst = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allst, t)
+            if rank == 0:
+                rng_ok = [int(v.item()) for v in allst] == [int(v) for v in sto]
+        ctx.close()
+        if rank == 0:
+            out[part] = {"moments_rel_l2_step1": max(errs[:2]), "moments_rel_l2_step2": max(errs[2:]),
+                         "ok": bool(max(errs) < 1e-10 and rng_ok), "ranks": world, "grid": [mx, my, mz], "ppc": ppc,
+                         "slabwise_sums": int(stats["compact_sums"]), "ranfp_states_equal_reference": bool(rng_ok) if part == "roundrobin" else None}
+        dist.barrier()
+    return out
+
+
+def measure_reference_partition(mrg, dist, torch, args, rank, world, local, dev, grid, params, steps=3, warmup=2):
+    """The same resident step on the REFERENCE's partition (round-robin ownership l = rank+1 mod N, F:1162; one whole-grid
+    ncclAllReduce per species; the reference's serial kick streams), timed like `value`: a short secondary leg so that every
+    N > 1 record carries the number for the reference decomposition next to the z-slab headline."""
+    mx, my, mz = grid
+    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, rank=rank, nranks=world, device=local)
+    ctx.comm_init(mrg.broadcast_unique_id(rank, device=dev))
+    for name in ("deposit", "iters", "group_min", "tile", "fused_keys", "fused_sort", "defer"):
+        ctx.set_option(name, getattr(args, name))
+    ctx.set_option("shard", 0)
+    ctx.set_option("compact", 0)
+    st = 7331
+    for ksp in (1, 2):
+        _, st = ctx.loadpt(ksp, args.ppc, vth(ksp), 0.0, VBEAM[ksp])
+    fsets = [[t.contiguous() for t in synth_fields(torch, mx, my, mz, seed, dtype=torch.float64, device=dev)] for seed in (1, 2)]
+    fptr = [[t.data_ptr() for t in fs] for fs in fsets]
+    for ksp in (1, 2):
+        ctx.sort(ksp, params.hdt)
+
+    def step():
+        nonlocal st
+        ctx.bind_fields_device(fptr[0])
+        for ksp in (1, 2):
+            if args.defer:
+                ctx.fulmov_deferred(ksp, QSPEC[ksp], WSPEC[ksp], params)
+            else:
+                ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, st)
+        ctx.bind_fields_device(fptr[1])
+        for ksp in (1, 2):
+            _, _, st = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, params, st)
+        for ksp in (1, 2):
+            ctx.sort(ksp, params.hdt)
+
+    for _ in range(warmup):
+        step()
+    ctx.synchronize(); torch.cuda.synchronize(); dist.barrier()
+    ctx.event_record(0)
+    for _ in range(steps):
+        step()
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1)
+    ctx.synchronize(); torch.cuda.synchronize(); dist.barrier()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    stats = ctx.prep_stats()
+    ctx.close()
+    del fsets
+    torch.cuda.empty_cache()
+    ms = float(t[0])
+    return {"value": 2.0 * mx * my * mz * args.ppc * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "warmup": warmup, "sharding": "round-robin l = rank+1 (mod N), whole-grid ncclAllReduce(fp64) per species, reference kick order",
+            "slabwise_sums": int(stats["compact_sums"])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -287,6 +409,12 @@ def run_ours(args):
     if args.slab_of:      # one GPU holds what one rank of an N-GPU job holds (no NCCL): development aid, not a bench line
         mx, my, mz = GRIDS[args.slab_of[0]]
     ppc = args.ppc
+    mrp = None
+    if world > 1 and not args.no_rank_parity:
+        try:
+            mrp = multi_rank_parity(mrg, dist, torch, rank, world, local, dev)
+        except Exception as ex:
+            mrp = {"error": repr(ex)}
     ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, rank=rank, nranks=world, device=local)
     if world > 1:
         uid = mrg.broadcast_unique_id(rank, device=dev)
@@ -585,19 +713,29 @@ def run_ours(args):
         except Exception as ex:                             # the oracle is a reported baseline only
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
+    prep_stats = ctx.prep_stats()
+    refpart = None
+    if world > 1 and args.shard == "slab" and not args.slab_of and not args.no_reference_partition:
+        ctx.close()
+        del fsets
+        torch.cuda.empty_cache()
+        try:
+            refpart = measure_reference_partition(mrg, dist, torch, args, rank, world, local, dev, (mx, my, mz), params)
+        except Exception as ex:
+            refpart = {"error": repr(ex)}
     if rank == 0:
         cfg = workload_config(args.gpus, args)
         cfg["parallelism"] = "particle-sharded x%d" % world
         if args.slab_of:
             cfg["emulated_rank"] = "slab %d of %d on one GPU, no NCCL sum (development aid, not a bench line)" % (args.slab_of[1], args.slab_of[0])
-        cfg["prep"] = ctx.prep_stats()
+        cfg["prep"] = prep_stats
         cfg["rank_sum"] = ("none (1 GPU)" if world == 1 else
                            "%d of %d moment sums went through the slab-wise exchange, the rest through ncclAllReduce"
                            % (cfg["prep"]["compact_sums"], 2 * (args.steps + args.warmup + (e2e["steps"] + 1 if e2e else 0))))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity,
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity, "multi_rank_parity": mrp, "reference_partition": refpart,
                 "wall_ms_per_step": 1e3 * wall / args.steps,
                 "pct_hbm_roofline_whole_step": None if world > 1 else 100.0 * roofline["whole_step"]["frac"]}
         print(json.dumps(line))
@@ -696,6 +834,8 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=4)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-reference-partition", action="store_true", help="skip the secondary round-robin leg of --gpus N > 1")
+    ap.add_argument("--no-rank-parity", action="store_true", help="skip the small all-rank parity pass of --gpus N > 1")
     ap.add_argument("--no-check-direct", action="store_true", help="skip the tiled-vs-direct moment cross-check of the parity object")
     ap.add_argument("--verify", action="store_true",
                     help="full-size parity: one predictor + one corrector pass per species at --grid/--ppc against the CPU oracle "

@@ -1,7 +1,6 @@
-"""2-GPU test of the NCCL moment sum (needs two devices: run with
-`gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).  Each
-rank is one process with one context; the library's own ncclAllReduce replaces
-mpi_allreduce (F:2379-2384, 2533, 1312-1315)."""
+"""Multi-GPU tests of the rank sum of the moments (2, 4 and 8 ranks; each case needs that many devices: run with
+`gpurun --gpus N -- python -m pytest tests/test_gpu_multi.py -m gpu`).  Each rank is one process with one context;
+the library's own ncclAllReduce replaces mpi_allreduce (F:2379-2384, 2533, 1312-1315)."""
 import os
 import socket
 
@@ -65,20 +64,28 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_two_gpu_nccl_moment_sum():
+def _spawn(worker, world, *extra):
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=worker, args=(r, world, port, q) + extra) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=600) for _ in range(2)]
+    res = [q.get(timeout=600) for _ in range(world)]
     for pr in procs:
         pr.join(timeout=120)
         assert pr.exitcode == 0
-    for rank, err, ok_rng in res:
+    return res
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_round_robin_ranks_nccl_moment_sum(world):
+    """the reference's own partition (l = rank+1 mod N) with the reference's serial per-rank kick streams: moments,
+    wkix/wkih, every owned particle and every rank's ranfp state against the oracle run as `world` ranks"""
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    for rank, err, ok_rng in _spawn(_worker, world):
         assert err < 1e-10 and ok_rng == 1, (rank, err, ok_rng)
 
 
@@ -94,7 +101,7 @@ def _worker_slab(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         uid = mrg.broadcast_unique_id(rank)
-        p = U.make_parm(12, 8, 48, Ez00=0.0)       # Ez00 = 0: the kick draws its random numbers but changes nothing,
+        p = U.make_parm(12, 8, max(48, 16 * world), Ez00=0.0)   # Ez00 = 0: the kick draws its random numbers but changes nothing,
         ppc = 8                                    # so the particles do not depend on which rank owns them (Q4)
         sp, ranfb = U.load_species(p, ppc)
         npr = len(sp[1][0])
@@ -145,18 +152,85 @@ def _worker_slab(rank, world, port, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.skipif(_ngpu() < 2, reason="needs 2 GPUs")
-def test_two_gpu_slab_deferred_restricted():
-    import torch.multiprocessing as mp
-    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    procs = [ctx.Process(target=_worker_slab, args=(r, 2, port, q)) for r in range(2)]
-    for pr in procs:
-        pr.start()
-    res = [q.get(timeout=600) for _ in range(2)]
-    for pr in procs:
-        pr.join(timeout=120)
-        assert pr.exitcode == 0
-    for rank, err, ok in res:
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_slab_ranks_deferred_restricted(world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    for rank, err, ok in _spawn(_worker_slab, world):
         assert err < 1e-10 and ok == 1, (rank, err, ok)
+
+
+def _worker_slab_kick(rank, world, port, q):
+    """z-slab ownership WITH the drive (Ez00 != 0): the kick draws by particle index (no reference stream exists for this
+    ownership), so the kicked set is not the oracle's -- but everything else must be: the summed moments before any kick,
+    every coordinate except vy of every particle, vy of the particles that were not kicked, the size of a kick
+    (Ez00 / bxa at the nearest node, F:1354) and the kick probability 0.001 per slab particle (F:1353)."""
+    import torch
+    import torch.distributed as dist
+    import mrg_b200 as mrg
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        uid = mrg.broadcast_unique_id(rank)
+        p = U.make_parm(16, 40, 16 * world)
+        p0 = U.make_parm(16, 40, 16 * world, Ez00=0.0)
+        ppc = 24
+        sp, ranfb = U.load_species(p, ppc)
+        ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, rank=rank, nranks=world, device=rank)
+        ctx.comm_init(uid)
+        ctx.set_option("shard", 1)
+        own = {}
+        for k in (1, 2):
+            ctx.loadpt(k, ppc, U.vth(k), 0.0, U.VBEAM[k])
+            zc = (sp[k][2] + 0.5 * p.hz) / p.zmax * world
+            own[k] = np.nonzero(np.clip(zc.astype(np.int64), 0, world - 1) == rank)[0]
+            ctx.sort(k, p.hdt)
+        par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
+        f12 = U.smooth_fields(p, seed=90)
+        a6 = O.field_prep(p, f12)
+        ctx.set_fields(f12)
+        errs, st = [], ranfb
+        ref = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+        for k in (1, 2):
+            r = O.fulmov(p, a6, *[a.copy() for a in sp[k]], U.QSPEC[k], U.WSPEC[k], 1, nranks=1)
+            ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 1, par, st)
+            mom = ctx.moments(k)
+            errs.append(max(U.rel_l2(mom[m], r["mom"][m]) for m in range(4)))
+        kicked = in_slab = 0
+        for k in (1, 2):
+            O.fulmov(p0, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 0, nranks=1)        # the same push without the kick
+            _, _, st = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 0, par, st)
+            got = ctx.download(k, len(own[k]))
+            want = [a[own[k]] for a in ref[k]]
+            for c in (0, 1, 2, 3, 5):
+                fl = p.hx if c < 3 else U.vth(k)
+                errs.append(float(np.max(np.abs(got[c] - want[c]) / np.maximum(np.abs(want[c]), fl))) * 1e2)
+            dvy = got[4] - want[4]
+            hit = np.abs(dvy) > 1e-12 * U.vth(k)
+            y, z = want[1], want[2]
+            slab = (np.abs(z - p.zcent) < 0.15 * p.zmax) & ((np.abs(y - p.ycent2) < 0.025 * p.ymax) | (np.abs(y - p.ycent1) < 0.025 * p.ymax))
+            assert not np.any(hit & ~slab)                                          # only slab particles are kicked
+            near2 = np.abs(y[hit] - p.ycent2) < 0.05 * p.ymax                        # vy -= vy0 near ycent2, += near ycent1
+            bx = np.where(near2, -1.0, 1.0) * p.Ez00 / dvy[hit]                       # = bxa at the nearest node
+            assert np.all((bx > 0.05) & (bx < 0.5)), bx                              # bxc = 0.2 +- the smooth modes
+            kicked += int(hit.sum())
+            in_slab += int(slab.sum())
+        ctx.close()
+        q.put((rank, max(errs), kicked, in_slab))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_ranks_drive_kick_statistics(world):
+    if _ngpu() < world:
+        pytest.skip("needs %d GPUs" % world)
+    res = _spawn(_worker_slab_kick, world)
+    kicked = sum(r[2] for r in res)
+    in_slab = sum(r[3] for r in res)
+    for rank, err, _, _ in res:
+        assert err < 1e-10, (rank, err)
+    mean = 0.001 * in_slab
+    assert in_slab > 20000 and abs(kicked - mean) < 5.0 * np.sqrt(mean) + 1, (kicked, in_slab)
