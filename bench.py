@@ -694,7 +694,6 @@ def run_ours(args):
                        + ("each rank fetches only the z planes its field preparation reads (mrg_set_fields_lazy) and delivers only its "
                           "own z block of the moments into host arrays shared by the ranks of the node (POSIX shm, option sink_share); "
                           if (lazy or share) else "")
-                       +
                        + ("the host marks its field updates (prefld: bx..bz, emfild: ex..bz, renewal on the device)"
                           if args.hints else "no field hints: all of COMMON /fields/ is uploaded in both phases")}
         barrier()

@@ -896,11 +896,11 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
   const long long npr = (long long)g.mx * g.my * g.mz * ppc;       // F:8937-8957
   const long long first = c->rank + 1, stride = c->nranks;         // F:219, F:1162
   long long n = owned_count(npr, first, stride);
-  if (n >= (1LL << 31) - 64) return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU");
   Species& s = c->sp[ksp - 1];
   const int nslab = c->opt_slab_n > 0 ? c->opt_slab_n : c->nranks;
   const int islab = c->opt_slab_n > 0 ? c->opt_slab_i : c->rank;
   const bool slab = c->opt_shard == 1 && nslab > 1;
+  if (!slab && n >= (1LL << 31) - 64) return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU");
   if (!slab) {
     rc = alloc_species(c, s, n);
     if (rc) return rc;
@@ -915,7 +915,9 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
   L.sa = (unsigned)*ranfa; L.sb = (unsigned)*ranfb;
   L.first = first; L.stride = stride;
   if (slab) {   // z-slab ownership: count, scan, fill (local order = increasing l)
-    if (npr >= (1LL << 31)) return fail(MRG_ERR_ARG, "slab loading needs npr < 2^31");
+    // npr itself may exceed 2^31 (BASELINE configs[3] at 8 GPUs: 3.36 G per species): the candidate index l0 and the LCG
+    // skip-ahead are 64-bit, the scanned block offsets count OWNED particles and stay below the per-GPU limit checked below
+    if ((npr + 255) / 256 >= (1LL << 31)) return fail(MRG_ERR_ARG, "slab loading needs npr < 2^39");
     const long long nb = (npr + 255) / 256;
     int* bc = nullptr;
     CK(cudaMalloc((void**)&bc, (size_t)(nb + 1) * sizeof(int)));
@@ -927,6 +929,7 @@ int mrg_loadpt(mrg_ctx* c, int32_t ksp, int32_t ppc, double vth, double vdr, dou
     CK(cudaMemcpyAsync(&total, bc + nb, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     n = total;
+    if (n < 0 || n >= (1LL << 31) - 64) { cudaFree(bc); return fail(MRG_ERR_ARG, "more than 2^31 particles of one species on one GPU"); }
     rc = alloc_species(c, s, n);
     if (rc) { cudaFree(bc); return rc; }
     if (n > 0) { k_loadpt_slab_fill<<<(unsigned)nb, 256, 0, c->stream>>>(g, L, soa(s), npr, nslab, islab, bc); CKL(c); }
