@@ -37,8 +37,27 @@ METRIC = "particle-pushes/sec incl. J/chi deposition"
 UNIT = "particle-pushes/s"
 
 
+SPECIES = (1, 2)      # ksp values of a step; --config 5 adds a heavy positive third species (qspec(4), wspec(4): F:1100)
+
+
 def vth(ksp):
-    return VETH / np.sqrt(1.0 * WSPEC[1]) if ksp == 1 else VETH       # F:8589-8594
+    return VETH / np.sqrt(1.0 * WSPEC[ksp]) if QSPEC[ksp] > 0 else VETH       # F:8589-8594 (te_by_ti = 1)
+
+
+def apply_config(args):
+    """BASELINE.json configs by number (1-based as in BASELINE.md): 2 = default (128^3 x 64 ppc per GPU, weak: 256^3 at 8);
+    4 = weak sweep 256x128x128 per GPU, 100 ppc; 5 = large-Dt run 512x256x256 (whole job), dt*wce > 10, heavy third species."""
+    global WCE, SPECIES
+    if args.config == 4:
+        args.grid = args.grid or [256, 128, 128 * max(args.gpus, 1)]
+        args.ppc = args.ppc or 100
+    elif args.config == 5:
+        args.grid = args.grid or [512, 256, 256]
+        args.ppc = args.ppc or 16
+        WCE = 9.0                                   # dt * wce = 10.8
+        QSPEC[3], WSPEC[3], VBEAM[3] = 1.0, 1600.0, 0.0
+        SPECIES = (1, 2, 3)
+    args.ppc = args.ppc or 64
 
 
 def synth_fields(xp, mx, my, mz, seed, **kw):
@@ -256,9 +275,10 @@ def workload_config(n, args):
                     "ncclAllReduce(fp64) of [qjx|qjy|qjz|q|wkix,wkih] per species per step (F:2379-2384, 2533, 1312-1315), "
                     "drive kick in the reference's serial per-rank ranfp order")
     return {"workload": "two-flux-bundle equilibrium (rec_3d80A / param_080A.h), %dx%dx%d grid, %d ppc/species, "
-                        "ions+electrons mi/me=100, dt=1.2, aimpl=0.6 (BASELINE configs[%s])"
-                        % (mx, my, mz, args.ppc, "1" if n == 1 else ("2" if n == 8 else "1 scaled")),
-            "grid": [mx, my, mz], "ppc": args.ppc, "species": 2, "particles_per_gpu": 2 * mx * my * mz * args.ppc // n,
+                        "ions+electrons mi/me=100%s, dt=1.2, aimpl=0.6, wce/wpe=%g (BASELINE configs[%s])"
+                        % (mx, my, mz, args.ppc, " + heavy ions q=+1 m=1600" if len(SPECIES) == 3 else "", WCE,
+                           {4: "3", 5: "4"}.get(getattr(args, "config", 2), "1" if n == 1 else ("2" if n == 8 else "1 scaled"))),
+            "grid": [mx, my, mz], "ppc": args.ppc, "species": len(SPECIES), "particles_per_gpu": len(SPECIES) * mx * my * mz * args.ppc // n,
             "sharding": sharding, "shard": args.shard if n > 1 else "none",
             "sort_every": args.sort_every, "sort_every_ions": args.sort_every_ions or args.sort_every, "deposit": args.deposit, "iters": args.iters, "tile": args.tile,
             "fused_keys": args.fused_keys, "fused_sort": args.fused_sort, "defer": args.defer, "planes": args.planes,
@@ -339,32 +359,32 @@ def measure_reference_partition(mrg, dist, torch, args, rank, world, local, dev,
     ncclAllReduce per species; the reference's serial kick streams), timed like `value`: a short secondary leg so that every
     N > 1 record carries the number for the reference decomposition next to the z-slab headline."""
     mx, my, mz = grid
-    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, rank=rank, nranks=world, device=local)
+    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=len(SPECIES), rank=rank, nranks=world, device=local)
     ctx.comm_init(mrg.broadcast_unique_id(rank, device=dev))
     for name in ("deposit", "iters", "group_min", "tile", "fused_keys", "fused_sort", "defer"):
         ctx.set_option(name, getattr(args, name))
     ctx.set_option("shard", 0)
     ctx.set_option("compact", 0)
     st = 7331
-    for ksp in (1, 2):
+    for ksp in SPECIES:
         _, st = ctx.loadpt(ksp, args.ppc, vth(ksp), 0.0, VBEAM[ksp])
     fsets = [[t.contiguous() for t in synth_fields(torch, mx, my, mz, seed, dtype=torch.float64, device=dev)] for seed in (1, 2)]
     fptr = [[t.data_ptr() for t in fs] for fs in fsets]
-    for ksp in (1, 2):
+    for ksp in SPECIES:
         ctx.sort(ksp, params.hdt)
 
     def step():
         nonlocal st
         ctx.bind_fields_device(fptr[0])
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             if args.defer:
                 ctx.fulmov_deferred(ksp, QSPEC[ksp], WSPEC[ksp], params)
             else:
                 ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, st)
         ctx.bind_fields_device(fptr[1])
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             _, _, st = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, params, st)
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             ctx.sort(ksp, params.hdt)
 
     for _ in range(warmup):
@@ -383,7 +403,7 @@ def measure_reference_partition(mrg, dist, torch, args, rank, world, local, dev,
     del fsets
     torch.cuda.empty_cache()
     ms = float(t[0])
-    return {"value": 2.0 * mx * my * mz * args.ppc * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+    return {"value": float(len(SPECIES)) * mx * my * mz * args.ppc * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
             "warmup": warmup, "sharding": "round-robin l = rank+1 (mod N), whole-grid ncclAllReduce(fp64) per species, reference kick order",
             "slabwise_sums": int(stats["compact_sums"])}
 
@@ -415,7 +435,7 @@ def run_ours(args):
             mrp = multi_rank_parity(mrg, dist, torch, rank, world, local, dev)
         except Exception as ex:
             mrp = {"error": repr(ex)}
-    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, rank=rank, nranks=world, device=local)
+    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=len(SPECIES), rank=rank, nranks=world, device=local)
     if world > 1:
         uid = mrg.broadcast_unique_id(rank, device=dev)
         ctx.comm_init(uid)
@@ -434,10 +454,10 @@ def run_ours(args):
     ctx.set_option("defer", args.defer)
     # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
     ranfb = 7331
-    for ksp in (1, 2):
+    for ksp in SPECIES:
         _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
-    nloc = ctx.num_local(1) + ctx.num_local(2)
-    ntot_particles = 2 * mx * my * mz * ppc if not args.slab_of else nloc
+    nloc = sum(ctx.num_local(k) for k in SPECIES)
+    ntot_particles = len(SPECIES) * mx * my * mz * ppc if not args.slab_of else nloc
     n_grid = ctx.n_grid
     c = mrg.Common(4, 4, 4, 1.0, 1.0, 1.0, dt=DT, aimpl=AIMPL, wce_by_wpe=WCE, Ez00=EZ00)   # scalars only
     c.mx, c.my, c.mz, c.xmax, c.ymax, c.zmax = mx, my, mz, HX * mx, HY * my, HZ * mz
@@ -449,7 +469,7 @@ def run_ours(args):
         f = synth_fields(torch, mx, my, mz, seed, dtype=torch.float64, device=dev)
         fsets.append([t.contiguous() for t in f])
     torch.cuda.synchronize()
-    for ksp in (1, 2):
+    for ksp in SPECIES:
         ctx.sort(ksp, c.hdt)          # sort key = cell of the gather position x + hdt*v
 
     state = {"ranfb": ranfb, "step": 0, "tp": [], "tc": []}
@@ -460,16 +480,16 @@ def run_ours(args):
         # the field arrays are resident in HBM (as a device-side emfild would leave them) and read in place
         ctx.bind_fields_device(fptr[0])
         wk = [ctx.fulmov_deferred(ksp, QSPEC[ksp], WSPEC[ksp], params) if args.defer
-              else ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"]) for ksp in (1, 2)]
+              else ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"]) for ksp in SPECIES]
         ctx.bind_fields_device(fptr[1])        # queued behind the moment sums: new fields need the moments
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             _, _, state["ranfb"] = ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 0, params, state["ranfb"])
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             state["tp"].append(ctx.pass_ms(ksp, 1))
             state["tc"].append(ctx.pass_ms(ksp, 0))
         state["wk"] = wk
         state["step"] += 1
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             every = args.sort_every_ions if (ksp == 1 and args.sort_every_ions) else args.sort_every
             if every and state["step"] % every == 0:
                 ctx.sort(ksp, c.hdt)
@@ -514,7 +534,7 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback 6650 (B200_PROFILING.md)"
-    n_sp = nloc / 2.0                                     # particles per launch (one species on this GPU)
+    n_sp = nloc / float(len(SPECIES))                     # particles per launch (one species on this GPU)
     bytes_pred = 48.0 * n_sp + (6 + 2 * 4) * 8.0 * n_grid
     bytes_corr = 96.0 * n_sp + 6 * 8.0 * n_grid
     tp, tc = float(np.mean(state["tp"])), float(np.mean(state["tc"]))
@@ -522,7 +542,7 @@ def run_ours(args):
     kn = {0: ("k_predict_run", "k_correct"), 1: ("k_predict_tile", "k_correct_tile")}[args.tile]
     dominant = kn[0] if tp >= tc else kn[1]
     ach = gb_pred if tp >= tc else gb_corr
-    step_bytes = 2 * (bytes_pred + bytes_corr)
+    step_bytes = len(SPECIES) * (bytes_pred + bytes_corr)
     traffic = None                                       # measured DRAM bytes per launch of the dominant kernel (one ncu capture)
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -560,9 +580,9 @@ def run_ours(args):
     parity = {"checked": True}
     try:
         worst_q, perm_ok, cells_ok = 0.0, True, True
-        for ksp in (1, 2):
+        for ksp in SPECIES:
             sc = ctx.self_check(ksp)
-            ntot_sp = ntot_particles // 2
+            ntot_sp = ntot_particles // len(SPECIES)
             parity["sum_q_raw_%d" % ksp] = sc["sums"][3]
             worst_q = max(worst_q, abs(sc["sums"][3] - QSPEC[ksp] * ntot_sp) / ntot_sp)
             perm_ok = perm_ok and sc["permutation_ok"]
@@ -576,12 +596,12 @@ def run_ours(args):
             ctx.set_option("defer", 0)
             ctx.bind_fields_device(fptr[0])
             tiled = {}
-            for ksp in (1, 2):
+            for ksp in SPECIES:
                 ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"])
                 tiled[ksp] = ctx.moments(ksp, folded=False)
             ctx.set_option("tile", 0); ctx.set_option("deposit", 0)
             worst = 0.0
-            for ksp in (1, 2):
+            for ksp in SPECIES:
                 ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, params, state["ranfb"])
                 direct = ctx.moments(ksp, folded=False)
                 for cidx in range(4):
@@ -640,9 +660,9 @@ def run_ours(args):
     if not args.no_e2e and host_ok == 0.0:
         c.ranfb = state["ranfb"]
         fm = mrg.Fulmov(c, ipar=rank + 1, size=world, device=local, sort_interval=args.sort_every, ctx=ctx,
-                        hints=bool(args.hints), defer=bool(args.defer), lazy=lazy, share_moments=share)
+                        hints=bool(args.hints), defer=bool(args.defer), lazy=lazy, share_moments=share, nspecies=len(SPECIES))
         dummy = [np.zeros(1)] * 6
-        npr = ntot_particles // 2
+        npr = ntot_particles // len(SPECIES)
         FN = mrg.host.FIELD_NAMES
         for name, arr in zip(FN, hsets[0]):
             setattr(c, name, arr)
@@ -656,7 +676,7 @@ def run_ours(args):
             for i in (3, 4, 5):
                 setattr(c, FN[i], new[i])
             fm.fields_changed(fm.MASK_B)
-            for ksp in (1, 2):
+            for ksp in SPECIES:
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 1, ksp)
             fm.finish_moments()
             if share:
@@ -664,7 +684,7 @@ def run_ours(args):
             for i in (0, 1, 2):
                 setattr(c, FN[i], new[i])
             fm.fields_changed(fm.MASK_NEW)
-            for ksp in (1, 2):
+            for ksp in SPECIES:
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 0, ksp)
             for i in range(6):
                 setattr(c, FN[i + 6], getattr(c, FN[i]))
@@ -732,7 +752,7 @@ def run_ours(args):
                            "%d of %d moment sums went through the slab-wise exchange, the rest through ncclAllReduce"
                            % (cfg["prep"]["compact_sums"], 2 * (args.steps + args.warmup + (e2e["steps"] + 1 if e2e else 0))))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config == 5 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity, "multi_rank_parity": mrp, "reference_partition": refpart,
                 "wall_ms_per_step": 1e3 * wall / args.steps,
@@ -754,25 +774,25 @@ def run_verify(args):
     ppc = args.ppc
     nthreads = min(len(os.sched_getaffinity(0)), 64)
     O.set_num_threads(nthreads)
-    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=2, device=0)
+    ctx = mrg.MrgContext(mx, my, mz, HX * mx, HY * my, HZ * mz, nspecies=len(SPECIES), device=0)
     for name in ("deposit", "iters", "group_min", "tile", "fused_keys", "fused_sort"):
         ctx.set_option(name, getattr(args, name))
     p = O.make_parm(mx, my, mz, HX * mx, HY * my, HZ * mz, DT, AIMPL, WCE, EZ00)
     par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
     ranfb = 7331
-    for ksp in (1, 2):
+    for ksp in SPECIES:
         _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
     fa = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 1, dtype=np.float64)]
     fb = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 2, dtype=np.float64)]
     rep = {"verify": True, "grid": [mx, my, mz], "ppc": ppc, "oracle_threads": nthreads, "species": {}}
     n = ctx.num_local(1)
     t00 = time.perf_counter()
-    for ksp in (1, 2):
+    for ksp in SPECIES:
         ctx.sort(ksp, p.hdt)
     st_o = np.array([ranfb], dtype=np.int32)
     st_g = ranfb
     worst_m = worst_p = 0.0
-    for ksp in (1, 2):           # one species at a time: 6 x n doubles on the host (6.4 GB at configs[1])
+    for ksp in SPECIES:           # one species at a time: 6 x n doubles on the host (6.4 GB at configs[1])
         host = ctx.download(ksp, n)
         ctx.set_fields(fa)
         a6 = O.field_prep(p, fa)
@@ -812,7 +832,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, nargs=3, default=None, help="override the grid (mx my mz)")
-    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--ppc", type=int, default=None, help="particles per cell per species (default 64; 100 / 16 for --config 4 / 5)")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE.md config number: 2 = 128^3 x 64 ppc per GPU (default), 4 = 256x128x128 per GPU x 100 ppc, "
+                         "5 = 512x256x256, three species, dt*wce > 10")
     ap.add_argument("--sort-every", type=int, default=1)
     ap.add_argument("--sort-every-ions", type=int, default=0, help="ion sort cadence (0 = same as --sort-every)")
     ap.add_argument("--deposit", type=int, default=2)
@@ -840,6 +863,7 @@ def main():
                     help="full-size parity: one predictor + one corrector pass per species at --grid/--ppc against the CPU oracle "
                          "(pinned bit for bit to the reference); prints a JSON report instead of a bench line")
     args = ap.parse_args()
+    apply_config(args)
     if args.gpus not in GRIDS and not args.grid:
         raise SystemExit("--gpus must be 1, 2, 4 or 8 (or give --grid)")
     if args.slab_of:

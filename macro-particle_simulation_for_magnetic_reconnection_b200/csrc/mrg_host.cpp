@@ -26,6 +26,8 @@ struct HostState {
   bool exit_on_error = true;
   int status = 0;
   bool have_id = false;
+  int nspecies = 2;            // the reference handles two (F:1321-1327); more only on request (qspec(4), wspec(4), F:1100)
+  double* extra[MRG_MAX_SPECIES][4] = {};   // moment arrays of species 3, 4 (the reference has none)
   unsigned char id[MRG_UNIQUE_ID_BYTES];
 } H;
 
@@ -61,6 +63,16 @@ void mrg_host_fields_renewed(void) {
   else H.renew = true;
 }
 void mrg_host_set_auto_fields(int32_t on) { H.auto_fields = on != 0; }
+int mrg_host_set_nspecies(int32_t n) {
+  if (n < 2 || n > MRG_MAX_SPECIES || H.ctx) return MRG_ERR_ARG;   // before the first fulmov call
+  H.nspecies = n;
+  return MRG_OK;
+}
+int mrg_host_bind_extra_moments(int32_t ksp, double* qjx, double* qjy, double* qjz, double* q) {
+  if (ksp < 3 || ksp > MRG_MAX_SPECIES) return MRG_ERR_ARG;
+  H.extra[ksp - 1][0] = qjx; H.extra[ksp - 1][1] = qjy; H.extra[ksp - 1][2] = qjz; H.extra[ksp - 1][3] = q;
+  return MRG_OK;
+}
 void mrg_host_set_sort_interval(int32_t n) { H.sort_interval = n < 0 ? 0 : n; }
 void mrg_host_set_exit_on_error(int32_t on) { H.exit_on_error = on != 0; }
 int mrg_host_status(void) { return H.status; }
@@ -82,15 +94,15 @@ void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, do
   if (!H.bound) { std::fprintf(stderr, "fulmov(gpu): mrg_host_bind was not called\n"); H.status = MRG_ERR_STATE; if (H.exit_on_error) std::exit(1); return; }
   const mrg_common_view& v = H.v;
   const int k = *ksp;
-  if (k < 1 || k > 2) {   // the reference handles exactly two species (F:1321-1327, 1377-1386)
-    std::fprintf(stderr, "fulmov(gpu): ksp must be 1 or 2\n");
+  if (k < 1 || k > H.nspecies) {   // the reference handles exactly two species (F:1321-1327, 1377-1386); see mrg_host_set_nspecies
+    std::fprintf(stderr, "fulmov(gpu): ksp must be 1..%d\n", H.nspecies);
     H.status = MRG_ERR_ARG;
     if (H.exit_on_error) std::exit(1);
     return;
   }
   int rc;
   if (!H.ctx) {
-    rc = mrg_create(&H.ctx, v.mx, v.my, v.mz, *v.xmax, *v.ymax, *v.zmax, 2, *ipar - 1, *size, H.device);
+    rc = mrg_create(&H.ctx, v.mx, v.my, v.mz, *v.xmax, *v.ymax, *v.zmax, H.nspecies, *ipar - 1, *size, H.device);
     if (rc) return die("mrg_create", rc);
     if (*size > 1) {
       if (!H.have_id) { std::fprintf(stderr, "fulmov(gpu): size > 1 needs mrg_host_set_unique_id\n"); H.status = MRG_ERR_STATE; if (H.exit_on_error) std::exit(1); return; }
@@ -133,7 +145,7 @@ void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, do
   if (rc) return die("mrg_fulmov", rc);
   *v.wkix = wkix;                                         // F:1316-1317
   *v.wkih = wkih;
-  if ((*v.it % *v.nha) == 0 && *v.io_pe == 1) {           // F:1320-1328
+  if ((*v.it % *v.nha) == 0 && *v.io_pe == 1 && k <= 2) {  // F:1320-1328
     const long row = *v.ldec - 1;
     const int col = (k == 1) ? 5 : 7;
     v.edec[row + 3000L * (col - 1)] = wkix;
@@ -141,7 +153,8 @@ void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, do
   }
   if (*ipc >= 1) {                                        // F:1377-1386
     rc = (k == 1) ? mrg_get_moments(H.ctx, 1, v.qix, v.qiy, v.qiz, v.qi, 1)
-                  : mrg_get_moments(H.ctx, 2, v.qex, v.qey, v.qez, v.qe, 1);
+       : (k == 2) ? mrg_get_moments(H.ctx, 2, v.qex, v.qey, v.qez, v.qe, 1)
+                  : mrg_get_moments(H.ctx, k, H.extra[k - 1][0], H.extra[k - 1][1], H.extra[k - 1][2], H.extra[k - 1][3], 1);
     if (rc) return die("mrg_get_moments", rc);
   } else {
     H.corrector_calls[k - 1]++;

@@ -49,6 +49,11 @@ void mrg_host_unbind(void);
  * always moves ions first after a field change, F:761-766, 782-787). */
 void mrg_host_fields_changed(void);
 void mrg_host_set_auto_fields(int32_t on);
+/* More than the reference's two species (qspec(4), wspec(4) exist, F:1100, but trans / fulmov / emfild handle ksp = 1|2
+ * only, F:1321-1327): allow ksp <= n (call before the first fulmov) and say where the moments of species 3, 4 go (the
+ * reference has no COMMON member for them; NULL = not delivered).  edec rows are written for ksp = 1, 2 only.          */
+int mrg_host_set_nspecies(int32_t n);
+int mrg_host_bind_extra_moments(int32_t ksp, double* qjx, double* qjy, double* qjz, double* q);
 /* Finer hints for a host that marks its three field updates in trans (turn
  * auto_fields off first): bit i of mask = member i of COMMON /fields/ changed
  * on the host (prefld F:759 -> 0x038 bx,by,bz; emfild F:771 -> 0x03F ex..bz);

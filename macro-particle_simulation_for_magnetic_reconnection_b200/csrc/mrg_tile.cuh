@@ -457,34 +457,34 @@ struct Stream {
   int a, b;         // this warp's particle slots [a, b); a is a multiple of 4 slots ...
   int lo;           // ... and slots below lo (only in the tile's first iteration) belong to the previous tile
   int nit;          // iterations
+  int issued;       // iterations whose copies have been issued
   unsigned char* ring;       // [NS][STAGE]
   unsigned ring_s, bar_s;    // the ring and its NS mbarriers as shared-window addresses
-  // issue cursor: iterations still to issue, slot coordinate and ring slot of the next one
-  int is_left, is_slot;
-  // read cursor: ring slot and mbarrier phase of the iteration being consumed, first slot coordinate of that iteration
-  int rd_slot;
+  // ring cursors of a ring whose depth is not a power of two (loop-carried; a power-of-two ring derives slot and
+  // phase from the iteration number with a mask and a shift, which is cheaper than carrying them)
+  int is_slot, rd_slot;
   unsigned rd_phase;
 };
 // the descriptors of a launch: particles always; ids / keys may be absent (nullptr)
 struct StreamMaps { const CUtensorMap* p; const CUtensorMap* id; const CUtensorMap* key; };
 
-// The cursors are loop-carried counters: the earlier form derived slot and phase from the iteration number with a
-// division by the ring depth in every issue, wait and read (IMAD.HI chains, ~95 of the predictor's 1053 instructions
-// per 32 particles went into stream bookkeeping).
+template <int NS> struct RingPow2 { static constexpr bool value = (NS & (NS - 1)) == 0; };
+
 template <int NS, int STAGE>
 __device__ __forceinline__ void stream_issue(const StreamMaps& M, Stream& st, int lane) {
-  if (st.is_left > 0) {                                        // warp-uniform
+  if (st.issued < st.nit) {                                    // warp-uniform
+    const int slot = RingPow2<NS>::value ? (st.issued & (NS - 1)) : st.is_slot;
     if (lane == 0) {
-      const unsigned dst = st.ring_s + st.is_slot * STAGE;
-      const unsigned bar = st.bar_s + st.is_slot * 8;
+      const int e = st.a + 32 * st.issued;
+      const unsigned dst = st.ring_s + slot * STAGE;
+      const unsigned bar = st.bar_s + slot * 8;
       mbar_expect_tx_s(bar, (unsigned)TSTAGE_P + (M.id ? 128u : 0u) + (M.key ? 128u : 0u));
-      const int e = st.a + 32 * (st.nit - st.is_left);
       tma_box_2d_s(dst, M.p, e, 0, bar);
       if (M.id) tma_box_1d_s(dst + TSTAGE_P, M.id, e, bar);
       if (M.key) tma_box_1d_s(dst + TSTAGE_P + 128, M.key, e, bar);
     }
-    st.is_left--;
-    st.is_slot = (st.is_slot + 1 == NS) ? 0 : st.is_slot + 1;
+    st.issued++;
+    if (!RingPow2<NS>::value) st.is_slot = (slot + 1 == NS) ? 0 : slot + 1;
   }
 }
 
@@ -499,11 +499,11 @@ __device__ __forceinline__ void stream_open(const StreamMaps& M, const Tile& t, 
   st.b = min(base + 32 * i1, t.p1);
   st.lo = t.p0;
   st.nit = i1 - i0;
+  st.issued = 0;
   st.ring = ring;
   st.ring_s = smem_u32(ring);
   st.bar_s = smem_u32(bar);
-  st.is_left = st.nit; st.is_slot = 0;
-  st.rd_slot = 0; st.rd_phase = 0u;
+  st.is_slot = 0; st.rd_slot = 0; st.rd_phase = 0u;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < NS; s++) mbar_init(bar + s, 1);
@@ -516,46 +516,51 @@ __device__ __forceinline__ void stream_open(const StreamMaps& M, const Tile& t, 
 // one particle's six phase-space coordinates
 struct P6 { double x, y, z, vx, vy, vz; };
 
-// wait for the stage of the iteration under the read cursor / of the one after it
+// ring slot / mbarrier phase of iteration `it` (it = the iteration under the read cursor, or the one after it)
 template <int NS>
-__device__ __forceinline__ void stream_wait(const Stream& st) {
-  mbar_wait_s(st.bar_s + st.rd_slot * 8, st.rd_phase);
+__device__ __forceinline__ int ring_slot(const Stream& st, int it, bool next) {
+  if (RingPow2<NS>::value) return (it + (next ? 1 : 0)) & (NS - 1);
+  return next ? ((st.rd_slot + 1 == NS) ? 0 : st.rd_slot + 1) : st.rd_slot;
 }
 template <int NS>
-__device__ __forceinline__ void stream_wait_next(const Stream& st) {
-  const bool wrap = st.rd_slot + 1 == NS;
-  mbar_wait_s(st.bar_s + (wrap ? 0 : st.rd_slot + 1) * 8, wrap ? (st.rd_phase ^ 1u) : st.rd_phase);
+__device__ __forceinline__ unsigned ring_phase(const Stream& st, int it, bool next) {
+  if (RingPow2<NS>::value) return (unsigned)(((it + (next ? 1 : 0)) / NS) & 1);
+  return (next && st.rd_slot + 1 == NS) ? (st.rd_phase ^ 1u) : st.rd_phase;
 }
-// move the read cursor to the next iteration
+template <int NS>
+__device__ __forceinline__ void stream_wait(const Stream& st, int it) {
+  mbar_wait_s(st.bar_s + ring_slot<NS>(st, it, false) * 8, ring_phase<NS>(st, it, false));
+}
+template <int NS>
+__device__ __forceinline__ void stream_wait_next(const Stream& st, int it) {
+  mbar_wait_s(st.bar_s + ring_slot<NS>(st, it, true) * 8, ring_phase<NS>(st, it, true));
+}
+// move the read cursor to the next iteration (a no-op for power-of-two rings)
 template <int NS>
 __device__ __forceinline__ void stream_advance(Stream& st) {
-  if (st.rd_slot + 1 == NS) { st.rd_slot = 0; st.rd_phase ^= 1u; }
-  else st.rd_slot++;
+  if (!RingPow2<NS>::value) {
+    if (st.rd_slot + 1 == NS) { st.rd_slot = 0; st.rd_phase ^= 1u; }
+    else st.rd_slot++;
+  }
 }
-// lane's particle of the iteration under the read cursor (whose stage has been waited for).  A lane outside [lo, b)
-// -- the first / last iteration of a slice may be partial -- reads the nearest particle of the slice instead (a
-// shared-memory broadcast): it then runs the same arithmetic on finite data and takes the same gather path as its
-// neighbour; its results are masked.
+// lane's particle of iteration `it` (whose stage has been waited for).  A lane outside [lo, b) -- the first / last
+// iteration of a slice may be partial -- reads the nearest particle of the slice instead (a shared-memory broadcast):
+// it then runs the same arithmetic on finite data and takes the same gather path as its neighbour; its results are masked.
 template <int NS, int STAGE>
 __device__ __forceinline__ void stream_read(const Stream& st, int it, int lane, P6& o) {
   const int first = st.a + 32 * it;
   const int le = min(max(first + lane, st.lo), st.b - 1) - first;
-  const double* src = reinterpret_cast<const double*>(st.ring + st.rd_slot * STAGE) + le;
+  const double* src = reinterpret_cast<const double*>(st.ring + ring_slot<NS>(st, it, false) * STAGE) + le;
   o.x = src[0]; o.y = src[32]; o.z = src[64];
   o.vx = src[96]; o.vy = src[128]; o.vz = src[160];
 }
 template <int NS, int STAGE>
-__device__ __forceinline__ int stream_read_id(const Stream& st, int lane) {
-  return reinterpret_cast<const int*>(st.ring + st.rd_slot * STAGE + TSTAGE_P)[lane];
+__device__ __forceinline__ int stream_read_id(const Stream& st, int it, int lane) {
+  return reinterpret_cast<const int*>(st.ring + ring_slot<NS>(st, it, false) * STAGE + TSTAGE_P)[lane];
 }
 template <int NS, int STAGE>
-__device__ __forceinline__ int stream_read_key(const Stream& st, int lane) {
-  return reinterpret_cast<const int*>(st.ring + st.rd_slot * STAGE + TSTAGE_P + 128)[lane];
-}
-template <int NS, int STAGE>
-__device__ __forceinline__ int stream_read_key_next(const Stream& st, int lane) {
-  const int ns = (st.rd_slot + 1 == NS) ? 0 : st.rd_slot + 1;
-  return reinterpret_cast<const int*>(st.ring + ns * STAGE + TSTAGE_P + 128)[lane];
+__device__ __forceinline__ int stream_read_key(const Stream& st, int it, int lane, bool next) {
+  return reinterpret_cast<const int*>(st.ring + ring_slot<NS>(st, it, next) * STAGE + TSTAGE_P + 128)[lane];
 }
 
 // per-warp partial sums of wkix/wkih (F:1282-1283) -> wk_partial[2*(block*nwarps + w)]
@@ -644,7 +649,7 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     for (int it = 0; it < st.nit; it++) {
       P6 c;
       stream_issue<PNS, TSTAGE_P>(maps, st, lane);           // refill the slot consumed in iteration it-1
-      stream_wait<PNS>(st);
+      stream_wait<PNS>(st, it);
       stream_read<PNS, TSTAGE_P>(st, it, lane, c);
       const int p = st.a + 32 * it + lane;
       const bool valid = p >= st.lo && p < st.b;
@@ -743,9 +748,9 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     const double hh2 = 0.5 * pp.hh;
     int cb = 0, crk = 0;         // claim of the current iteration: base (in the run's head lane), rank in the run
     int rlo = 0x7fffffff, rhi = -0x7fffffff;   // range of next-pass gather planes seen by this lane, relative to t.k
-    if (st.nit > 0) stream_wait<CNS>(st);                     // warp-uniform; a warp of a thin tile may have no iteration
+    if (st.nit > 0) stream_wait<CNS>(st, 0);                    // warp-uniform; a warp of a thin tile may have no iteration
     if (scatter && st.nit > 0) {
-      const int pk0 = stream_read_key<CNS, TSTAGE_PIK>(st, lane);
+      const int pk0 = stream_read_key<CNS, TSTAGE_PIK>(st, 0, lane, false);
       int cnt;
       bool head;
       crk = run_rank(pk0, st.a + lane >= st.lo && st.a + lane < st.b, lane, cnt, head);
@@ -759,12 +764,12 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
       const int p = st.a + 32 * it + lane;
       const bool valid = p >= st.lo && p < st.b;
       int kcell = -1;
-      const int idv = have_id ? stream_read_id<CNS, TSTAGE_PIK>(st, lane) : p;
+      const int idv = have_id ? stream_read_id<CNS, TSTAGE_PIK>(st, it, lane) : p;
       int nb = 0, nrk = 0;
       if (it + 1 < st.nit) {                                  // warp-uniform
-        stream_wait_next<CNS>(st);
+        stream_wait_next<CNS>(st, it);
         if (scatter) {                                        // claim the slots of iteration it + 1
-          const int pk1 = stream_read_key_next<CNS, TSTAGE_PIK>(st, lane);
+          const int pk1 = stream_read_key<CNS, TSTAGE_PIK>(st, it, lane, true);
           int cnt;
           bool head;
           nrk = run_rank(pk1, p + 32 < st.b, lane, cnt, head);

@@ -266,16 +266,18 @@ class Fulmov:
     MASK_NEW, MASK_B, MASK_OLD, MASK_ALL = 0x03F, 0x038, 0xFC0, 0xFFF
 
     def __init__(self, common, ipar=1, size=1, device=0, uid=None, sort_interval=1, ctx=None, hints=False,
-                 defer=False, lazy=False, share_moments=False):
+                 defer=False, lazy=False, share_moments=False, nspecies=2):
         self.c = common
         self.ipar, self.size = ipar, size
+        self.nspecies = nspecies      # the reference handles ksp = 1|2 (F:1321-1327); more only on request (qspec(4), F:1100)
+        self.extra = {}               # moment arrays of species 3, 4: the reference has no COMMON member for them
         self.resident = {}
         if ctx is not None:      # adopt a context whose particles are already resident (device loader)
             self.ctx = ctx
-            self.resident = {k: ctx.num_local(k) for k in (1, 2) if ctx.num_local(k) > 0}
+            self.resident = {k: ctx.num_local(k) for k in range(1, nspecies + 1) if ctx.num_local(k) > 0}
         else:
             self.ctx = MrgContext(common.mx, common.my, common.mz, common.xmax, common.ymax, common.zmax,
-                                  nspecies=2, rank=ipar - 1, nranks=size, device=device)
+                                  nspecies=nspecies, rank=ipar - 1, nranks=size, device=device)
             if size > 1:
                 if uid is None:
                     raise ValueError("size > 1 needs the NCCL unique id broadcast from rank 0")
@@ -290,7 +292,7 @@ class Fulmov:
         self.renew = False
         self.it0 = False
         self.sort_interval = sort_interval
-        self.ncorr = {1: 0, 2: 0}
+        self.ncorr = {k: 0 for k in range(1, 5)}
         self.defer = defer
         self.inflight = {}
         self.ctx.set_option("defer", 1 if defer else 0)
@@ -311,6 +313,10 @@ class Fulmov:
 
     def _moment_arrays(self, ksp):
         c = self.c
+        if ksp > 2:
+            if ksp not in self.extra:
+                self.extra[ksp] = [np.zeros(self.ctx.n_grid) for _ in range(4)]
+            return self.extra[ksp]
         return [c.qix, c.qiy, c.qiz, c.qi] if ksp == 1 else [c.qex, c.qey, c.qez, c.qe]
 
     def _push_fields(self, ksp):
@@ -334,7 +340,7 @@ class Fulmov:
     def _record_wk(self, ksp, wkix, wkih):
         c = self.c
         c.wkix, c.wkih = wkix, wkih
-        if c.it % c.nha == 0 and c.io_pe == 1:
+        if c.it % c.nha == 0 and c.io_pe == 1 and ksp <= 2:
             col = 5 if ksp == 1 else 7
             c.edec[col - 1, c.ldec - 1] = wkix
             c.edec[col, c.ldec - 1] = wkih
@@ -349,8 +355,8 @@ class Fulmov:
 
     def __call__(self, x, y, z, vx, vy, vz, qmult, wmult, npr, ipc, ksp):
         c = self.c
-        if ksp not in (1, 2):
-            raise ValueError("ksp must be 1 or 2 (F:1321-1327)")
+        if not 1 <= ksp <= self.nspecies:
+            raise ValueError("ksp must be 1 or 2 (F:1321-1327) unless the mirror was created with nspecies > 2")
         if not self.resident.get(ksp):
             self.ctx.upload(ksp, x[:npr], y[:npr], z[:npr], vx[:npr], vy[:npr], vz[:npr], self.ipar, self.size)
             self.resident[ksp] = npr
