@@ -452,6 +452,7 @@ def run_ours(args):
         ctx.set_option("slab_index", args.slab_of[1])
     ctx.set_option("planes", args.planes)
     ctx.set_option("defer", args.defer)
+    ctx.set_option("phases", 1)
     # synthetic two-flux-bundle load generated on the device (same values as loadpt, F:8937-9040)
     ranfb = 7331
     for ksp in SPECIES:
@@ -506,6 +507,7 @@ def run_ours(args):
         step_resident()
     state["tp"], state["tc"] = [], []
     ctx.counters(reset=True)
+    ctx.phase_ms(reset=True)
     barrier()
     ctx.event_record(0)
     t0 = time.perf_counter()
@@ -516,6 +518,17 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     barrier()
+    phases, _ = ctx.phase_ms(reset=True)
+    pt = torch.tensor([phases[k] / args.steps for k in ("prep", "setup", "kernel", "rank_sum", "fold", "kick")], dtype=torch.float64, device=dev)
+    if world > 1:
+        pmax = pt.clone(); dist.all_reduce(pmax, op=dist.ReduceOp.MAX)
+        pmin = pt.clone(); dist.all_reduce(pmin, op=dist.ReduceOp.MIN)
+    else:
+        pmax = pmin = pt
+    phases_rec = {"unit": "device ms per step (CUDA events on the stream each phase runs on; rank_sum and fold run on the second stream "
+                          "in deferred mode and overlap the next kernel, so the phases need not add up to ms_per_step)",
+                  "max_over_ranks": dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick"), [float(v) for v in pmax])),
+                  "min_over_ranks": dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick"), [float(v) for v in pmin]))}
     cnt = ctx.counters(reset=True)
     tms = torch.tensor([ms, float(cnt["launches"])], dtype=torch.float64, device=dev)
     if world > 1:
@@ -754,7 +767,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config == 5 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
-                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity, "multi_rank_parity": mrp, "reference_partition": refpart,
+                "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "parity": parity, "multi_rank_parity": mrp, "reference_partition": refpart, "phases": phases_rec,
                 "wall_ms_per_step": 1e3 * wall / args.steps,
                 "pct_hbm_roofline_whole_step": None if world > 1 else 100.0 * roofline["whole_step"]["frac"]}
         print(json.dumps(line))

@@ -288,6 +288,25 @@ int mrg_compact_layout(int32_t mz, int32_t nranks, int32_t rank,
 int mrg_event_record(mrg_ctx* ctx, int32_t slot);
 int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
 
+/* Device time of the phases of the mrg_fulmov calls since the last reset, in
+ * milliseconds, measured with CUDA events on the stream each phase runs on
+ * (option "phases" = 1 turns the recording on; it costs a few event records
+ * per call).  out[MRG_PH_PREP] field preparation (F:1127-1148, incl. lazy
+ * plane uploads), [MRG_PH_SETUP] memsets, histogram scans and other work
+ * around the particle kernel, [MRG_PH_KERNEL] the particle kernel,
+ * [MRG_PH_SUM] the rank sum of the moments / of wkix,wkih (NCCL), [MRG_PH_FOLD]
+ * vmesh fold + unpack, [MRG_PH_KICK] the serial-order drive kick chain.
+ * Phases on the two streams overlap in deferred mode, so the sum can exceed
+ * the step time; *calls = number of mrg_fulmov calls covered.                */
+#define MRG_PH_PREP 0
+#define MRG_PH_SETUP 1
+#define MRG_PH_KERNEL 2
+#define MRG_PH_SUM 3
+#define MRG_PH_FOLD 4
+#define MRG_PH_KICK 5
+#define MRG_NPHASE 6
+int mrg_phase_ms(mrg_ctx* ctx, double out[MRG_NPHASE], int64_t* calls, int32_t reset);
+
 /* Cheap invariants of the resident state, for callers that want to check a
  * run without a CPU reference (bench.py prints them with every line):
  *   sums[0..3]  sums over the extended grid of the RAW (rank-summed, unfolded)

@@ -210,11 +210,46 @@ struct mrg_ctx {
   int opt_slab_n = 0, opt_slab_i = 0;   // "slab_of"/"slab_index": mrg_loadpt loads slab i of n whatever nranks is (sizing aid)
   long long launches = 0, h2d = 0, d2h = 0;
   double last_kernel_ms = 0.0;
+  // per-phase device time of the mrg_fulmov calls (option "phases"): event pairs on the stream each phase runs on,
+  // read back lazily (a pair is read right before it is recorded again, and by mrg_phase_ms)
+  int opt_phases = 0;
+  cudaEvent_t ph_ev[MRG_MAX_SPECIES][2][MRG_NPHASE][2] = {};
+  bool ph_rec[MRG_MAX_SPECIES][2][MRG_NPHASE] = {};
+  double ph_ms[MRG_NPHASE] = {};
+  long long ph_calls = 0;
 };
 
 namespace {
 
 int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
+
+// ---- phase timers (option "phases") ------------------------------------------------------------
+int phase_collect(mrg_ctx* c, int k, int ipc, int ph) {
+  if (!c->ph_rec[k][ipc][ph]) return MRG_OK;
+  c->ph_rec[k][ipc][ph] = false;
+  CK(cudaEventSynchronize(c->ph_ev[k][ipc][ph][1]));
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ph_ev[k][ipc][ph][0], c->ph_ev[k][ipc][ph][1]));
+  c->ph_ms[ph] += ms;
+  return MRG_OK;
+}
+struct PhaseScope {      // records begin on construction, end on done(); no-op unless the option is on
+  mrg_ctx* c; int k, ipc, ph; cudaStream_t st; bool on;
+  PhaseScope(mrg_ctx* c_, int k_, int ipc_, int ph_, cudaStream_t st_) : c(c_), k(k_), ipc(ipc_ != 0), ph(ph_), st(st_), on(c_->opt_phases != 0) {
+    if (!on) return;
+    phase_collect(c, k, ipc, ph);
+    for (int e = 0; e < 2; e++)
+      if (!c->ph_ev[k][ipc][ph][e]) cudaEventCreate(&c->ph_ev[k][ipc][ph][e]);
+    cudaEventRecord(c->ph_ev[k][ipc][ph][0], st);
+  }
+  void done() {
+    if (!on) return;
+    cudaEventRecord(c->ph_ev[k][ipc][ph][1], st);
+    c->ph_rec[k][ipc][ph] = true;
+    on = false;
+  }
+  ~PhaseScope() { done(); }
+};
 
 // ---- TMA descriptors (cuTensorMapEncodeTiled through the runtime's driver entry point: no libcuda link) ----
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -780,6 +815,10 @@ int mrg_destroy(mrg_ctx* c) {
   for (int k = 0; k < MRG_MAX_SPECIES; k++)
     for (int q = 0; q < 4; q++) if (c->pass_ev[k][q >> 1][q & 1]) cudaEventDestroy(c->pass_ev[k][q >> 1][q & 1]);
   for (int k = 0; k < 8; k++) cudaEventDestroy(c->user_ev[k]);
+  for (int k = 0; k < MRG_MAX_SPECIES; k++)
+    for (int i = 0; i < 2; i++)
+      for (int ph = 0; ph < MRG_NPHASE; ph++)
+        for (int e = 0; e < 2; e++) if (c->ph_ev[k][i][ph][e]) cudaEventDestroy(c->ph_ev[k][i][ph][e]);
   cudaStreamDestroy(c->stream);
   delete c;
   return MRG_OK;
@@ -1033,8 +1072,12 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
   c->ev0 = c->pass_ev[ksp - 1][ipc != 0][0];
   c->ev1 = c->pass_ev[ksp - 1][ipc != 0][1];
   c->pass_timed[ksp - 1][ipc != 0] = false;
-  rc = ensure_prep(c, p, ksp);
-  if (rc) return rc;
+  if (c->opt_phases) c->ph_calls++;
+  {
+    PhaseScope ps(c, ksp - 1, ipc, MRG_PH_PREP, c->stream);
+    rc = ensure_prep(c, p, ksp);
+    if (rc) return rc;
+  }
   const GP& g = c->g;
   PushParams pp;
   pp.dt = p->dt; pp.adt = p->adt; pp.hdt = p->hdt; pp.aimpl = p->aimpl;
@@ -1050,6 +1093,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
   double wk_host[2] = {0.0, 0.0};
 
   if (ipc >= 1) {
+    PhaseScope ph_setup(c, ksp - 1, 1, MRG_PH_SETUP, c->stream);
     CK(cudaMemsetAsync(s.M4, 0, ((size_t)g.ntot * 4 + 2) * sizeof(double), c->stream));
     int blocks = 1;
     const int B = 128;
@@ -1066,6 +1110,8 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       rc = ensure(c, (void**)&c->wk_partial, &c->wk_partial_cap, 2LL * nparts, sizeof(double));
       if (rc) return rc;
       if (tiled) CK(cudaMemsetAsync(c->wk_partial, 0, 2 * sizeof(double), c->stream));
+      ph_setup.done();
+      PhaseScope ph_kernel(c, ksp - 1, 1, MRG_PH_KERNEL, c->stream);
       CK(cudaEventRecord(c->ev0, c->stream));
       const int gm = c->opt_group_min * 4;   // option counts particles; a particle is a quad of lanes
       if (tiled) {
@@ -1092,8 +1138,10 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       else return fail(MRG_ERR_ARG, "option iters must be 4, 8, 16 or 32");
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
+      ph_kernel.done();
       k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, s.M4 + (size_t)g.ntot * 4); CKL(c);
     }
+    ph_setup.done();
     // moment sum + fold; in deferred mode they run on the communication stream, so the next call's particle
     // kernel overlaps them and the host does not wait here
     cudaStream_t ms = c->stream;
@@ -1103,6 +1151,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       ms = c->cstream;
     }
     if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
+      PhaseScope ph_sum(c, ksp - 1, 1, MRG_PH_SUM, ms);
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
       if (s.compact_ok && compact_possible(c) && (s.n == 0 || (s.zocc_valid && s.zocc_lookahead == p->hdt))) {
         rc = compact_sum(c, s.M4, ms);
@@ -1114,7 +1163,10 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       }
     }
     Ptr4 o; for (int k = 0; k < 4; k++) o.p[k] = s.out4[k];
-    k_fold_unpack<<<grid_for(g.ntot, 256), 256, 0, ms>>>(g, s.M4, o, 1); CKL(c);   // F:2398, 2544
+    {
+      PhaseScope ph_fold(c, ksp - 1, 1, MRG_PH_FOLD, ms);
+      k_fold_unpack<<<grid_for(g.ntot, 256), 256, 0, ms>>>(g, s.M4, o, 1); CKL(c);   // F:2398, 2544
+    }
     s.have_moments = true;
     if (c->opt_defer) {
       CK(cudaMemcpyAsync(c->wk_pinned + 2 * (ksp - 1), s.M4 + (size_t)g.ntot * 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, ms));
@@ -1162,6 +1214,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CK(cudaMemsetAsync(c->slab_bits, 0, (size_t)nwords * sizeof(unsigned), c->stream));
       CK(cudaMemsetAsync(c->slab_count, 0, sizeof(int), c->stream));
     }
+    PhaseScope ph_setup(c, ksp - 1, 0, MRG_PH_SETUP, c->stream);
     CK(cudaMemsetAsync(c->wk2, 0, 3 * sizeof(double), c->stream));
     s.keys_valid = false;
     s.fresh = false;
@@ -1199,6 +1252,8 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       unsigned* zocc = nullptr;
       if (tiled) { rc = zocc_begin(c, s, &zocc); if (rc) return rc; }
       else s.zocc_valid = false;
+      ph_setup.done();
+      PhaseScope ph_kernel(c, ksp - 1, 0, MRG_PH_KERNEL, c->stream);
       CK(cudaEventRecord(c->ev0, c->stream));
       if (tiled) {
         CUtensorMap tmP, tmId, tmKey;
@@ -1219,6 +1274,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       }
       CKL(c);
       CK(cudaEventRecord(c->ev1, c->stream));
+      ph_kernel.done();
       if (zocc) { rc = zocc_fetch(c, s, p->hdt, true); if (rc) return rc; }   // completed by the synchronize below
       if (key_out) { s.keys_valid = true; s.keys_lookahead = p->hdt; }
       if (fused_scatter) {   // the spare buffers now hold the updated particles in the next order
@@ -1235,7 +1291,9 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       s.prekeys_valid = false;
       k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c);
     }
+    ph_setup.done();
     double wk3[3] = {0.0, 0.0, 0.0};
+    PhaseScope ph_kick(c, ksp - 1, 0, MRG_PH_KICK, c->stream);
     if (pp.kick_inline) {
       *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)s.n);   // every particle owns one draw of the call
     } else if (pp.drive_on && s.n > 0) {
@@ -1252,6 +1310,8 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)slab_n);
       }
     }
+    ph_kick.done();
+    PhaseScope ph_sum(c, ksp - 1, 0, MRG_PH_SUM, c->stream);
     if (c->nranks > 1) {                                           // F:1312-1315
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
       // third word: this rank's vote on exchanging slabs instead of allreducing the grid in the next ipc>=1 call of
@@ -1455,6 +1515,8 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value < -1 || value > 0) return fail(MRG_ERR_ARG, "compact must be -1 (slab-wise moment exchange when the ranks agree it is possible) or 0 (always allreduce)");
     c->opt_compact = (int)value;
     for (auto& sp : c->sp) sp.compact_ok = false;
+  } else if (n == "phases") {
+    c->opt_phases = value != 0;
   } else if (n == "sink_share") {
     c->opt_sink_share = value != 0;
   } else if (n == "defer") {
@@ -1581,6 +1643,18 @@ int mrg_dfma_peak(mrg_ctx* c, double* dfma_per_s) {
   CK(cudaEventDestroy(e0));
   CK(cudaEventDestroy(e1));
   *dfma_per_s = best;
+  return MRG_OK;
+}
+
+int mrg_phase_ms(mrg_ctx* c, double out[MRG_NPHASE], int64_t* calls, int32_t reset) {
+  if (!c || !out) return fail(MRG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < MRG_MAX_SPECIES; k++)
+    for (int i = 0; i < 2; i++)
+      for (int ph = 0; ph < MRG_NPHASE; ph++) { int rc = phase_collect(c, k, i, ph); if (rc) return rc; }
+  for (int ph = 0; ph < MRG_NPHASE; ph++) out[ph] = c->ph_ms[ph];
+  if (calls) *calls = c->ph_calls;
+  if (reset) { for (int ph = 0; ph < MRG_NPHASE; ph++) c->ph_ms[ph] = 0.0; c->ph_calls = 0; }
   return MRG_OK;
 }
 

@@ -97,6 +97,10 @@ struct Target {
   }
 };
 
+#ifndef MRG_DEPOSIT_UNROLL
+#define MRG_DEPOSIT_UNROLL 2
+#endif
+constexpr int DEPOSIT_UNROLL = MRG_DEPOSIT_UNROLL;   // unroll of the four sub-iterations of deposit_parked
 constexpr int PR_WARPS = 4;        // warps per block
 constexpr int PR_W_STRIDE = 10;    // doubles per particle in the W slab: wxz[9] + key
 // Q slab: four rows (one per lane role q) of 32 double2.  Rows are 34 double2 apart: in the phase-B read the 8 lanes
@@ -153,7 +157,7 @@ __device__ __forceinline__ void deposit_parked(const double2* Wq, const double2*
                                                int group_min, const Target<TILED>& tg) {
   const int q = lane & 3;
   unsigned bad = __ballot_sync(FULL, own_key >= 0 && own_key != cur);   // bit p: particle p does not continue the current cell
-#pragma unroll 1
+#pragma unroll DEPOSIT_UNROLL
   for (int sub = 0; sub < 4; sub++, Wq += 8 * PR_W_STRIDE / 2, Qq += 8, bad >>= 8) {
     const double2 w01 = Wq[0], w23 = Wq[1], w45 = Wq[2], w67 = Wq[3], w8k = Wq[4];
     const double2 qv = Qq[0];

@@ -227,6 +227,13 @@ class MrgContext:
         return {"sums": list(sums), "n": n, "cell_end_last": cnt[1],
                 "permutation_ok": (cnt[2] & m64) == want1 and ((cnt[3] & m64) == want2 or n <= 0)}
 
+    def phase_ms(self, reset=False):
+        """device milliseconds per phase of the mrg_fulmov calls since the last reset (option "phases" must be 1)"""
+        out = (C.c_double * 6)()
+        calls = C.c_int64()
+        check(self.lib.mrg_phase_ms(self.h, out, C.byref(calls), 1 if reset else 0))
+        return dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick"), out)), calls.value
+
     def dfma_peak(self):
         v = C.c_double()
         check(self.lib.mrg_dfma_peak(self.h, C.byref(v)))
