@@ -477,3 +477,54 @@ def test_abi_errors(mrg, case):
     ctx.fulmov(1, 1.0, 100.0, 1, params_of(mrg, p))
     assert all(np.all(m == 0) for m in ctx.moments(1))
     ctx.close()
+
+
+# ---- BASELINE configs[4]: three species, dt * wce > 10 ------------------------------------------------
+def test_three_species_large_dt(mrg):
+    """a heavy positive third species (q = +1, m = 1600; qspec(4), wspec(4) exist in the reference, F:1100, although trans
+    only calls fulmov for two) next to ions and electrons, with wce/wpe = 9 so that dt * wce = 10.8 (ht * |B| ~ 5 for the
+    electrons): two full steps through the C ABI and through the Python mirror with nspecies = 3, against the oracle (which
+    is pinned to the reference in this regime by tests/test_ref_pin.py::test_large_dt_heavy_species_bit_identical)"""
+    p = O.make_parm(24, 10, 12, U.HX * 24, U.HY * 10, U.HZ * 12, 1.2, 0.6, 9.0, 0.25e-2)
+    Q = {1: 1.0, 2: -1.0, 3: 1.0}
+    W = {1: 100.0, 2: 1.0, 3: 1600.0}
+    sp, ranfb = U.load_species(p, 12)
+    arrs3, _, _ = O.loadpt(p, 12, U.VETH / np.sqrt(W[3]), 0.0, 0.0)
+    sp[3] = arrs3
+    n = len(sp[1][0])
+    ref = {k: [a.copy() for a in sp[k]] for k in (1, 2, 3)}
+    st = np.array([ranfb], dtype=np.int32)
+    c = mrg.Common(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, dt=p.dt, aimpl=p.aimpl, wce_by_wpe=p.bxc, Ez00=p.Ez00)
+    c.ranfb, c.it = ranfb, 1
+    fm = mrg.Fulmov(c, ipar=1, size=1, nspecies=3)
+    with pytest.raises(ValueError):
+        mrg.Fulmov(c, ipar=1, size=1, ctx=fm.ctx)(*sp[3], Q[3], W[3], n, 1, 3)      # the default mirror keeps the reference's ksp = 1|2
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2, 3)}
+    FN = mrg.host.FIELD_NAMES
+    for step in range(2):
+        f12 = U.smooth_fields(p, seed=600 + 2 * step, amp_b=0.5)
+        for name, a in zip(FN, f12):
+            getattr(c, name)[:] = a
+        fm.fields_changed()
+        a6 = O.field_prep(p, f12)
+        for k in (1, 2, 3):
+            r = O.fulmov(p, a6, *ref[k], Q[k], W[k], 1, nranks=1, ranfb=st)
+            fm(*host[k], Q[k], W[k], n, 1, k)
+            got = fm._moment_arrays(k)
+            for ci in range(4):
+                assert U.rel_l2(got[ci], r["mom"][ci]) < MTOL, (step, k, ci)
+            assert abs(c.wkix - r["wkix"]) < MTOL * abs(r["wkix"])
+        f12 = U.smooth_fields(p, seed=601 + 2 * step, amp_b=0.5)
+        for name, a in zip(FN, f12):
+            getattr(c, name)[:] = a
+        fm.fields_changed()
+        a6 = O.field_prep(p, f12)
+        for k in (1, 2, 3):
+            O.fulmov(p, a6, *ref[k], Q[k], W[k], 0, nranks=1, ranfb=st)
+            fm(*host[k], Q[k], W[k], n, 0, k)
+        assert c.ranfb == int(st[0])
+    for k in (1, 2, 3):
+        fm.pull(k, *host[k], n)
+        vfl = U.VETH / np.sqrt(W[k]) if Q[k] > 0 else U.VETH
+        assert U.particle_err(host[k], ref[k], p.hx, vfl) < 2 * PTOL, k
+    fm.ctx.close()
