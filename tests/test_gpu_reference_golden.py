@@ -25,50 +25,19 @@ def test_cuda_path_matches_reference_output(name, tile):
     G = np.load(os.path.join(GOLD, "ref_%s.npz" % name))
     p, sp, ranfb, fsets = CASES[name]()
     nranks, steps, sample = int(G["nranks"][0]), int(G["steps"][0]), int(G["sample"][0])
-    n = len(sp[1][0])
-    par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
-    ctxs = [mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax) for _ in range(nranks)]
-    st = [ranfb] * nranks
-    for r, ctx in enumerate(ctxs):
-        ctx.set_option("tile", tile)
-        for k in (1, 2):
-            ctx.upload(k, *sp[k], first=r + 1, stride=nranks)
-            ctx.sort(k, p.hdt)
-    worst_m = worst_p = 0.0
+    gpu = RC.gpu_steps(mrg, p, sp, ranfb, fsets, nranks, tile=tile)
+    worst_m = 0.0
     for s in range(steps):
-        for ctx in ctxs:
-            ctx.set_fields(fsets[s][0])
         for k in (1, 2):
-            raw = [np.zeros(O.mxyzA(p)) for _ in range(4)]
-            wk = [0.0, 0.0]
-            for r, ctx in enumerate(ctxs):
-                wx, wh, _ = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 1, par, st[r])
-                part = ctx.moments(k, folded=False)
-                for c in range(4):
-                    raw[c] += part[c]
-                wk[0] += wx
-                wk[1] += wh
-            O.vmesh3(p, raw[0], raw[1], raw[2])
-            O.vmesh1(p, raw[3])
             ref = G["mom_%d_%d" % (s, k)]
-            for c in range(4):
-                worst_m = max(worst_m, U.rel_l2(raw[c], ref[c]))
+            worst_m = max(worst_m, max(U.rel_l2(gpu["mom"][s][k][c], ref[c]) for c in range(4)))
             wref = G["wk_%d_%d" % (s, k)]
-            assert abs(wk[0] - wref[0]) <= 1e-10 * abs(wref[0]) and abs(wk[1] - wref[1]) <= 1e-10 * abs(wref[1])
-        for ctx in ctxs:
-            ctx.set_fields(fsets[s][1])
-        for k in (1, 2):
-            for r, ctx in enumerate(ctxs):
-                _, _, st[r] = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 0, par, st[r])
-                ctx.sort(k, p.hdt)
+            got = gpu["wk_pred"][s][k] + gpu["wk_corr"][s][k]
+            assert all(abs(a - b) <= 1e-10 * abs(b) for a, b in zip(got, wref))
     assert worst_m < 1e-10, worst_m
+    worst_p = 0.0
     for k in (1, 2):
-        got = [np.zeros(n) for _ in range(6)]
-        for r, ctx in enumerate(ctxs):
-            ctx.download(k, n, r + 1, nranks, out=got)
-        ref = list(G["out_%d" % k])
-        worst_p = max(worst_p, U.particle_err([a[::sample] for a in got], ref, p.hx, U.vth(k)))
+        worst_p = max(worst_p, U.particle_err([a[::sample] for a in gpu["final"][k]], list(G["out_%d" % k]), p.hx, U.vth(k)))
     assert worst_p < 1e-12 * steps, worst_p
+    st = gpu["ranfb"]
     assert st == [int(v) for v in G["ranfb_out"]]      # same number of draws on every rank => same kicked set sizes
-    for ctx in ctxs:
-        ctx.close()
