@@ -136,7 +136,9 @@ int mrg_renew_fields(mrg_ctx* ctx);
  *             NCCL sum over ranks, vmesh3/vmesh1 fold;
  *   ipc == 0  (F:1162-1365) the same gather/rotation, in-place update,
  *             partbc, E x B drive kick with the rank's ranfp stream.
- * wkix/wkih receive the rank-summed values of F:1312-1317.  ranfb is the
+ * wkix/wkih receive the rank-summed values of F:1312-1317 (the tiled kernels
+ * add their warp partials with fp64 atomics, so the last bits of these two
+ * diagnostics depend on the order of the adds, like any parallel sum).  ranfb is the
  * rank's COMMON /ranfb/ state (in/out; only ipc==0 advances it).            */
 int mrg_fulmov(mrg_ctx* ctx, int32_t ksp, double qmult, double wmult,
                int32_t ipc, const mrg_step_params* p, int32_t* ranfb,
@@ -224,7 +226,11 @@ int mrg_sort(mrg_ctx* ctx, int32_t ksp, double lookahead);
  *                boundary strips (ncclSend/Recv) and the complete blocks are
  *                all-gathered in place -- half the bytes of the whole-grid
  *                allreduce, same sums; 0 = always ncclAllReduce.  Every rank
- *                must use the same setting
+ *                must use the same setting, and calls that invalidate the
+ *                agreement (mrg_upload_particles, mrg_loadpt, options "planes",
+ *                "compact") are collective: every rank makes them between the
+ *                same two steps.  A violated precondition (|vz| dt >= hz) would
+ *                drop charge: mrg_self_check's sums[3] = qmult * N detects it
  *   "defer"      1 = mrg_fulmov(ipc >= 1) returns once its work is queued: the
  *                NCCL moment sum and the fold run on a second stream and
  *                overlap the next species' particle kernel.  *wkix, *wkih are

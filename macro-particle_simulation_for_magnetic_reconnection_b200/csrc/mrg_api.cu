@@ -1153,7 +1153,11 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     if (c->nranks > 1) {                                           // F:2379-2384, 2533, 1312-1315
       PhaseScope ph_sum(c, ksp - 1, 1, MRG_PH_SUM, ms);
       if (!c->comm) return fail(MRG_ERR_STATE, "nranks > 1 but mrg_comm_init was not called");
-      if (s.compact_ok && compact_possible(c) && (s.n == 0 || (s.zocc_valid && s.zocc_lookahead == p->hdt))) {
+      // Which collective runs is decided ONLY by state every rank agrees on: the vote taken in the preceding corrector
+      // call (compact_ok, summed over the ranks there) and the job-wide configuration.  A rank-local condition here could
+      // make ranks enqueue different collectives and hang; calls that reset compact_ok (upload, loadpt,
+      // options "planes" / "compact") are therefore collective: every rank makes them between the same two steps.
+      if (s.compact_ok && compact_possible(c)) {
         rc = compact_sum(c, s.M4, ms);
         if (rc) return rc;
         c->compact_count++;

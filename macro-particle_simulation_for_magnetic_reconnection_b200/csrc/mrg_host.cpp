@@ -31,10 +31,15 @@ struct HostState {
   unsigned char id[MRG_UNIQUE_ID_BYTES];
 } H;
 
+void (*g_abort)(int) = nullptr;   // e.g. a wrapper around MPI_Abort: a rank that dies alone leaves its peers in NCCL forever
+
 void die(const char* where, int rc) {
   H.status = rc;
   std::fprintf(stderr, "fulmov(gpu): %s failed (%d): %s\n", where, rc, mrg_last_error());
-  if (H.exit_on_error) std::exit(1);   // the reference has no status argument: stop
+  if (H.exit_on_error) {               // the reference has no status argument: stop
+    if (g_abort) g_abort(rc);
+    std::exit(1);
+  }
 }
 
 }  // namespace
@@ -75,6 +80,7 @@ int mrg_host_bind_extra_moments(int32_t ksp, double* qjx, double* qjy, double* q
 }
 void mrg_host_set_sort_interval(int32_t n) { H.sort_interval = n < 0 ? 0 : n; }
 void mrg_host_set_exit_on_error(int32_t on) { H.exit_on_error = on != 0; }
+void mrg_host_set_abort(void (*fn)(int)) { g_abort = fn; }
 int mrg_host_status(void) { return H.status; }
 void* mrg_host_context(void) { return H.ctx; }
 void mrg_host_particles_changed(int32_t ksp) {

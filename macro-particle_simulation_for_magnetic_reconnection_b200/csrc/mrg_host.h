@@ -66,6 +66,9 @@ void mrg_host_set_sort_interval(int32_t n);
 /* 0: return to the caller after an error (mrg_host_status() != 0) instead of
  * exiting -- used by the tests. */
 void mrg_host_set_exit_on_error(int32_t on);
+/* Multi-rank hosts: called with the error code before the process exits on a failure, so that the host can take the
+ * whole job down (a wrapper around MPI_Abort) instead of leaving the other ranks blocked in a collective.            */
+void mrg_host_set_abort(void (*fn)(int));
 int mrg_host_status(void);
 
 /* The drop-in: same name and argument list as F:1044. */
