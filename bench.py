@@ -302,6 +302,8 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
         ctx = mrg.MrgContext(mx, my, mz, p.xmax, p.ymax, p.zmax, nspecies=2, rank=rank, nranks=world, device=local)
         ctx.comm_init(mrg.broadcast_unique_id(rank, device=dev))
         ctx.set_option("shard", 1 if part == "slab" else 0)
+        if part == "slab":
+            ctx.map_peers(2, device=dev)
         par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
         st = 7331
         for ksp in (1, 2):
@@ -338,6 +340,7 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
                 if rank == 0:
                     O.fulmov(p, a6, *sp[ksp], QSPEC[ksp], WSPEC[ksp], 0, nranks=nr, ranfb=sto)
         stats = ctx.prep_stats()
+        pushes = ctx.peer_pushes()
         rng_ok = True
         if part == "roundrobin":          # every rank's ranfp state after the reference-order kicks
             t = torch.tensor([float(st)], dtype=torch.float64, device=dev)
@@ -349,7 +352,7 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
         if rank == 0:
             out[part] = {"moments_rel_l2_step1": max(errs[:2]), "moments_rel_l2_step2": max(errs[2:]),
                          "ok": bool(max(errs) < 1e-10 and rng_ok), "ranks": world, "grid": [mx, my, mz], "ppc": ppc,
-                         "slabwise_sums": int(stats["compact_sums"]), "ranfp_states_equal_reference": bool(rng_ok) if part == "roundrobin" else None}
+                         "slabwise_sums": int(stats["compact_sums"]), "peer_pushes": int(pushes), "ranfp_states_equal_reference": bool(rng_ok) if part == "roundrobin" else None}
         dist.barrier()
     return out
 
@@ -457,6 +460,8 @@ def run_ours(args):
     ranfb = 7331
     for ksp in SPECIES:
         _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
+    if world > 1 and args.peer_push:
+        ctx.map_peers(len(SPECIES), device=dev)          # NVLink peer memory for the slab-wise exchange (cudaIpc handles over torch.distributed)
     nloc = sum(ctx.num_local(k) for k in SPECIES)
     ntot_particles = len(SPECIES) * mx * my * mz * ppc if not args.slab_of else nloc
     n_grid = ctx.n_grid
@@ -746,6 +751,7 @@ def run_ours(args):
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
 
     prep_stats = ctx.prep_stats()
+    prep_stats["peer_pushes"] = int(ctx.peer_pushes())
     refpart = None
     if world > 1 and args.shard == "slab" and not args.slab_of and not args.no_reference_partition:
         ctx.close()
@@ -762,8 +768,10 @@ def run_ours(args):
             cfg["emulated_rank"] = "slab %d of %d on one GPU, no NCCL sum (development aid, not a bench line)" % (args.slab_of[1], args.slab_of[0])
         cfg["prep"] = prep_stats
         cfg["rank_sum"] = ("none (1 GPU)" if world == 1 else
-                           "%d of %d moment sums went through the slab-wise exchange, the rest through ncclAllReduce"
-                           % (cfg["prep"]["compact_sums"], 2 * (args.steps + args.warmup + (e2e["steps"] + 1 if e2e else 0))))
+                           "%d of %d moment sums went through the slab-wise exchange (%d of them finished by the fused add+push kernel over "
+                           "NVLink peer memory, the others by ncclAllGather), the rest through ncclAllReduce"
+                           % (cfg["prep"]["compact_sums"], len(SPECIES) * (args.steps + args.warmup + (e2e["steps"] + 1 if e2e else 0)),
+                              cfg["prep"]["peer_pushes"]))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config == 5 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
@@ -864,6 +872,7 @@ def main():
     ap.add_argument("--slab-of", type=int, nargs=2, default=None, metavar=("N", "I"),
                     help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
+    ap.add_argument("--peer-push", type=int, default=1, help="N > 1: finish the slab-wise exchange with the fused add+push kernel over NVLink peer memory (0 = ncclAllGather)")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")
     ap.add_argument("--cpu-steps", type=int, default=4)

@@ -294,6 +294,21 @@ int mrg_compact_layout(int32_t mz, int32_t nranks, int32_t rank,
 int mrg_event_record(mrg_ctx* ctx, int32_t slot);
 int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
 
+/* NVLink peer memory for the slab-wise moment exchange (option "compact"): every
+ * rank exports a cudaIpc handle of its raw-moment array of species ksp, the
+ * host carries the 64 bytes to the other ranks (MPI_Allgather / torch
+ * all_gather) and every rank imports its peers' handles.  Once all nranks-1
+ * peers are mapped, a rank finishes the exchange with ONE kernel that adds the
+ * neighbour strips into its own block and stores the block into every peer's
+ * array over NVLink (instead of ncclAllGather + two ncclBroadcast); option
+ * "peer_push" = 0 keeps the NCCL path.  Ranks must be processes of one node
+ * with peer access (NVSwitch); at most 8 ranks.  mrg_peer_pushes counts the
+ * exchanges finished that way.                                               */
+#define MRG_IPC_HANDLE_BYTES 64
+int mrg_peer_export(mrg_ctx* ctx, int32_t ksp, unsigned char handle[MRG_IPC_HANDLE_BYTES]);
+int mrg_peer_import(mrg_ctx* ctx, int32_t ksp, int32_t rank, const unsigned char handle[MRG_IPC_HANDLE_BYTES]);
+int64_t mrg_peer_pushes(mrg_ctx* ctx, int32_t reset);
+
 /* Device time of the phases of the mrg_fulmov calls since the last reset, in
  * milliseconds, measured with CUDA events on the stream each phase runs on
  * (option "phases" = 1 turns the recording on; it costs a few event records

@@ -96,6 +96,8 @@ struct Species {
   int* id = nullptr;       // nullptr = identity order
   long long n = 0, cap = 0;
   double* M4 = nullptr;    // raw moments [ntot][4] + 2 (wkix, wkih)
+  double* peerM4[8] = {};  // the other ranks' M4 of this species, mapped through cudaIpc (mrg_peer_import); nullptr = not mapped
+  int npeer = 0;
   double* out4[4] = {nullptr, nullptr, nullptr, nullptr};  // folded, reference layout
   bool have_moments = false;
   // cell index of the current slot order (built by mrg_sort): cell_end[c] = end slot of cell c
@@ -203,6 +205,8 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_peer_push = 1;    // slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
+  long long push_count = 0;
   int opt_sink_share = 0;   // deferred D2H of the folded moments copies only this rank's z block (ranks of a node share the host arrays)
   int opt_kick = -1;     // drive-kick draws: -1 = by particle index when "shard" = 1 (no reference stream exists), else the reference's serial order; 0 / 1 force
   int opt_compact = -1;  // slab-wise moment exchange instead of the whole-grid allreduce: -1 = when possible, 0 = never
@@ -547,7 +551,8 @@ bool compact_eligible(const mrg_ctx* c, const Species& s, double hdt) {
   return compact_planes_ok(mz, c->nranks, c->rank, occ);
 }
 // the exchange itself, on stream ms; M4 = raw moments [nz planes][nxy][4] + (wkix, wkih)
-int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
+int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
+  double* M4 = s.M4;
   const GP& g = c->g;
   const int N = c->nranks, r = c->rank, L = g.mz / N;
   const size_t P = (size_t)g.nxy * 4;                       // doubles per plane
@@ -565,10 +570,23 @@ int compact_sum(mrg_ctx* c, double* M4, cudaStream_t ms) {
   if (!n) n = g_nccl.Recv(c->halo_rx[1], cnt, kNcclFloat64, up, c->comm, ms);   // the upper neighbour's downward strip
   const int e = g_nccl.GroupEnd();
   if (n || e) return fail(MRG_ERR_NCCL, "halo exchange: " + nccl_err(n ? n : e));
-  k_add_strips<<<grid_for((long long)cnt, 256), 256, 0, ms>>>(M4 + add_lo * P, c->halo_rx[0], M4 + add_hi * P, c->halo_rx[1], (long long)cnt); CKL(c);
-  n = g_nccl.AllGather(M4 + (size_t)(2 + r * L) * P, M4 + 2 * P, (size_t)L * P, kNcclFloat64, c->comm, ms);
-  if (!n) n = g_nccl.Broadcast(M4, M4, 2 * P, kNcclFloat64, 0, c->comm, ms);
-  if (!n) n = g_nccl.Broadcast(M4 + (size_t)(g.mz + 2) * P, M4 + (size_t)(g.mz + 2) * P, 2 * P, kNcclFloat64, N - 1, c->comm, ms);
+  if (s.npeer == N - 1 && c->opt_peer_push) {
+    // fused add + push over NVLink peer memory (k_add_push); the allreduce below is the completion barrier
+    const size_t e0 = (r == 0) ? 0 : (size_t)(2 + r * L), e1 = (r == N - 1) ? (size_t)g.nz : (size_t)(2 + (r + 1) * L);
+    PeerPtrs pp;
+    pp.n = 0;
+    for (int q = 0; q < N; q++)
+      if (q != r) pp.p[pp.n++] = s.peerM4[q];
+    for (int q = pp.n; q < 8; q++) pp.p[q] = nullptr;
+    k_add_push<<<148 * 8, 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp); CKL(c);
+    c->push_count++;
+    n = 0;
+  } else {
+    k_add_strips<<<grid_for((long long)cnt, 256), 256, 0, ms>>>(M4 + add_lo * P, c->halo_rx[0], M4 + add_hi * P, c->halo_rx[1], (long long)cnt); CKL(c);
+    n = g_nccl.AllGather(M4 + (size_t)(2 + r * L) * P, M4 + 2 * P, (size_t)L * P, kNcclFloat64, c->comm, ms);
+    if (!n) n = g_nccl.Broadcast(M4, M4, 2 * P, kNcclFloat64, 0, c->comm, ms);
+    if (!n) n = g_nccl.Broadcast(M4 + (size_t)(g.mz + 2) * P, M4 + (size_t)(g.mz + 2) * P, 2 * P, kNcclFloat64, N - 1, c->comm, ms);
+  }
   if (!n) n = g_nccl.AllReduce(M4 + (size_t)g.ntot * 4, M4 + (size_t)g.ntot * 4, 2, kNcclFloat64, kNcclSum, c->comm, ms);
   if (n) return fail(MRG_ERR_NCCL, "slab exchange: " + nccl_err(n));
   return MRG_OK;
@@ -798,6 +816,7 @@ int mrg_destroy(mrg_ctx* c) {
   cudaFree(c->alt[0]);
   cudaFree(c->F6); cudaFree(c->alt_id);
   for (auto& s : c->sp) {
+    for (int q = 0; q < 8; q++) if (s.peerM4[q]) cudaIpcCloseMemHandle(s.peerM4[q]);
     cudaFree(s.d[0]);
     cudaFree(s.id); cudaFree(s.M4); cudaFree(s.cell_end); cudaFree(s.cell_end2); cudaFree(s.key); cudaFree(s.hist);
     cudaFree(s.zocc); cudaFree(s.kocc);
@@ -1094,7 +1113,21 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
 
   if (ipc >= 1) {
     PhaseScope ph_setup(c, ksp - 1, 1, MRG_PH_SETUP, c->stream);
-    CK(cudaMemsetAsync(s.M4, 0, ((size_t)g.ntot * 4 + 2) * sizeof(double), c->stream));
+    if (c->nranks > 1 && s.compact_ok && compact_possible(c)) {
+      // slab-wise exchange ahead: this rank deposits only into its own block and the two strips it sends, every other
+      // plane is overwritten by the peers' blocks -- and must not be touched here once peers push into it
+      const int N = c->nranks, r = c->rank, L = g.mz / N;
+      const size_t P = (size_t)g.nxy * 4;
+      int lay[4];
+      compact_layout(g.mz, N, r, lay);
+      const size_t e0 = (r == 0) ? 0 : (size_t)(2 + r * L), e1 = (r == N - 1) ? (size_t)g.nz : (size_t)(2 + (r + 1) * L);
+      CK(cudaMemsetAsync(s.M4 + e0 * P, 0, (e1 - e0) * P * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(s.M4 + (size_t)lay[0] * P, 0, (size_t)HALO_PLANES * P * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(s.M4 + (size_t)lay[1] * P, 0, (size_t)HALO_PLANES * P * sizeof(double), c->stream));
+      CK(cudaMemsetAsync(s.M4 + (size_t)g.ntot * 4, 0, 2 * sizeof(double), c->stream));
+    } else {
+      CK(cudaMemsetAsync(s.M4, 0, ((size_t)g.ntot * 4 + 2) * sizeof(double), c->stream));
+    }
     int blocks = 1;
     const int B = 128;
     if (s.n > 0) {
@@ -1158,7 +1191,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       // make ranks enqueue different collectives and hang; calls that reset compact_ok (upload, loadpt,
       // options "planes" / "compact") are therefore collective: every rank makes them between the same two steps.
       if (s.compact_ok && compact_possible(c)) {
-        rc = compact_sum(c, s.M4, ms);
+        rc = compact_sum(c, s, ms);
         if (rc) return rc;
         c->compact_count++;
       } else {
@@ -1519,6 +1552,8 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     if (value < -1 || value > 0) return fail(MRG_ERR_ARG, "compact must be -1 (slab-wise moment exchange when the ranks agree it is possible) or 0 (always allreduce)");
     c->opt_compact = (int)value;
     for (auto& sp : c->sp) sp.compact_ok = false;
+  } else if (n == "peer_push") {
+    c->opt_peer_push = value != 0;
   } else if (n == "phases") {
     c->opt_phases = value != 0;
   } else if (n == "sink_share") {
@@ -1650,6 +1685,36 @@ int mrg_dfma_peak(mrg_ctx* c, double* dfma_per_s) {
   return MRG_OK;
 }
 
+int mrg_peer_export(mrg_ctx* c, int32_t ksp, unsigned char handle[MRG_IPC_HANDLE_BYTES]) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (!handle) return fail(MRG_ERR_ARG, "null handle");
+  CK(cudaSetDevice(c->device));
+  Species& s = c->sp[ksp - 1];
+  if (!s.M4) { rc = alloc_species(c, s, 0); if (rc) return rc; }
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, s.M4));
+  static_assert(sizeof(h) == MRG_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+  memcpy(handle, &h, sizeof(h));
+  return MRG_OK;
+}
+
+int mrg_peer_import(mrg_ctx* c, int32_t ksp, int32_t rank, const unsigned char handle[MRG_IPC_HANDLE_BYTES]) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (!handle || rank < 0 || rank >= c->nranks || rank >= 8 || rank == c->rank) return fail(MRG_ERR_ARG, "bad peer rank / handle");
+  CK(cudaSetDevice(c->device));
+  Species& s = c->sp[ksp - 1];
+  if (s.peerM4[rank]) return MRG_OK;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* ptr = nullptr;
+  CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  s.peerM4[rank] = (double*)ptr;
+  s.npeer++;
+  return MRG_OK;
+}
+
 int mrg_phase_ms(mrg_ctx* c, double out[MRG_NPHASE], int64_t* calls, int32_t reset) {
   if (!c || !out) return fail(MRG_ERR_ARG, "null argument");
   CK(cudaSetDevice(c->device));
@@ -1689,6 +1754,13 @@ int mrg_get_prep_stats(mrg_ctx* c, int64_t out[4], int32_t reset) {
   out[0] = c->prep_count; out[1] = c->prep_restricted_count; out[2] = c->prep_planes_sum; out[3] = c->compact_count;
   if (reset) { c->prep_count = 0; c->prep_restricted_count = 0; c->prep_planes_sum = 0; c->compact_count = 0; }
   return MRG_OK;
+}
+
+int64_t mrg_peer_pushes(mrg_ctx* c, int32_t reset) {
+  if (!c) return -1;
+  const long long v = c->push_count;
+  if (reset) c->push_count = 0;
+  return v;
 }
 
 }  // extern "C"

@@ -178,6 +178,30 @@ __global__ void k_add_strips(double* __restrict__ lo, const double* __restrict__
   hi[t] += rx_hi[t];
 }
 
+// Slab-wise exchange over NVLink peer memory: ONE kernel adds the two strips received from the ring neighbours into
+// the rank's own block of the raw moments and pushes the finished block straight into every peer's copy of the array
+// (plain 128-bit stores to the peers' mapped buffers, cudaIpc) -- what ncclAllGather + two ncclBroadcasts did after a
+// separate add kernel.  [g0, g0 + cnt) is the block in doubles (ghost planes included on the two end ranks); the strips
+// [lo0, lo0 + strip) and [hi0, hi0 + strip) lie inside it.  The 2-double allreduce that follows on the same stream is the
+// barrier that tells every rank all blocks have landed.
+struct PeerPtrs { double* p[8]; int n; };
+__global__ void __launch_bounds__(256) k_add_push(double* __restrict__ M4, size_t g0, size_t cnt, size_t lo0, const double* __restrict__ rx_lo,
+                                                  size_t hi0, const double* __restrict__ rx_hi, size_t strip, PeerPtrs peers) {
+  const size_t n2 = cnt >> 1;
+  for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n2; t += (size_t)gridDim.x * blockDim.x) {
+    const size_t g = g0 + 2 * t;
+    double2 v = *reinterpret_cast<const double2*>(M4 + g);
+    bool changed = false;
+    if (g - lo0 < strip) { const double2 a = *reinterpret_cast<const double2*>(rx_lo + (g - lo0)); v.x += a.x; v.y += a.y; changed = true; }
+    if (g - hi0 < strip) { const double2 a = *reinterpret_cast<const double2*>(rx_hi + (g - hi0)); v.x += a.x; v.y += a.y; changed = true; }
+    if (changed) *reinterpret_cast<double2*>(M4 + g) = v;
+#pragma unroll
+    for (int q = 0; q < 8; q++)
+      if (q < peers.n) *reinterpret_cast<double2*>(peers.p[q] + g) = v;
+  }
+  __threadfence_system();
+}
+
 // packed F6 -> six reference-layout arrays (mrg_get_prepared_fields)
 __global__ void k_unpack6(GP g, const double* __restrict__ F6, Ptr6 out) {
   const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;

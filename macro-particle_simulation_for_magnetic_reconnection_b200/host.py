@@ -110,6 +110,26 @@ class MrgContext:
     def comm_init(self, uid):
         check(self.lib.mrg_comm_init(self.h, uid))
 
+    def map_peers(self, nspecies=2, device=None):
+        """NVLink peer memory for the slab-wise moment exchange: all-gather the cudaIpc handles of the raw-moment arrays
+        over torch.distributed (a Fortran host would MPI_Allgather the 64 bytes) and map every peer's array.  Collective."""
+        import torch
+        import torch.distributed as dist
+        if self.nranks == 1:
+            return
+        for ksp in range(1, nspecies + 1):
+            buf = C.create_string_buffer(64)
+            check(self.lib.mrg_peer_export(self.h, ksp, buf))
+            mine = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(device if device is not None else "cpu")
+            allh = [torch.zeros_like(mine) for _ in range(self.nranks)]
+            dist.all_gather(allh, mine)
+            for r in range(self.nranks):
+                if r != self.rank:
+                    check(self.lib.mrg_peer_import(self.h, ksp, r, bytes(allh[r].cpu().numpy().tobytes())))
+
+    def peer_pushes(self, reset=False):
+        return self.lib.mrg_peer_pushes(self.h, 1 if reset else 0)
+
     # -- particles ---------------------------------------------------------
     def upload(self, ksp, x, y, z, vx, vy, vz, first=1, stride=1):
         check(self.lib.mrg_upload_particles(self.h, ksp, *[as_dp(a) for a in (x, y, z, vx, vy, vz)],

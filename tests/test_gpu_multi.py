@@ -109,6 +109,7 @@ def _worker_slab(rank, world, port, q):
         ctx.comm_init(uid)
         ctx.set_option("shard", 1)
         ctx.set_option("defer", 1)
+        ctx.map_peers(2)                            # NVLink peer memory: the exchange ends with the fused add + push kernel
         own = {}
         for k in (1, 2):
             ctx.loadpt(k, ppc, U.vth(k), 0.0, U.VBEAM[k])
@@ -143,7 +144,7 @@ def _worker_slab(rank, world, port, q):
         stats = ctx.prep_stats()
         # every preparation restricted to the slab; after the first step (where the ranks vote) the moments of
         # both species are summed slab-wise (halo strips + in-place allgather) instead of by a whole-grid allreduce
-        ok = int(stats["restricted"] == stats["preps"] == 4 and stats["compact_sums"] == 2)
+        ok = int(stats["restricted"] == stats["preps"] == 4 and stats["compact_sums"] == 2 and ctx.peer_pushes() == 2)
         if not ok:
             print("rank", rank, stats)
         ctx.close()
