@@ -106,6 +106,7 @@ struct Species {
   // fused sort: keys of the NEXT order written by the tiled predictor (+ their histogram in hist); the tiled
   // corrector scatters by them into the spare buffers, so the order is fresh without a sort pass
   bool prekeys_valid = false;
+  bool prescan_valid = false;   // cell_end2 / kocc of the next order were already scanned from the predictor's histogram (under the moment exchange)
   bool fresh = false; double fresh_lookahead = 0.0;
   int* cell_end2 = nullptr;
   // next-sort keys emitted by the corrector (fused_keys) + their histogram
@@ -341,6 +342,7 @@ int alloc_species(mrg_ctx* c, Species& s, long long n) {
   s.index_valid = false;
   s.keys_valid = false;
   s.prekeys_valid = false;
+  s.prescan_valid = false;
   s.fresh = false;
   s.zocc_valid = false;
   s.hull_valid = false;
@@ -1134,6 +1136,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       const int iters = (c->opt_deposit == 2) ? c->opt_iters : 1;
       const bool tiled = c->opt_tile == 1 && c->opt_deposit == 2 && s.index_valid;
       s.prekeys_valid = false;
+      s.prescan_valid = false;
       const long long per_block = (long long)(B / 32) * 32 * iters;
       blocks = (int)((s.n + per_block - 1) / per_block);
       GP gl = g;                               // tiled launches cover only the z planes of the order that own slots
@@ -1161,6 +1164,16 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(gl, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
         s.prekeys_valid = prekey != nullptr;
         s.keys_valid = false;
+        s.prescan_valid = false;
+        if (prekey) {
+          // cell starts + occupied planes of the next order, needed by the corrector's scatter: scanned here, on the particle
+          // stream, so that they run under this species' moment exchange instead of in front of the corrector
+          rc = scan_excl(c, s.hist, s.cell_end2, c->ncell + 1, nullptr);
+          if (rc) return rc;
+          rc = kocc_begin(c, s, s.cell_end2);
+          if (rc) return rc;
+          s.prescan_valid = true;
+        }
       }
       else if (c->opt_deposit == 0) k_predict_direct<<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial);
       else if (iters == 1) k_predict_run<1><<<blocks, B, 0, c->stream>>>(g, pp, P, c->F6, s.M4, c->wk_partial, gm);
@@ -1273,10 +1286,12 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       if (scatter) {   // cell starts of the next order; the kernel advances them to the ends
         rc = ensure_alt(c, s.cap, true);
         if (rc) return rc;
-        rc = scan_excl(c, s.hist, s.cell_end2, c->ncell + 1, nullptr);
-        if (rc) return rc;
-        rc = kocc_begin(c, s, s.cell_end2);
-        if (rc) return rc;
+        if (!s.prescan_valid) {
+          rc = scan_excl(c, s.hist, s.cell_end2, c->ncell + 1, nullptr);
+          if (rc) return rc;
+          rc = kocc_begin(c, s, s.cell_end2);
+          if (rc) return rc;
+        }
         for (int k = 0; k < 6; k++) { D.src[k] = s.d[k]; D.dst[k] = c->alt[k]; }
         D.id_src = s.id; D.id_dst = c->alt_id;
       }
@@ -1326,6 +1341,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         s.fresh_lookahead = p->hdt;
       }
       s.prekeys_valid = false;
+      s.prescan_valid = false;
       k_wk_final<<<1, 256, 0, c->stream>>>(c->wk_partial, nparts, c->wk2); CKL(c);
     }
     ph_setup.done();
@@ -1465,6 +1481,7 @@ int mrg_sort(mrg_ctx* c, int32_t ksp, double lookahead) {
   if (s.n == 0) return MRG_OK;
   if (s.fresh && s.index_valid && s.fresh_lookahead == lookahead) return MRG_OK;   // the fused sort of the last corrector already produced this order
   s.prekeys_valid = false;
+  s.prescan_valid = false;
   s.fresh = false;
   rc = ensure_alt(c, s.cap, true);
   if (rc) return rc;
