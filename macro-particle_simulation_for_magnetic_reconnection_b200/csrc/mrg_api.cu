@@ -407,7 +407,7 @@ int complete_moments(mrg_ctx* c, int k) {
 
 // ---- plane tracking -----------------------------------------------------------
 bool tracking(const mrg_ctx* c) { return c->opt_planes == 1 || (c->opt_planes < 0 && c->nranks > 1); }
-int zocc_words(const mrg_ctx* c) { return (c->g.mz + 1 + 31) / 32; }
+int zocc_words(const mrg_ctx* c) { return (c->g.mz + 1 + 31) / 32 + 1; }   // plane bitmap + one word of flags (bit 0: |vz| dt >= hz seen)
 
 // zero the species' plane bitmap before a kernel that marks it (nullptr when tracking is off)
 int zocc_begin(mrg_ctx* c, Species& s, unsigned** out) {
@@ -431,6 +431,9 @@ int zocc_fetch(mrg_ctx* c, Species& s, double lookahead, bool approx) {
   return MRG_OK;
 }
 bool occ_bit(const Species& s, int kp) { return (s.zocc_host[kp >> 5] >> (kp & 31)) & 1u; }
+// the corrector saw a particle that moves a whole plane or more per step: the +-1 plane bound of the recorded planes and
+// the strips of the slab-wise exchange no longer hold, so the record is not used (full preparation, whole-grid allreduce)
+bool occ_violated(const Species& s) { return !s.zocc_host.empty() && (s.zocc_host.back() & 1u); }
 // OR the species' gather planes into occ[0..mz]
 void add_occupancy(const Species& s, int mz, std::vector<char>& occ) {
   if (s.n == 0) return;
@@ -546,7 +549,7 @@ bool compact_possible(const mrg_ctx* c) {
 }
 bool compact_eligible(const mrg_ctx* c, const Species& s, double hdt) {
   if (s.n == 0) return true;
-  if (!(s.zocc_valid && s.zocc_lookahead == hdt)) return false;
+  if (!(s.zocc_valid && s.zocc_lookahead == hdt) || occ_violated(s)) return false;
   const int mz = c->g.mz;
   std::vector<char> occ(mz + 1, 0);
   add_occupancy(s, mz, occ);
@@ -623,7 +626,7 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   PrepKey key{p->aimpl, p->bxc, p->byc, p->bzc, p->ifilx, p->ifily, p->ifilz, c->field_version};
   const GP& g = c->g;
   const int mz = g.mz, nz = g.nz;
-  auto usable = [&](const Species& s) { return s.n == 0 || (s.zocc_valid && s.zocc_lookahead == p->hdt); };
+  auto usable = [&](const Species& s) { return s.n == 0 || (s.zocc_valid && s.zocc_lookahead == p->hdt && !occ_violated(s)); };
   if (c->prep_valid && key == c->prep_key) {
     if (c->prep_full) return MRG_OK;
     bool covered = ksp >= 1;          // ksp = 0: the caller wants every plane

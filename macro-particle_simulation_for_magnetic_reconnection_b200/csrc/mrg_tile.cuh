@@ -284,7 +284,7 @@ __device__ __forceinline__ void bulk_g2s_stream(void* dst, const void* src, unsi
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
   unsigned ok = 0;
 #pragma unroll 1
-  for (int spin = 0; spin < (1 << 22); spin++) {
+  for (int spin = 0; spin < (1 << 26); spin++) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
@@ -292,7 +292,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phas
         : "memory");
     if (ok) return;
   }
-  __trap();   // a lost TMA completion must not hang the GPU
+  __trap();   // a lost TMA completion must not hang the GPU (each try_wait suspends the warp for a hardware time slice, so 2^26 of them is minutes, not a profiler replay or a preemption)
 }
 
 // ---------------------------------------------------------------------------
@@ -417,7 +417,7 @@ __device__ __forceinline__ void mbar_expect_tx_s(unsigned bar_s, unsigned bytes)
 __device__ __forceinline__ void mbar_wait_s(unsigned bar_s, unsigned phase) {
   unsigned ok = 0;
 #pragma unroll 1
-  for (int spin = 0; spin < (1 << 24); spin++) {
+  for (int spin = 0; spin < (1 << 26); spin++) {
     asm volatile(
         "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
         : "=r"(ok)
@@ -605,6 +605,7 @@ __device__ __forceinline__ void warp_wk_atomic(double wx, double wh, double* __r
 // Predictor on TMA-staged tiles.
 // ---------------------------------------------------------------------------
 constexpr int PNS = MRG_PRED_NSTAGE, CNS = MRG_CORR_NSTAGE;
+constexpr int ZOCC_VIOLATION = 0x7ffffff0;
 constexpr int PRED_ACC_D = MRG_PRED_SMEM_TILE ? 6 * TILE_ACC_D : 0;      // the accumulator tile exists only when it is used
 constexpr int PRED_RING_BYTES = PR_WARPS * PNS * TSTAGE_P;               // first in the carve-up: tensor TMA wants 128-byte aligned boxes
 constexpr int PRED_SMEM_BYTES = PRED_RING_BYTES + (6 * TILE_ROW_D + PRED_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + PR_Q_D)) * 8 +
@@ -796,7 +797,10 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
         int kq = gather_plane_fast(g, z, vz, lookahead) - t.k;
         const int hmz = g.mz >> 1;
         kq = kq > hmz ? kq - g.mz : (kq < -hmz ? kq + g.mz : kq);
-        if (valid) { rlo = min(rlo, kq); rhi = max(rhi, kq); }
+        // precondition of the +-1 plane bound and of the slab-wise exchange: |vz| dt < hz.  A violation rides in rhi as a
+        // sentinel and ends up in the flag word behind the bitmap; the host then ignores the record (full preparation,
+        // whole-grid allreduce)
+        if (valid) { rlo = min(rlo, kq); rhi = max(rhi, (fabs(vz) * pp.dt >= g.hz) ? ZOCC_VIOLATION : kq); }
       }
       if (pp.drive_on && pp.kick_inline) {                    // E x B drive kick with a per-particle draw, F:1343-1364
         if (valid && (fabs(z - pp.zcent) < pp.zw) && ((fabs(y - pp.ycent2) < pp.yw) || (fabs(y - pp.ycent1) < pp.yw))) {
@@ -858,6 +862,10 @@ k_correct_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     if (zocc) {                                               // one range per warp; bits already set cost a load only
       rlo = __reduce_min_sync(FULL, rlo);
       rhi = __reduce_max_sync(FULL, rhi);
+      if (rhi == ZOCC_VIOLATION) {
+        if (lane == 0) atomicOr(zocc + ((g.mz + 1 + 31) >> 5), 1u);
+        rhi = g.mz;
+      }
       if (lane == 0 && rlo <= rhi) {
         for (int r = max(rlo, -g.mz); r <= min(rhi, g.mz); r++) {
           int k = t.k + r;

@@ -306,3 +306,43 @@ def test_lazy_host_fields_follow_the_trans_protocol(mrg, planes):
     if planes:
         assert h2d < 0.85 * full, (h2d, full)
     fm.ctx.close()
+
+
+def test_fast_particles_disable_the_plane_record(mrg):
+    """|vz| dt >= hz breaks the +-1 plane bound of the recorded gather planes (the precondition was only
+    documented).  The tiled corrector now reports it, the host ignores the record and prepares every plane: results still
+    match the oracle, and no restricted preparation runs."""
+    p = U.make_parm(12, 10, 24)
+    sp_all, ranfb = U.load_species(p, 10)
+    sp = slab_subset(p, sp_all, 6.0, 11.0)
+    k = 2
+    sp[k][5][::7] = 1.3 * p.hz / p.dt * np.sign(sp[k][5][::7] + 1e-30)      # every 7th electron crosses more than a plane per step
+    n = len(sp[k][0])
+    ref = [a.copy() for a in sp[k]]
+    st = np.array([ranfb], dtype=np.int32)
+    ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax)
+    ctx.set_option("planes", 1)
+    ctx.upload(k, *sp[k])
+    ctx.sort(k, p.hdt)
+    st_gpu = ranfb
+    restricted = []
+    for step in range(3):
+        for ipc in (1, 0):
+            f12 = U.smooth_fields(p, seed=500 + 10 * step + ipc)
+            a6 = O.field_prep(p, f12)
+            ctx.set_fields(f12)
+            ctx.prep_stats(reset=True)
+            r = O.fulmov(p, a6, *ref, U.QSPEC[k], U.WSPEC[k], ipc, nranks=1, ranfb=st)
+            _, _, st_gpu = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], ipc, params_of(mrg, p), st_gpu)
+            restricted.append(ctx.prep_stats()["restricted"])
+            if ipc >= 1:
+                mom = ctx.moments(k)
+                for c in range(4):
+                    assert U.rel_l2(mom[c], r["mom"][c]) < MTOL, (step, c)
+            else:
+                ctx.sort(k, p.hdt)
+    got = ctx.download(k, n)
+    assert U.particle_err(got, ref, p.hx, U.vth(k)) < 30 * PTOL
+    assert st_gpu == int(st[0])
+    assert sum(restricted[2:]) == 0, restricted        # after the first corrector reported the violation: full preparations only
+    ctx.close()
