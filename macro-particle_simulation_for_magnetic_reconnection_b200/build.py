@@ -59,10 +59,10 @@ def build_cuda(force=False, verbose=False, out=None, defines=()):
 
 def build_host(force=False):
     srcs = [os.path.join(CSRC, "mrg_host.cpp"), os.path.join(CSRC, "mrg_host.h"),
-            os.path.join(ROOT, "include", "mrg_fulmov.h")]
+            os.path.join(ROOT, "include", "mrg_fulmov.h"), os.path.join(CSRC, "mrg_restart.cpp"), os.path.join(CSRC, "mrg_restart.h")]
     if not force and not _stale(HOSTLIB, srcs + [LIB]):
         return HOSTLIB
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOSTLIB, srcs[0],
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", HOSTLIB, srcs[0], srcs[3],
            "-L" + HERE, "-lmrg_fulmov", "-Wl,-rpath,$ORIGIN"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
