@@ -461,6 +461,7 @@ def run_ours(args):
     for ksp in SPECIES:
         _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
     if world > 1 and args.peer_push:
+        ctx.set_option("peer_push", args.peer_push)
         ctx.map_peers(len(SPECIES), device=dev)          # NVLink peer memory for the slab-wise exchange (cudaIpc handles over torch.distributed)
     nloc = sum(ctx.num_local(k) for k in SPECIES)
     ntot_particles = len(SPECIES) * mx * my * mz * ppc if not args.slab_of else nloc
@@ -872,7 +873,7 @@ def main():
     ap.add_argument("--slab-of", type=int, nargs=2, default=None, metavar=("N", "I"),
                     help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
-    ap.add_argument("--peer-push", type=int, default=1, help="N > 1: finish the slab-wise exchange with the fused add+push kernel over NVLink peer memory (0 = ncclAllGather)")
+    ap.add_argument("--peer-push", type=int, default=64, help="N > 1: CTAs of the fused add+push kernel that finishes the slab-wise exchange over NVLink peer memory (0 = ncclAllGather)")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")
     ap.add_argument("--cpu-steps", type=int, default=4)

@@ -206,7 +206,7 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
-  int opt_peer_push = 1;    // slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
+  int opt_peer_push = 64;   // CTAs of the fused add+push kernel (0 = off): slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
   long long push_count = 0;
   int opt_sink_share = 0;   // deferred D2H of the folded moments copies only this rank's z block (ranks of a node share the host arrays)
   int opt_kick = -1;     // drive-kick draws: -1 = by particle index when "shard" = 1 (no reference stream exists), else the reference's serial order; 0 / 1 force
@@ -583,7 +583,9 @@ int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
     for (int q = 0; q < N; q++)
       if (q != r) pp.p[pp.n++] = s.peerM4[q];
     for (int q = pp.n; q < 8; q++) pp.p[q] = nullptr;
-    k_add_push<<<148 * 8, 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp); CKL(c);
+    // a small grid: 64 CTAs keep NVLink busy (fire-and-forget 128-bit peer stores) and leave the SMs to the other species'
+    // particle kernel that runs next to this exchange in deferred mode (1184 CTAs cost that kernel 0.6 ms at 8 GPUs, measured)
+    k_add_push<<<std::max(1, c->opt_peer_push), 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp); CKL(c);
     c->push_count++;
     n = 0;
   } else {
@@ -1573,7 +1575,8 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
     c->opt_compact = (int)value;
     for (auto& sp : c->sp) sp.compact_ok = false;
   } else if (n == "peer_push") {
-    c->opt_peer_push = value != 0;
+    if (value < 0 || value > 4096) return fail(MRG_ERR_ARG, "peer_push must be 0 (ncclAllGather) or the number of CTAs of the push kernel");
+    c->opt_peer_push = (int)value;
   } else if (n == "phases") {
     c->opt_phases = value != 0;
   } else if (n == "sink_share") {

@@ -150,9 +150,14 @@ __device__ __forceinline__ int sort_cell_folded(const GP& g, double x, double y,
   int ip = __double2loint(__dadd_rd(fma(g.hxi, x, 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
   int jp = __double2loint(__dadd_rd(fma(g.hyi, y, 0.000000001 + 65536.0), MRG_TWO52)) - 65536;
   int kp = __double2loint(__dadd_rd(fma(g.hzi, z, 0.500000001 + 65536.0), MRG_TWO52)) - 65536;
-  ip = ip < 0 ? ip + g.mx : (ip >= g.mx ? ip - g.mx : ip);
-  kp = kp < 0 ? kp + g.mz : (kp >= g.mz ? kp - g.mz : kp);
-  jp = jp < 0 ? -1 - jp : (jp >= g.my ? 2 * g.my - 1 - jp : jp);
+  // one periodic image either side in x and z, one mirror image at either wall in y -- with masks instead of branches
+  // (the compiler turned the conditional form into three divergent regions per particle)
+  ip += (ip >> 31) & g.mx;
+  ip -= ((g.mx - 1 - ip) >> 31) & g.mx;
+  kp += (kp >> 31) & g.mz;
+  kp -= ((g.mz - 1 - kp) >> 31) & g.mz;
+  jp ^= jp >> 31;                                        // jp < 0  -> -1 - jp
+  jp += ((g.my - 1 - jp) >> 31) & (2 * g.my - 1 - 2 * jp);   // jp >= my -> 2 my - 1 - jp
   ip = min(max(ip, 0), g.mx - 1);
   jp = min(max(jp, 0), g.my - 1);
   kp = min(max(kp, 0), g.mz - 1);
