@@ -724,10 +724,26 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt[0])
+        # what landed in the host's COMMON /srimp7/ arrays during the timed steps must be what the device holds: with shared
+        # arrays every rank delivered one z block, and rank 0 checks all of them against its own complete folded arrays
+        shared_ok = None
+        if share:
+            dist.barrier()
+            ctx.set_option("sink_share", 0)
+            ok = 1.0
+            if rank == 0:
+                for ksp in (1, 2):
+                    full = ctx.moments(ksp, folded=True)
+                    for a, b in zip(full, fm._moment_arrays(ksp)):
+                        ok = ok if np.array_equal(a, b) else 0.0
+            ctx.set_option("sink_share", 1)
+            flag = torch.tensor([ok], dtype=torch.float64, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            shared_ok = bool(float(flag[0]) == 1.0)
         e2e = {"value": ntot_particles * ne / te, "unit": UNIT, "h2d_bytes_per_step": cnt_e["h2d_bytes"] // ne,
                "d2h_bytes_per_step": cnt_e["d2h_bytes"] // ne, "steps": ne, "ms_per_step": 1e3 * te / ne,
                "pcie_gb_per_s_per_rank": (cnt_e["h2d_bytes"] + cnt_e["d2h_bytes"]) / te / 1e9,
-               "lazy_fields": lazy, "shared_moment_arrays": share,
+               "lazy_fields": lazy, "shared_moment_arrays": share, "shared_arrays_equal_device_moments": shared_ok,
                "note": "host fields in pinned memory -> mrg_set_fields (H2D), moments -> COMMON /srimp7/ arrays (D2H) every "
                        "step through the Fulmov mirror of the reference call; particles stay resident in HBM by design; "
                        + ("each rank fetches only the z planes its field preparation reads (mrg_set_fields_lazy) and delivers only its "
