@@ -1166,7 +1166,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         CUtensorMap tmP;
         rc = particle_map(s.d[0], s.cap, &tmP);
         if (rc) return rc;
-        k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(gl, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist, P);
+        k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(gl, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
         s.prekeys_valid = prekey != nullptr;
         s.keys_valid = false;
         s.prescan_valid = false;

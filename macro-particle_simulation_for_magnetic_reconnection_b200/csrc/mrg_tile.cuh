@@ -608,16 +608,12 @@ constexpr int PNS = MRG_PRED_NSTAGE, CNS = MRG_CORR_NSTAGE;
 constexpr int ZOCC_VIOLATION = 0x7ffffff0;
 constexpr int PRED_ACC_D = MRG_PRED_SMEM_TILE ? 6 * TILE_ACC_D : 0;      // the accumulator tile exists only when it is used
 constexpr int PRED_RING_BYTES = PR_WARPS * PNS * TSTAGE_P;               // first in the carve-up: tensor TMA wants 128-byte aligned boxes
-#ifndef MRG_DEFER_STRAYS
-#define MRG_DEFER_STRAYS 0
-#endif
-constexpr int STRAY_CAP = 64;      // per-warp list of deferred strays (slots); drained whenever more than 32 are waiting
 constexpr int PRED_SMEM_BYTES = PRED_RING_BYTES + (6 * TILE_ROW_D + PRED_ACC_D + PR_WARPS * (32 * PR_W_STRIDE + PR_Q_D)) * 8 +
-                                (PR_WARPS * PNS + 1) * 8 + (MRG_DEFER_STRAYS ? PR_WARPS * STRAY_CAP * 4 : 0);
+                                (PR_WARPS * PNS + 1) * 8;
 __global__ void __launch_bounds__(PR_WARPS * 32, MRG_PRED_MINB)
 k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, const double* __restrict__ F6, double* __restrict__ M4,
                const int* __restrict__ cell_end, double* __restrict__ wk_partial, int group_min,
-               int* __restrict__ prekey, int* __restrict__ prehist, ParticleSoA P) {
+               int* __restrict__ prekey, int* __restrict__ prehist) {
   // dynamic shared memory (PRED_SMEM_BYTES > 48 KB static limit), carved up by hand
   extern __shared__ __align__(1024) unsigned char smem_pred[];
   unsigned char* sRing = smem_pred;                            // [warps][PNS][TSTAGE_P]  particle stages
@@ -628,10 +624,6 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
   unsigned long long* sBar = reinterpret_cast<unsigned long long*>(smQ + PR_WARPS * PR_Q_D);   // [warps][PNS] + 1
   unsigned long long& bar = sBar[PR_WARPS * PNS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#if MRG_DEFER_STRAYS
-  int* slist = reinterpret_cast<int*>(sBar + PR_WARPS * PNS + 1) + w * STRAY_CAP;
-  int scount = 0;
-#endif
   const Tile t = tile_of(g, cell_end, blockIdx.x);
   const bool busy = t.p1 > t.p0;                              // block-uniform
   double wx = 0.0, wh = 0.0;
@@ -658,110 +650,6 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
     for (int n = 0; n < 18; n++) acc[n] = 0.0;
     int cur = -1;
     const double ah = pp.aimpl * pp.hh, hh2 = 0.5 * pp.hh;
-#if MRG_DEFER_STRAYS
-    // Strays (gather cell outside this CTA's tile) leave the hot loop: their slots are collected in a per-warp list and
-    // pushed afterwards, 32 at a time with every lane busy, through L1 and with direct atomics.  The hot loop then holds
-    // no global gather path at all (a warp-iteration with ONE stray used to run both paths for the whole warp).
-    int it = 0;
-    for (;;) {
-#pragma unroll 1
-      for (; it < st.nit; it++) {
-        P6 c;
-        stream_issue<PNS, TSTAGE_P>(maps, st, lane);
-        stream_wait<PNS>(st, it);
-        stream_read<PNS, TSTAGE_P>(st, it, lane, c);
-        const int p = st.a + 32 * it + lane;
-        bool valid = p >= st.lo && p < st.b;
-        stream_advance<PNS>(st);
-        int key = -1;
-        {
-          double qvy[8], wxz[9];
-          double rx = __dadd_rn(c.x, __dmul_rn(pp.hdt, c.vx));          // F:1163-1165
-          double ry = __dadd_rn(c.y, __dmul_rn(pp.hdt, c.vy));
-          double rz = __dadd_rn(c.z, __dmul_rn(pp.hdt, c.vz));
-          if (__any_sync(FULL, maybe_wrap(g, rx, ry, rz))) wrap_pos(g, rx, ry, rz);   // partbcEST, F:1168
-          Stencil s;
-          make_stencil<true>(g, rx, ry, rz, s);
-          const unsigned d = (unsigned)(s.n0 - t.n0_first);
-          const bool stray = d >= (unsigned)t.ncell;
-          double f[6];
-          gather6_tile(sF, stray ? 0 : (int)d, s, f);
-          const unsigned sm = __ballot_sync(FULL, valid && stray);
-          if (sm) {                                                   // rare: remember the slots, mask the lanes
-            if (valid && stray) slist[scount + __popc(sm & ((1u << lane) - 1u))] = p;
-            scount += __popc(sm);
-            valid = valid && !stray;
-          }
-          const Kick k = rotate(f, c.vx, c.vy, c.vz, pp.ht, pp.ht2);
-          Predicted o;
-          o.vxj = fma(ah, k.dvx, c.vx);                         // F:1300-1302
-          o.vyj = fma(ah, k.dvy, c.vy);
-          o.vzj = fma(ah, k.dvz, c.vz);
-          o.rx = fma(pp.adt, fma(hh2, k.dvx, c.vx), c.x);       // F:1304-1306
-          o.ry = fma(pp.adt, fma(hh2, k.dvy, c.vy), c.y);
-          o.rz = fma(pp.adt, fma(hh2, k.dvz, c.vz), c.z);
-          if (__any_sync(FULL, maybe_wrap(g, o.rx, o.ry, o.rz))) {
-            if (wrap_pos(g, o.rx, o.ry, o.rz)) o.vyj = -o.vyj;  // partbc, F:1375
-          }
-          key = scatter_factors(g, valid ? pp.qmult : 0.0, o, qvy, wxz);
-          if (valid) { wx += k.wx; wh += k.wh; } else key = -1;
-          park_factors(W, Q, lane, qvy, wxz, key);
-          if (prekey) {
-            const double xn = fma(pp.dt, fma(hh2, k.dvx, c.vx), c.x), un = fma(pp.hh, k.dvx, c.vx);
-            const double yn = fma(pp.dt, fma(hh2, k.dvy, c.vy), c.y), vn = fma(pp.hh, k.dvy, c.vy);
-            const double zn = fma(pp.dt, fma(hh2, k.dvz, c.vz), c.z), wn = fma(pp.hh, k.dvz, c.vz);
-            const int kcell = sort_cell_folded(g, fma(pp.hdt, un, xn), fma(pp.hdt, vn, yn), fma(pp.hdt, wn, zn));
-            int cnt;
-            bool head;
-            run_rank(kcell, valid, lane, cnt, head);
-            if (valid) prekey[p] = kcell;
-            if (head) atomicAdd(prehist + kcell, cnt);
-          }
-        }
-        __syncwarp();
-        deposit_parked<(MRG_PRED_SMEM_TILE != 0)>(Wq, Qq, key, lane, acc, cur, group_min, tg);
-        __syncwarp();
-        if (scount > STRAY_CAP - 32) { it++; break; }            // warp-uniform: drain before the list can overflow
-      }
-      // ---- drain: the collected strays, one per lane, through L1 and direct atomics (cold) -------------------------
-      for (int base = 0; base < scount; base += 32) {
-        const int e = base + lane;
-        if (e < scount) {
-          const int p = slist[e];
-          double swx = 0.0, swh = 0.0;
-          const double x = P.x[p], y = P.y[p], z = P.z[p], vx = P.vx[p], vy = P.vy[p], vz = P.vz[p];
-          double rx = __dadd_rn(x, __dmul_rn(pp.hdt, vx)), ry = __dadd_rn(y, __dmul_rn(pp.hdt, vy)), rz = __dadd_rn(z, __dmul_rn(pp.hdt, vz));
-          wrap_pos(g, rx, ry, rz);
-          Stencil s;
-          make_stencil<true>(g, rx, ry, rz, s);
-          double f[6];
-          gather6(F6, g, s, f);
-          const Kick k = rotate(f, vx, vy, vz, pp.ht, pp.ht2);
-          swx = k.wx; swh = k.wh;
-          Predicted o;
-          o.vxj = fma(ah, k.dvx, vx); o.vyj = fma(ah, k.dvy, vy); o.vzj = fma(ah, k.dvz, vz);
-          o.rx = fma(pp.adt, fma(hh2, k.dvx, vx), x); o.ry = fma(pp.adt, fma(hh2, k.dvy, vy), y); o.rz = fma(pp.adt, fma(hh2, k.dvz, vz), z);
-          if (wrap_pos(g, o.rx, o.ry, o.rz)) o.vyj = -o.vyj;
-          double qvy[8], wxz[9];
-          const int n0 = scatter_factors(g, pp.qmult, o, qvy, wxz);
-          deposit_direct72(qvy, wxz, n0, g, M4);
-          if (prekey) {
-            const double xn = fma(pp.dt, fma(hh2, k.dvx, vx), x), un = fma(pp.hh, k.dvx, vx);
-            const double yn = fma(pp.dt, fma(hh2, k.dvy, vy), y), vn = fma(pp.hh, k.dvy, vy);
-            const double zn = fma(pp.dt, fma(hh2, k.dvz, vz), z), wn = fma(pp.hh, k.dvz, vz);
-            const int kcell = sort_cell_folded(g, fma(pp.hdt, un, xn), fma(pp.hdt, vn, yn), fma(pp.hdt, wn, zn));
-            prekey[p] = kcell;
-            atomicAdd(prehist + kcell, 1);
-          }
-          atomicAdd(wk_partial, swx);
-          atomicAdd(wk_partial + 1, swh);
-        }
-      }
-      __syncwarp();
-      scount = 0;
-      if (it >= st.nit) break;
-    }
-#else
 #pragma unroll 1
     for (int it = 0; it < st.nit; it++) {
       P6 c;
@@ -807,7 +695,6 @@ k_predict_tile(GP g, PushParams pp, const __grid_constant__ CUtensorMap tmP, con
       deposit_parked<(MRG_PRED_SMEM_TILE != 0)>(Wq, Qq, key, lane, acc, cur, group_min, tg);
       __syncwarp();
     }
-#endif
     if (cur >= 0) flush_quad<(MRG_PRED_SMEM_TILE != 0)>(acc, cur, tg);
 #if MRG_PRED_SMEM_TILE
     __syncthreads();
