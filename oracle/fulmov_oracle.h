@@ -6,13 +6,20 @@
  * --impl reference legs may build, load or call it, and only as the checker
  * or the reported CPU baseline.
  *
- * PARITY UNPINNED: the reference (one Fortran 2003 file) ships no tests, no
- * golden vectors and no fixtures for this path, and neither this container
- * nor the GPU box has a Fortran compiler or MPI, so oracle/_ref cannot be
- * built.  The pin is this restatement, the analytic invariants in
- * tests/test_oracle_invariants.py, and bit-for-bit agreement with a second,
- * independent transcription of the same Fortran (oracle/np_restatement.py,
- * tests/test_oracle_crosscheck.py).
+ * PINNED TO THE REFERENCE'S OWN CODE: the reference ships no tests, golden
+ * vectors or fixtures and the image has no Fortran compiler, so
+ * oracle/f03c.py (a Fortran-2003-subset -> C translator) compiles the
+ * reference's fulmov, init, loadpt, partbc*, srimp1/2, outmesh3, filt3e,
+ * vmesh3/1, ranf(p) from /root/reference/@mrg37-080A.f03 where it lies into
+ * oracle/_ref/ (oracle/build_ref.py; git-ignored).  This restatement agrees
+ * with that library BIT FOR BIT on loads, folded moments, wkix/wkih,
+ * corrector output with the drive kick and every rank's ranfp state, for 1-8
+ * simulated ranks, edge placements and the dt*wce > 10 regime
+ * (tests/test_ref_pin.py), and reproduces the committed reference-output
+ * fixtures tests/golden/ref_*.npz bit for bit.  A second, independent numpy
+ * transcription (oracle/np_restatement.py, tests/test_oracle_crosscheck.py)
+ * and the analytic invariants (tests/test_oracle_invariants.py) remain as
+ * further layers.
  *
  * Citation shorthand: F:n = /root/reference/@mrg37-080A.f03 line n.
  * Arrays use the reference layout real(C_DOUBLE)(-2:mx+1,-1:my+1,-2:mz+1),

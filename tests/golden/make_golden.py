@@ -1,9 +1,9 @@
 """Generates tests/golden/fulmov_small.npz from the CPU oracle.
 
-The reference ships no golden vectors and cannot be compiled here (Fortran
-2003 + MPI, no compiler in the image), so these fixtures are a REGRESSION pin
-of the oracle restatement (inputs and outputs of one predictor + one corrector
-call per species on an 8x6x8 grid), not an independent pin of the reference.
+A REGRESSION pin of the oracle restatement (inputs and outputs of one predictor
++ one corrector call per species on an 8x6x8 grid).  The independent pin --
+fixtures written by the reference's own code -- is tests/golden/ref_*.npz, made
+by make_golden_ref.py through oracle/_ref.
 Run:  python tests/golden/make_golden.py
 """
 import os
