@@ -411,6 +411,26 @@ def measure_reference_partition(mrg, dist, torch, args, rank, world, local, dev,
             "slabwise_sums": int(stats["compact_sums"])}
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and hence the first-touch placement of the pinned field / moment arrays it allocates)
+    to the CPUs next to its GPU, what `mpiexec --bind-to` / numactl does for an MPI host.  Without it eight ranks' PCIe
+    traffic crosses the socket interconnect at random.  Returns the number of CPUs bound to, or 0 when NVML is not usable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return 0
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -426,6 +446,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists); use --impl reference for the CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = bind_to_gpu_numa(local) if (world > 1 and args.numa_bind) else 0
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     mx, my, mz = GRIDS[args.gpus] if not args.grid else tuple(args.grid)
@@ -781,6 +802,7 @@ def run_ours(args):
     if rank == 0:
         cfg = workload_config(args.gpus, args)
         cfg["parallelism"] = "particle-sharded x%d" % world
+        cfg["host_binding"] = ("each rank bound to the %d CPUs next to its GPU (NVML affinity)" % numa_cpus) if numa_cpus else "none"
         if args.slab_of:
             cfg["emulated_rank"] = "slab %d of %d on one GPU, no NCCL sum (development aid, not a bench line)" % (args.slab_of[1], args.slab_of[0])
         cfg["prep"] = prep_stats
@@ -890,6 +912,7 @@ def main():
                     help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
     ap.add_argument("--peer-push", type=int, default=64, help="N > 1: CTAs of the fused add+push kernel that finishes the slab-wise exchange over NVLink peer memory (0 = ncclAllGather)")
+    ap.add_argument("--numa-bind", type=int, default=1, help="N > 1: bind each rank to the CPUs next to its GPU before it allocates pinned host arrays")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")
     ap.add_argument("--cpu-steps", type=int, default=4)
