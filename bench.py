@@ -483,6 +483,7 @@ def run_ours(args):
         _, ranfb = ctx.loadpt(ksp, ppc, vth(ksp), 0.0, VBEAM[ksp])
     if world > 1 and args.peer_push:
         ctx.set_option("peer_push", args.peer_push)
+        ctx.set_option("peer_push_last", args.peer_push_last)
         ctx.map_peers(len(SPECIES), device=dev)          # NVLink peer memory for the slab-wise exchange (cudaIpc handles over torch.distributed)
     nloc = sum(ctx.num_local(k) for k in SPECIES)
     ntot_particles = len(SPECIES) * mx * my * mz * ppc if not args.slab_of else nloc
@@ -545,6 +546,8 @@ def run_ours(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     barrier()
+    detail = {"%d/%s" % (ksp, "pred" if ipc else "corr"): {k: round(v / args.steps, 4) for k, v in ctx.phase_detail(ksp, ipc).items() if v > 0.0}
+              for ksp in SPECIES for ipc in (1, 0)}
     phases, _ = ctx.phase_ms(reset=True)
     pt = torch.tensor([phases[k] / args.steps for k in ("prep", "setup", "kernel", "rank_sum", "fold", "kick")], dtype=torch.float64, device=dev)
     if world > 1:
@@ -556,6 +559,12 @@ def run_ours(args):
                           "in deferred mode and overlap the next kernel, so the phases need not add up to ms_per_step)",
                   "max_over_ranks": dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick"), [float(v) for v in pmax])),
                   "min_over_ranks": dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick"), [float(v) for v in pmin]))}
+    if world > 1:      # every rank's own breakdown (species/pass; the rank sum split into strips, push, barrier): who waits for whom
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, {"ms": ms, "detail": detail})
+        phases_rec["per_rank"] = per_rank
+    else:
+        phases_rec["detail"] = detail
     cnt = ctx.counters(reset=True)
     tms = torch.tensor([ms, float(cnt["launches"])], dtype=torch.float64, device=dev)
     if world > 1:
@@ -675,6 +684,13 @@ def run_ours(args):
                     f.truncate(n * 8)
             dist.barrier()
             t = torch.from_file(path, shared=True, size=n, dtype=torch.float64)
+            # first touch: every rank faults in the z block it will deliver, so those pages sit on the NUMA node next to its GPU
+            nz = mz + 4
+            nxy = n // nz
+            e0 = 0 if rank == 0 else mz * rank // world + 2
+            e1 = nz if rank == world - 1 else mz * (rank + 1) // world + 2
+            t[e0 * nxy:e1 * nxy].zero_()
+            dist.barrier()
             rc = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), n * 8, 0)
             if int(rc) != 0:
                 raise RuntimeError("cudaHostRegister failed: %r" % (rc,))
@@ -912,6 +928,7 @@ def main():
                     help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
     ap.add_argument("--peer-push", type=int, default=64, help="N > 1: CTAs of the fused add+push kernel that finishes the slab-wise exchange over NVLink peer memory (0 = ncclAllGather)")
+    ap.add_argument("--peer-push-last", type=int, default=0, help="N > 1: CTAs of that kernel for the last species of the step, whose exchange nothing overlaps (0 = --peer-push)")
     ap.add_argument("--numa-bind", type=int, default=1, help="N > 1: bind each rank to the CPUs next to its GPU before it allocates pinned host arrays")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")

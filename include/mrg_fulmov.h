@@ -301,8 +301,9 @@ int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
  * peers are mapped, a rank finishes the exchange with ONE kernel that adds the
  * neighbour strips into its own block and stores the block into every peer's
  * array over NVLink (instead of ncclAllGather + two ncclBroadcast); option
- * "peer_push" = number of CTAs of that kernel (default 64; 0 keeps the NCCL path).  Ranks must be processes of one node
- * with peer access (NVSwitch); at most 8 ranks.  mrg_peer_pushes counts the
+ * "peer_push" = number of CTAs of that kernel (default 64; 0 keeps the NCCL path); "peer_push_last" = CTAs when the
+ * species is the last of the step (ksp = nspecies), whose exchange no particle kernel overlaps (0 = same as
+ * "peer_push").  Ranks must be processes of one node with peer access (NVSwitch); at most 8 ranks.  mrg_peer_pushes counts the
  * exchanges finished that way.                                               */
 #define MRG_IPC_HANDLE_BYTES 64
 int mrg_peer_export(mrg_ctx* ctx, int32_t ksp, unsigned char handle[MRG_IPC_HANDLE_BYTES]);
@@ -327,6 +328,15 @@ int64_t mrg_peer_pushes(mrg_ctx* ctx, int32_t reset);
 #define MRG_PH_KICK 5
 #define MRG_NPHASE 6
 int mrg_phase_ms(mrg_ctx* ctx, double out[MRG_NPHASE], int64_t* calls, int32_t reset);
+/* The same timers per species and kind of call (ipc = 0 | 1), with the rank sum of an ipc >= 1 call split further:
+ * [MRG_PH_STRIPS] the strips exchanged with the two ring neighbours (ncclSend/ncclRecv; includes waiting for the
+ * neighbours' particle kernels), [MRG_PH_PUSH] the add + push / all-gather of the blocks, [MRG_PH_BARRIER] the
+ * 2-double all-reduce that completes it (waits for the slowest rank).  Sums since the last reset of mrg_phase_ms. */
+#define MRG_PH_STRIPS 6
+#define MRG_PH_PUSH 7
+#define MRG_PH_BARRIER 8
+#define MRG_NPHASE_DETAIL 9
+int mrg_phase_detail(mrg_ctx* ctx, int32_t ksp, int32_t ipc, double out[MRG_NPHASE_DETAIL]);
 
 /* Cheap invariants of the resident state, for callers that want to check a
  * run without a CPU reference (bench.py prints them with every line):

@@ -22,7 +22,7 @@ SYMBOLS = [
     "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_sort", "mrg_set_option",
     "mrg_get_counters", "mrg_last_kernel_ms", "mrg_event_record", "mrg_event_elapsed_ms",
     "mrg_synchronize", "mrg_bind_fields_device", "mrg_renew_fields", "mrg_pass_ms", "mrg_get_prep_stats",
-    "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak", "mrg_set_fields_lazy", "mrg_renew_fields_host", "mrg_phase_ms", "mrg_peer_export", "mrg_peer_import", "mrg_peer_pushes",
+    "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak", "mrg_set_fields_lazy", "mrg_renew_fields_host", "mrg_phase_ms", "mrg_phase_detail", "mrg_peer_export", "mrg_peer_import", "mrg_peer_pushes",
 ]
 
 
@@ -100,6 +100,7 @@ def load(build_if_missing=True):
     L.mrg_self_check.argtypes = [vp, i32, dp, C.POINTER(i64)]
     L.mrg_dfma_peak.argtypes = [vp, dp]
     L.mrg_phase_ms.argtypes = [vp, dp, C.POINTER(i64), i32]
+    L.mrg_phase_detail.argtypes = [vp, i32, i32, dp]
     L.mrg_peer_export.argtypes = [vp, i32, C.c_char_p]
     L.mrg_peer_import.argtypes = [vp, i32, i32, C.c_char_p]
     L.mrg_peer_pushes.argtypes = [vp, i32]

@@ -168,7 +168,6 @@ struct mrg_ctx {
   const double* fhost[12] = {};
   bool flazy[12] = {};
   std::vector<char> fplane[12];
-  double* A6[6] = {};
   double* T1[6] = {};
   double* T2[6] = {};
   double* F6 = nullptr;
@@ -196,6 +195,8 @@ struct mrg_ctx {
   unsigned* slab_bits = nullptr; int* slab_words = nullptr; long long slab_words_cap = 0;
   int* slab_list = nullptr; long long slab_list_cap = 0;
   int* slab_count = nullptr;
+  int* slab_n_host = nullptr;    // pinned landing word of slab_count
+  int num_sms = 148;
   double* h_pinned = nullptr; size_t h_pinned_bytes = 0;
   // nccl
   void* comm = nullptr;
@@ -206,6 +207,7 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_peer_push_last = 0;   // CTAs for the LAST species of a step (nothing overlaps its exchange: the host needs all moments next, F:742-760); 0 = same as peer_push
   int opt_peer_push = 64;   // CTAs of the fused add+push kernel (0 = off): slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
   long long push_count = 0;
   int opt_sink_share = 0;   // deferred D2H of the folded moments copies only this rank's z block (ranks of a node share the host arrays)
@@ -218,9 +220,10 @@ struct mrg_ctx {
   // per-phase device time of the mrg_fulmov calls (option "phases"): event pairs on the stream each phase runs on,
   // read back lazily (a pair is read right before it is recorded again, and by mrg_phase_ms)
   int opt_phases = 0;
-  cudaEvent_t ph_ev[MRG_MAX_SPECIES][2][MRG_NPHASE][2] = {};
-  bool ph_rec[MRG_MAX_SPECIES][2][MRG_NPHASE] = {};
+  cudaEvent_t ph_ev[MRG_MAX_SPECIES][2][MRG_NPHASE_DETAIL][2] = {};
+  bool ph_rec[MRG_MAX_SPECIES][2][MRG_NPHASE_DETAIL] = {};
   double ph_ms[MRG_NPHASE] = {};
+  double ph_detail[MRG_MAX_SPECIES][2][MRG_NPHASE_DETAIL] = {};
   long long ph_calls = 0;
 };
 
@@ -235,7 +238,8 @@ int phase_collect(mrg_ctx* c, int k, int ipc, int ph) {
   CK(cudaEventSynchronize(c->ph_ev[k][ipc][ph][1]));
   float ms = 0.f;
   CK(cudaEventElapsedTime(&ms, c->ph_ev[k][ipc][ph][0], c->ph_ev[k][ipc][ph][1]));
-  c->ph_ms[ph] += ms;
+  if (ph < MRG_NPHASE) c->ph_ms[ph] += ms;
+  c->ph_detail[k][ipc][ph] += ms;
   return MRG_OK;
 }
 struct PhaseScope {      // records begin on construction, end on done(); no-op unless the option is on
@@ -558,6 +562,7 @@ bool compact_eligible(const mrg_ctx* c, const Species& s, double hdt) {
 // the exchange itself, on stream ms; M4 = raw moments [nz planes][nxy][4] + (wkix, wkih)
 int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
   double* M4 = s.M4;
+  const int ks = (int)(&s - c->sp);
   const GP& g = c->g;
   const int N = c->nranks, r = c->rank, L = g.mz / N;
   const size_t P = (size_t)g.nxy * 4;                       // doubles per plane
@@ -568,6 +573,7 @@ int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
   int lay[4];
   compact_layout(g.mz, N, r, lay);
   const size_t send_up = lay[0], send_dn = lay[1], add_lo = lay[2], add_hi = lay[3];   // first plane of each strip
+  PhaseScope ph_strips(c, ks, 1, MRG_PH_STRIPS, ms);
   int n = g_nccl.GroupStart();
   if (!n) n = g_nccl.Send(M4 + send_up * P, cnt, kNcclFloat64, up, c->comm, ms);
   if (!n) n = g_nccl.Send(M4 + send_dn * P, cnt, kNcclFloat64, dn, c->comm, ms);
@@ -575,6 +581,8 @@ int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
   if (!n) n = g_nccl.Recv(c->halo_rx[1], cnt, kNcclFloat64, up, c->comm, ms);   // the upper neighbour's downward strip
   const int e = g_nccl.GroupEnd();
   if (n || e) return fail(MRG_ERR_NCCL, "halo exchange: " + nccl_err(n ? n : e));
+  ph_strips.done();
+  PhaseScope ph_push(c, ks, 1, MRG_PH_PUSH, ms);
   if (s.npeer == N - 1 && c->opt_peer_push) {
     // fused add + push over NVLink peer memory (k_add_push); the allreduce below is the completion barrier
     const size_t e0 = (r == 0) ? 0 : (size_t)(2 + r * L), e1 = (r == N - 1) ? (size_t)g.nz : (size_t)(2 + (r + 1) * L);
@@ -585,7 +593,8 @@ int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
     for (int q = pp.n; q < 8; q++) pp.p[q] = nullptr;
     // a small grid: 64 CTAs keep NVLink busy (fire-and-forget 128-bit peer stores) and leave the SMs to the other species'
     // particle kernel that runs next to this exchange in deferred mode (1184 CTAs cost that kernel 0.6 ms at 8 GPUs, measured)
-    k_add_push<<<std::max(1, c->opt_peer_push), 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp); CKL(c);
+    const int ctas = (ks == c->nspecies - 1 && c->opt_peer_push_last > 0) ? c->opt_peer_push_last : c->opt_peer_push;
+    k_add_push<<<std::max(1, ctas), 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp); CKL(c);
     c->push_count++;
     n = 0;
   } else {
@@ -594,8 +603,11 @@ int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
     if (!n) n = g_nccl.Broadcast(M4, M4, 2 * P, kNcclFloat64, 0, c->comm, ms);
     if (!n) n = g_nccl.Broadcast(M4 + (size_t)(g.mz + 2) * P, M4 + (size_t)(g.mz + 2) * P, 2 * P, kNcclFloat64, N - 1, c->comm, ms);
   }
+  ph_push.done();
+  PhaseScope ph_barrier(c, ks, 1, MRG_PH_BARRIER, ms);
   if (!n) n = g_nccl.AllReduce(M4 + (size_t)g.ntot * 4, M4 + (size_t)g.ntot * 4, 2, kNcclFloat64, kNcclSum, c->comm, ms);
   if (n) return fail(MRG_ERR_NCCL, "slab exchange: " + nccl_err(n));
+  ph_barrier.done();
   return MRG_OK;
 }
 
@@ -688,14 +700,19 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   }
   const long long per = (long long)g.mx * (g.my + 1);
   CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->fcur[k];
-  Ptr6 A, T1, T2; for (int k = 0; k < 6; k++) { A.p[k] = c->A6[k]; T1.p[k] = c->T1[k]; T2.p[k] = c->T2[k]; }
-  k_blend<<<grid_for(per * nB, B), B, 0, c->stream>>>(g, f, A, T1, p->aimpl, 1.0 - p->aimpl, p->bxc, p->byc, p->bzc, dB, nB); CKL(c);
+  Ptr6 T1, T2; for (int k = 0; k < 6; k++) { T1.p[k] = c->T1[k]; T2.p[k] = c->T2[k]; }
+  const double om = 1.0 - p->aimpl;
+  // blend (+ first z sweep) -> remaining sweeps -> finalize (+ last y sweep): three kernels for the usual ifil* = 1
   Ptr6 src = T1, dst = T2;
   auto as_const = [](const Ptr6& q) { CPtr6 r; for (int k = 0; k < 6; k++) r.p[k] = q.p[k]; return r; };
-  for (int n = 0; n < p->ifilz; n++) { k_filter<2><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
+  if (p->ifilz > 0) { k_blend_filter_z<<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, f, src, p->aimpl, om, p->bxc, p->byc, p->bzc, dGI, nGI); CKL(c); }
+  else { k_blend<<<grid_for(per * nB, B), B, 0, c->stream>>>(g, f, src, p->aimpl, om, p->bxc, p->byc, p->bzc, dB, nB); CKL(c); }
+  for (int n = 1; n < p->ifilz; n++) { k_filter<2><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
   for (int n = 0; n < p->ifilx; n++) { k_filter<0><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
-  for (int n = 0; n < p->ifily; n++) { k_filter<1><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
-  k_finalize<<<grid_for((long long)g.nxy * nG, B), B, 0, c->stream>>>(g, as_const(A), as_const(src), c->F6, p->bxc, p->byc, p->bzc, dG, nG); CKL(c);
+  for (int n = 1; n < p->ifily; n++) { k_filter<1><<<grid_for(per * nGI, B), B, 0, c->stream>>>(g, as_const(src), dst, dGI, nGI); CKL(c); std::swap(src, dst); }
+  if (p->ifily > 0) k_finalize<true><<<grid_for((long long)g.nxy * nG, B), B, 0, c->stream>>>(g, f, as_const(src), c->F6, p->aimpl, om, p->bxc, p->byc, p->bzc, dG, nG);
+  else k_finalize<false><<<grid_for((long long)g.nxy * nG, B), B, 0, c->stream>>>(g, f, as_const(src), c->F6, p->aimpl, om, p->bxc, p->byc, p->bzc, dG, nG);
+  CKL(c);
   c->prep_key = key;
   c->prep_valid = true;
   c->prep_full = !restricted;
@@ -782,14 +799,17 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   CK(cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming));
   for (auto& sp : c->sp) CK(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&c->wk_pinned, MRG_MAX_SPECIES * 2 * sizeof(double)));
+  CK(cudaMallocHost((void**)&c->slab_n_host, sizeof(int)));
+  *c->slab_n_host = 0;
+  CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
   for (int k = 0; k < MRG_MAX_SPECIES; k++)
     for (int q = 0; q < 4; q++) CK(cudaEventCreate(&c->pass_ev[k][q >> 1][q & 1]));
   for (int k = 0; k < 8; k++) CK(cudaEventCreate(&c->user_ev[k]));
   const size_t gb = (size_t)ntot * sizeof(double);
   for (int k = 0; k < 12; k++) { CK(cudaMalloc((void**)&c->f12[k], gb)); CK(cudaMemsetAsync(c->f12[k], 0, gb, c->stream)); c->fcur[k] = c->f12[k]; }
   for (int k = 0; k < 6; k++) {
-    CK(cudaMalloc((void**)&c->A6[k], gb)); CK(cudaMalloc((void**)&c->T1[k], gb)); CK(cudaMalloc((void**)&c->T2[k], gb));
-    CK(cudaMemsetAsync(c->A6[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T1[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T2[k], 0, gb, c->stream));
+    CK(cudaMalloc((void**)&c->T1[k], gb)); CK(cudaMalloc((void**)&c->T2[k], gb));
+    CK(cudaMemsetAsync(c->T1[k], 0, gb, c->stream)); CK(cudaMemsetAsync(c->T2[k], 0, gb, c->stream));
   }
   CK(cudaMalloc((void**)&c->F6, gb * 6));
   CK(cudaMalloc((void**)&c->wk2, 3 * sizeof(double)));   // wkix, wkih + the ranks' vote on the slab-wise exchange
@@ -819,7 +839,7 @@ int mrg_destroy(mrg_ctx* c) {
   if (c->cstream) cudaStreamSynchronize(c->cstream);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   for (int k = 0; k < 12; k++) cudaFree(c->f12[k]);
-  for (int k = 0; k < 6; k++) { cudaFree(c->A6[k]); cudaFree(c->T1[k]); cudaFree(c->T2[k]); cudaFree(c->tmp6[k]); }
+  for (int k = 0; k < 6; k++) { cudaFree(c->T1[k]); cudaFree(c->T2[k]); cudaFree(c->tmp6[k]); }
   cudaFree(c->alt[0]);
   cudaFree(c->F6); cudaFree(c->alt_id);
   for (auto& s : c->sp) {
@@ -835,6 +855,7 @@ int mrg_destroy(mrg_ctx* c) {
   cudaFree(c->scan_tiles); cudaFree(c->slab_bits); cudaFree(c->slab_words); cudaFree(c->slab_list); cudaFree(c->slab_count);
   if (c->h_pinned) cudaFreeHost(c->h_pinned);
   if (c->wk_pinned) cudaFreeHost(c->wk_pinned);
+  if (c->slab_n_host) cudaFreeHost(c->slab_n_host);
   cudaFree(c->plane_lists);
   if (c->ev_kernel) cudaEventDestroy(c->ev_kernel);
   if (c->cstream) cudaStreamDestroy(c->cstream);
@@ -843,7 +864,7 @@ int mrg_destroy(mrg_ctx* c) {
   for (int k = 0; k < 8; k++) cudaEventDestroy(c->user_ev[k]);
   for (int k = 0; k < MRG_MAX_SPECIES; k++)
     for (int i = 0; i < 2; i++)
-      for (int ph = 0; ph < MRG_NPHASE; ph++)
+      for (int ph = 0; ph < MRG_NPHASE_DETAIL; ph++)
         for (int e = 0; e < 2; e++) if (c->ph_ev[k][i][ph][e]) cudaEventDestroy(c->ph_ev[k][i][ph][e]);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -1247,7 +1268,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     CK(cudaMemcpyAsync(wk_host, s.M4 + (size_t)g.ntot * 4, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   } else {
-    int slab_n = 0;
+    bool slab_pending = false;
     if (pp.drive_on && !ranfb) return fail(MRG_ERR_ARG, "ranfb state pointer is required when the drive kick is on");
     {
       const bool want = c->opt_kick == 1 || (c->opt_kick < 0 && c->opt_shard == 1 && (c->nranks > 1 || c->opt_slab_n > 1));
@@ -1355,18 +1376,18 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
     if (pp.kick_inline) {
       *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)s.n);   // every particle owns one draw of the call
     } else if (pp.drive_on && s.n > 0) {
-      CK(cudaMemcpyAsync(&slab_n, c->slab_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-      CK(cudaStreamSynchronize(c->stream));
-      if (slab_n > 0) {
-        const long long nwords = (s.n + 31) / 32 + 1;
-        k_popc<<<grid_for(nwords, 256), 256, 0, c->stream>>>(c->slab_bits, nwords, c->slab_words); CKL(c);
-        rc = scan_excl(c, c->slab_words, c->slab_words, nwords, nullptr);
-        if (rc) return rc;
-        k_kick<<<grid_for(slab_n, 256), 256, 0, c->stream>>>(g, soa(s), c->F6, c->slab_bits, c->slab_words, c->slab_list,
-                                                              c->slab_count, (unsigned)*ranfb, p->Ez00, p->ycent1,
-                                                              p->ycent2, 0.05 * g.ymax, c->lcg_tab); CKL(c);
-        *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)slab_n);
-      }
+      // the chain runs without knowing the slab count on the host (no synchronize between the corrector and the
+      // kick): k_kick reads it on the device and strides over the list; the host reads it with wk below
+      const long long nwords = (s.n + 31) / 32 + 1;
+      k_popc<<<grid_for(nwords, 256), 256, 0, c->stream>>>(c->slab_bits, nwords, c->slab_words); CKL(c);
+      rc = scan_excl(c, c->slab_words, c->slab_words, nwords, nullptr);
+      if (rc) return rc;
+      const int kick_blocks = (int)std::min<long long>(grid_for(s.n, 256), 8LL * c->num_sms);
+      k_kick<<<kick_blocks, 256, 0, c->stream>>>(g, soa(s), c->F6, c->slab_bits, c->slab_words, c->slab_list,
+                                                 c->slab_count, (unsigned)*ranfb, p->Ez00, p->ycent1,
+                                                 p->ycent2, 0.05 * g.ymax, c->lcg_tab); CKL(c);
+      CK(cudaMemcpyAsync(c->slab_n_host, c->slab_count, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+      slab_pending = true;
     }
     ph_kick.done();
     PhaseScope ph_sum(c, ksp - 1, 0, MRG_PH_SUM, c->stream);
@@ -1390,6 +1411,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
       CK(cudaStreamSynchronize(c->stream));
     }
     wk_host[0] = wk3[0]; wk_host[1] = wk3[1];
+    if (slab_pending) *ranfb = (int32_t)lcg_skip((unsigned)*ranfb, (unsigned long long)*c->slab_n_host);
     if (fused_scatter) kocc_finish(c, s);   // planes of the order the particles are in now
   }
   c->pass_timed[ksp - 1][ipc != 0] = s.n > 0;
@@ -1577,6 +1599,9 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
   } else if (n == "peer_push") {
     if (value < 0 || value > 4096) return fail(MRG_ERR_ARG, "peer_push must be 0 (ncclAllGather) or the number of CTAs of the push kernel");
     c->opt_peer_push = (int)value;
+  } else if (n == "peer_push_last") {
+    if (value < 0 || value > 4096) return fail(MRG_ERR_ARG, "peer_push_last must be 0 (= peer_push) or the number of CTAs of the push kernel of the last species");
+    c->opt_peer_push_last = (int)value;
   } else if (n == "phases") {
     c->opt_phases = value != 0;
   } else if (n == "sink_share") {
@@ -1743,10 +1768,25 @@ int mrg_phase_ms(mrg_ctx* c, double out[MRG_NPHASE], int64_t* calls, int32_t res
   CK(cudaSetDevice(c->device));
   for (int k = 0; k < MRG_MAX_SPECIES; k++)
     for (int i = 0; i < 2; i++)
-      for (int ph = 0; ph < MRG_NPHASE; ph++) { int rc = phase_collect(c, k, i, ph); if (rc) return rc; }
+      for (int ph = 0; ph < MRG_NPHASE_DETAIL; ph++) { int rc = phase_collect(c, k, i, ph); if (rc) return rc; }
   for (int ph = 0; ph < MRG_NPHASE; ph++) out[ph] = c->ph_ms[ph];
   if (calls) *calls = c->ph_calls;
-  if (reset) { for (int ph = 0; ph < MRG_NPHASE; ph++) c->ph_ms[ph] = 0.0; c->ph_calls = 0; }
+  if (reset) {
+    for (int ph = 0; ph < MRG_NPHASE; ph++) c->ph_ms[ph] = 0.0;
+    memset(c->ph_detail, 0, sizeof(c->ph_detail));
+    c->ph_calls = 0;
+  }
+  return MRG_OK;
+}
+
+int mrg_phase_detail(mrg_ctx* c, int32_t ksp, int32_t ipc, double out[MRG_NPHASE_DETAIL]) {
+  int rc = check_species(c, ksp);
+  if (rc) return rc;
+  if (!out) return fail(MRG_ERR_ARG, "null argument");
+  CK(cudaSetDevice(c->device));
+  const int i = ipc != 0;
+  for (int ph = 0; ph < MRG_NPHASE_DETAIL; ph++) { rc = phase_collect(c, ksp - 1, i, ph); if (rc) return rc; }
+  for (int ph = 0; ph < MRG_NPHASE_DETAIL; ph++) out[ph] = c->ph_detail[ksp - 1][i][ph];
   return MRG_OK;
 }
 

@@ -63,24 +63,66 @@ __device__ __forceinline__ bool interior_ijk(const GP& g, long long t, const int
   return true;
 }
 
-// F:1127-1139: A = aimpl*f + (1-aimpl)*f0 (+dc for B); then F:7351-7359: T = A - dc.
-__global__ void k_blend(GP g, CPtr12 f, Ptr6 A, Ptr6 T, double aimpl, double om, double bxc, double byc, double bzc,
+// F:1127-1139: A = aimpl*f + (1-aimpl)*f0 (+dc for B); then F:7351-7359: T = A - dc.  A itself is only needed on the
+// few nodes whose periodic images are ghosts (k_finalize), which recompute it, so no kernel stores it.
+__device__ __forceinline__ double blend_A(const CPtr12& f, int c, int m, double aimpl, double om, double dcc) {
+  double a = __dadd_rn(__dmul_rn(aimpl, f.p[c][m]), __dmul_rn(om, f.p[c + 6][m]));
+  if (c >= 3) a = __dadd_rn(a, dcc);
+  return a;
+}
+__device__ __forceinline__ double filter5(double a0, double a1, double a2, double a3, double a4) {   // source order of the sum
+  double t = __dmul_rn(-0.0625, a0);
+  t = __dadd_rn(t, __dmul_rn(0.25, a1));
+  t = __dadd_rn(t, __dmul_rn(0.625, a2));
+  t = __dadd_rn(t, __dmul_rn(0.25, a3));
+  return __dsub_rn(t, __dmul_rn(0.0625, a4));
+}
+__global__ void k_blend(GP g, CPtr12 f, Ptr6 T, double aimpl, double om, double bxc, double byc, double bzc,
                         const int* __restrict__ planes, int nplanes) {
   int i, j, k;
   if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, planes, nplanes, i, j, k)) return;
   const int m = node_of(g, i, j, k);
   const double dc[6] = {0.0, 0.0, 0.0, bxc, byc, bzc};
 #pragma unroll
+  for (int c = 0; c < 6; c++) T.p[c][m] = __dsub_rn(blend_A(f, c, m, aimpl, om, dc[c]), dc[c]);
+}
+// the blend fused with the first z sweep (F:7365-7395): the five planes of T are blended on the fly (they sit in L2
+// between neighbouring planes of the launch), so neither A nor the unfiltered T is written
+__global__ void k_blend_filter_z(GP g, CPtr12 f, Ptr6 D, double aimpl, double om, double bxc, double byc, double bzc,
+                                 const int* __restrict__ planes, int nplanes) {
+  int i, j, k;
+  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, planes, nplanes, i, j, k)) return;
+  const int kr = (k == g.mz - 1) ? 0 : k + 1, kl = (k == 0) ? g.mz - 1 : k - 1;
+  const int krr = (kr == g.mz - 1) ? 0 : kr + 1, kll = (kl == 0) ? g.mz - 1 : kl - 1;
+  const int m = node_of(g, i, j, k);
+  const int m0 = node_of(g, i, j, krr), m1 = node_of(g, i, j, kr), m3 = node_of(g, i, j, kl), m4 = node_of(g, i, j, kll);
+  const double dc[6] = {0.0, 0.0, 0.0, bxc, byc, bzc};
+#pragma unroll
   for (int c = 0; c < 6; c++) {
-    double a = __dadd_rn(__dmul_rn(aimpl, f.p[c][m]), __dmul_rn(om, f.p[c + 6][m]));
-    if (c >= 3) a = __dadd_rn(a, dc[c]);
-    A.p[c][m] = a;
-    T.p[c][m] = __dsub_rn(a, dc[c]);
+    const double a0 = __dsub_rn(blend_A(f, c, m0, aimpl, om, dc[c]), dc[c]);
+    const double a1 = __dsub_rn(blend_A(f, c, m1, aimpl, om, dc[c]), dc[c]);
+    const double a2 = __dsub_rn(blend_A(f, c, m, aimpl, om, dc[c]), dc[c]);
+    const double a3 = __dsub_rn(blend_A(f, c, m3, aimpl, om, dc[c]), dc[c]);
+    const double a4 = __dsub_rn(blend_A(f, c, m4, aimpl, om, dc[c]), dc[c]);
+    D.p[c][m] = filter5(a0, a1, a2, a3, a4);
   }
 }
 
 // One (-1,4,10,4,-1)/16 sweep, F:7365-7395 (AXIS=2, z), F:7401-7434 (AXIS=0, x),
 // F:7438-7492 (AXIS=1, y with wall mirror rows; rows j=0 and j=my are copied).
+// y sweep of one node (F:7438-7492): rows j = 0 and j = my are copied; mirror rows a(-1) = sg*e(1), a(my+1) = sg*e(my-1)
+// (F:7455-7471): the E call has sym=-1 (F:1144), the B call sym=+1 (F:1147); the y component takes -sym.
+__device__ __forceinline__ double filter_y(const GP& g, const double* __restrict__ s, int c, int i, int j, int k, int m) {
+  if (j < 1 || j > g.my - 1) return s[m];
+  const double sg = ((c < 3) ? -1.0 : 1.0) * ((c % 3 == 1) ? -1.0 : 1.0);
+  const int jp2 = j + 2, jm2 = j - 2;
+  const double a0 = (jp2 == g.my + 1) ? sg * s[node_of(g, i, g.my - 1, k)] : s[node_of(g, i, jp2, k)];
+  const double a1 = s[node_of(g, i, j + 1, k)];
+  const double a2 = s[m];
+  const double a3 = s[node_of(g, i, j - 1, k)];
+  const double a4 = (jm2 == -1) ? sg * s[node_of(g, i, 1, k)] : s[node_of(g, i, jm2, k)];
+  return filter5(a0, a1, a2, a3, a4);
+}
 template <int AXIS>
 __global__ void k_filter(GP g, CPtr6 S, Ptr6 D, const int* __restrict__ planes, int nplanes) {
   int i, j, k;
@@ -101,24 +143,10 @@ __global__ void k_filter(GP g, CPtr6 S, Ptr6 D, const int* __restrict__ planes, 
       a0 = s[node_of(g, ill, j, k)]; a1 = s[node_of(g, il, j, k)]; a2 = s[m];
       a3 = s[node_of(g, ir, j, k)]; a4 = s[node_of(g, irr, j, k)];
     } else {
-      if (j < 1 || j > g.my - 1) { D.p[c][m] = s[m]; continue; }
-      // mirror rows a(-1) = sg*e(1), a(my+1) = sg*e(my-1)  (F:7455-7471): the
-      // E call has sym=-1 (F:1144), the B call sym=+1 (F:1147); the y
-      // component takes -sym.
-      const double sg = ((c < 3) ? -1.0 : 1.0) * ((c % 3 == 1) ? -1.0 : 1.0);
-      const int jp2 = j + 2, jm2 = j - 2;
-      a0 = (jp2 == g.my + 1) ? sg * s[node_of(g, i, g.my - 1, k)] : s[node_of(g, i, jp2, k)];
-      a1 = s[node_of(g, i, j + 1, k)];
-      a2 = s[m];
-      a3 = s[node_of(g, i, j - 1, k)];
-      a4 = (jm2 == -1) ? sg * s[node_of(g, i, 1, k)] : s[node_of(g, i, jm2, k)];
+      D.p[c][m] = filter_y(g, s, c, i, j, k, m);
+      continue;
     }
-    double t = __dmul_rn(-0.0625, a0);
-    t = __dadd_rn(t, __dmul_rn(0.25, a1));
-    t = __dadd_rn(t, __dmul_rn(0.625, a2));
-    t = __dadd_rn(t, __dmul_rn(0.25, a3));
-    t = __dsub_rn(t, __dmul_rn(0.0625, a4));
-    D.p[c][m] = t;
+    D.p[c][m] = filter5(a0, a1, a2, a3, a4);
   }
 }
 
@@ -131,8 +159,10 @@ __global__ void k_filter(GP g, CPtr6 S, Ptr6 D, const int* __restrict__ planes, 
 // with NaN, so a gather that strays beyond the prepared planes cannot pass
 // unnoticed.
 constexpr int PLANE_GUARD = 1 << 30;
-__global__ void k_finalize(GP g, CPtr6 A, CPtr6 T, double* __restrict__ F6, double bxc, double byc, double bzc,
-                           const int* __restrict__ planes, int nplanes) {
+// FY: the last y sweep (F:7438-7492) is done here instead of in a pass of its own: T then holds the sweep's input
+template <bool FY>
+__global__ void k_finalize(GP g, CPtr12 f, CPtr6 T, double* __restrict__ F6, double aimpl, double om, double bxc, double byc,
+                           double bzc, const int* __restrict__ planes, int nplanes) {
   long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (t >= (long long)g.nxy * nplanes) return;
   bool guard = false;
@@ -152,7 +182,7 @@ __global__ void k_finalize(GP g, CPtr6 A, CPtr6 T, double* __restrict__ F6, doub
     for (int c = 0; c < 6; c++) out[c] = __longlong_as_double(0x7ff8000000000000ll);
   } else if (in) {
 #pragma unroll
-    for (int c = 0; c < 6; c++) out[c] = __dadd_rn(T.p[c][t], dc[c]);
+    for (int c = 0; c < 6; c++) out[c] = __dadd_rn(FY ? filter_y(g, T.p[c], c, i, j, k, (int)t) : T.p[c][t], dc[c]);
   } else if (j < 0 || j > g.my) {
 #pragma unroll
     for (int c = 0; c < 6; c++) out[c] = 0.0;
@@ -161,7 +191,7 @@ __global__ void k_finalize(GP g, CPtr6 A, CPtr6 T, double* __restrict__ F6, doub
     const int ks = k < 0 ? k + g.mz : (k >= g.mz ? k - g.mz : k);
     const int m = node_of(g, is, j, ks);
 #pragma unroll
-    for (int c = 0; c < 6; c++) out[c] = A.p[c][m];
+    for (int c = 0; c < 6; c++) out[c] = blend_A(f, c, m, aimpl, om, dc[c]);
   }
   double2* o = reinterpret_cast<double2*>(F6) + t * 3;
   o[0] = make_double2(out[0], out[1]);
@@ -681,22 +711,23 @@ __global__ void k_kick(GP g, ParticleSoA P, const double* __restrict__ F6, const
                        const int* __restrict__ word_off, const int* __restrict__ slab_list,
                        const int* __restrict__ slab_count, unsigned state0, double Ez00, double ycent1,
                        double ycent2, double yw2, const unsigned* __restrict__ lcg_tab) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= *slab_count) return;
-  const int slot = slab_list[e];
-  const int id = P.id ? P.id[slot] : slot;
-  const unsigned w = bits[id >> 5];
-  const int rank = word_off[id >> 5] + __popc(w & ((1u << (id & 31)) - 1u));
-  const unsigned ir = (lcg_pow_tab(lcg_tab, (unsigned long long)rank + 1ull) * state0) & 0x7fffffffu;   // = lcg_skip(state0, rank + 1)
-  const double u = (double)ir * (1.0 / 2147483648.0);     // F:9302
-  if (u > 0.999) {                                          // F:1353
-    const double x = P.x[slot], y = P.y[slot], z = P.z[slot];
-    int ip, jp, kp;
-    cell_of(g, x, y, z, ip, jp, kp);                        // F:1347-1349
-    const double bxa = F6[(size_t)node_of(g, ip, jp, kp) * 6 + 3];
-    const double vy0 = __ddiv_rn(Ez00, bxa);                // F:1354
-    if (fabs(y - ycent2) < yw2) P.vy[slot] = __dsub_rn(P.vy[slot], vy0);
-    else if (fabs(y - ycent1) < yw2) P.vy[slot] = __dadd_rn(P.vy[slot], vy0);
+  const int count = *slab_count;   // read on the device: the host sizes the grid without knowing it
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < count; e += gridDim.x * blockDim.x) {
+    const int slot = slab_list[e];
+    const int id = P.id ? P.id[slot] : slot;
+    const unsigned w = bits[id >> 5];
+    const int rank = word_off[id >> 5] + __popc(w & ((1u << (id & 31)) - 1u));
+    const unsigned ir = (lcg_pow_tab(lcg_tab, (unsigned long long)rank + 1ull) * state0) & 0x7fffffffu;   // = lcg_skip(state0, rank + 1)
+    const double u = (double)ir * (1.0 / 2147483648.0);     // F:9302
+    if (u > 0.999) {                                          // F:1353
+      const double x = P.x[slot], y = P.y[slot], z = P.z[slot];
+      int ip, jp, kp;
+      cell_of(g, x, y, z, ip, jp, kp);                        // F:1347-1349
+      const double bxa = F6[(size_t)node_of(g, ip, jp, kp) * 6 + 3];
+      const double vy0 = __ddiv_rn(Ez00, bxa);                // F:1354
+      if (fabs(y - ycent2) < yw2) P.vy[slot] = __dsub_rn(P.vy[slot], vy0);
+      else if (fabs(y - ycent1) < yw2) P.vy[slot] = __dadd_rn(P.vy[slot], vy0);
+    }
   }
 }
 

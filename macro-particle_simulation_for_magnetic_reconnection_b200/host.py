@@ -254,6 +254,12 @@ class MrgContext:
         check(self.lib.mrg_phase_ms(self.h, out, C.byref(calls), 1 if reset else 0))
         return dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick"), out)), calls.value
 
+    def phase_detail(self, ksp, ipc):
+        """the same timers for one species and kind of call; the rank sum of ipc >= 1 calls split into strips / push / barrier"""
+        out = (C.c_double * 9)()
+        check(self.lib.mrg_phase_detail(self.h, ksp, ipc, out))
+        return dict(zip(("prep", "setup", "kernel", "rank_sum", "fold", "kick", "strips", "push", "barrier"), out))
+
     def dfma_peak(self):
         v = C.c_double()
         check(self.lib.mrg_dfma_peak(self.h, C.byref(v)))
