@@ -928,7 +928,7 @@ def main():
                     help="development aid: hold z slab I of the N-GPU job's load and grid on ONE GPU (no NCCL); implies --no-e2e")
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
     ap.add_argument("--peer-push", type=int, default=64, help="N > 1: CTAs of the fused add+push kernel that finishes the slab-wise exchange over NVLink peer memory (0 = ncclAllGather)")
-    ap.add_argument("--peer-push-last", type=int, default=0, help="N > 1: CTAs of that kernel for the last species of the step, whose exchange nothing overlaps (0 = --peer-push)")
+    ap.add_argument("--peer-push-last", type=int, default=296, help="N > 1: CTAs of that kernel for the last species of the step, whose exchange nothing overlaps (0 = --peer-push)")
     ap.add_argument("--numa-bind", type=int, default=1, help="N > 1: bind each rank to the CPUs next to its GPU before it allocates pinned host arrays")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")

@@ -302,7 +302,7 @@ int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
  * neighbour strips into its own block and stores the block into every peer's
  * array over NVLink (instead of ncclAllGather + two ncclBroadcast); option
  * "peer_push" = number of CTAs of that kernel (default 64; 0 keeps the NCCL path); "peer_push_last" = CTAs when the
- * species is the last of the step (ksp = nspecies), whose exchange no particle kernel overlaps (0 = same as
+ * species is the last of the step (ksp = nspecies), whose exchange no particle kernel overlaps (default 296; 0 = same as
  * "peer_push").  Ranks must be processes of one node with peer access (NVSwitch); at most 8 ranks.  mrg_peer_pushes counts the
  * exchanges finished that way.                                               */
 #define MRG_IPC_HANDLE_BYTES 64

@@ -207,7 +207,7 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
-  int opt_peer_push_last = 0;   // CTAs for the LAST species of a step (nothing overlaps its exchange: the host needs all moments next, F:742-760); 0 = same as peer_push
+  int opt_peer_push_last = 296; // CTAs for the LAST species of a step (nothing overlaps its exchange: emfild reads all moments next, F:762-771); 0 = same as peer_push
   int opt_peer_push = 64;   // CTAs of the fused add+push kernel (0 = off): slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
   long long push_count = 0;
   int opt_sink_share = 0;   // deferred D2H of the folded moments copies only this rank's z block (ranks of a node share the host arrays)
