@@ -288,14 +288,14 @@ def workload_config(n, args):
 
 def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
     """Small parity pass on ALL ranks of this job before the timed loop (so that a scaling record carries 2/4/8-rank
-    evidence): 16 x 12 x 16N grid, 8 ppc, two steps, both particle partitions.  Checker = the CPU oracle on rank 0
+    evidence): 16 x 12 x 32N grid, 8 ppc, two steps, both particle partitions.  Checker = the CPU oracle on rank 0
     (pinned bit for bit to the reference's own fulmov, tests/test_ref_pin.py); it is not on any measured path.
       roundrobin  the reference's partition and its serial per-rank kick streams: summed folded moments of step 1 and
                   step 2 (step 2 sees the corrector and the kick of step 1) against the oracle run as N ranks;
       slab        z-slab ownership, slab-wise exchange when the ranks agree: the same with the drive off (that
                   ownership has no reference kick stream)."""
     from oracle import pyoracle as O
-    mx, my, mz, ppc = 16, 12, 16 * world, 8
+    mx, my, mz, ppc = 16, 12, 32 * world, 8
     out = {}
     for part in ("roundrobin", "slab"):
         p = O.make_parm(mx, my, mz, HX * mx, HY * my, HZ * mz, DT, AIMPL, WCE, EZ00 if part == "roundrobin" else 0.0)
@@ -303,6 +303,7 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
         ctx.comm_init(mrg.broadcast_unique_id(rank, device=dev))
         ctx.set_option("shard", 1 if part == "slab" else 0)
         if part == "slab":
+            ctx.set_option("defer", 1)
             ctx.map_peers(2, device=dev)
         par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
         st = 7331
@@ -325,8 +326,11 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
             ctx.set_fields(fa)
             if rank == 0:
                 a6 = O.field_prep(p, fa)
+            if part == "slab":       # both predictor calls queued before any moment is read, as in the timed loop
+                wkd = [ctx.fulmov_deferred(ksp, QSPEC[ksp], WSPEC[ksp], par) for ksp in (1, 2)]   # filled when the moments are read
             for ksp in (1, 2):
-                ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, par, st)
+                if part != "slab":
+                    ctx.fulmov(ksp, QSPEC[ksp], WSPEC[ksp], 1, par, st)
                 mom = ctx.moments(ksp)
                 if rank == 0:
                     r = O.fulmov(p, a6, *sp[ksp], QSPEC[ksp], WSPEC[ksp], 1, nranks=nr)
@@ -341,6 +345,7 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
                     O.fulmov(p, a6, *sp[ksp], QSPEC[ksp], WSPEC[ksp], 0, nranks=nr, ranfb=sto)
         stats = ctx.prep_stats()
         pushes = ctx.peer_pushes()
+        splits = ctx.split_pushes()
         rng_ok = True
         if part == "roundrobin":          # every rank's ranfp state after the reference-order kicks
             t = torch.tensor([float(st)], dtype=torch.float64, device=dev)
@@ -352,7 +357,7 @@ def multi_rank_parity(mrg, dist, torch, rank, world, local, dev):
         if rank == 0:
             out[part] = {"moments_rel_l2_step1": max(errs[:2]), "moments_rel_l2_step2": max(errs[2:]),
                          "ok": bool(max(errs) < 1e-10 and rng_ok), "ranks": world, "grid": [mx, my, mz], "ppc": ppc,
-                         "slabwise_sums": int(stats["compact_sums"]), "peer_pushes": int(pushes), "ranfp_states_equal_reference": bool(rng_ok) if part == "roundrobin" else None}
+                         "slabwise_sums": int(stats["compact_sums"]), "peer_pushes": int(pushes), "split_launches": int(splits), "ranfp_states_equal_reference": bool(rng_ok) if part == "roundrobin" else None}
         dist.barrier()
     return out
 
@@ -484,6 +489,7 @@ def run_ours(args):
     if world > 1 and args.peer_push:
         ctx.set_option("peer_push", args.peer_push)
         ctx.set_option("peer_push_last", args.peer_push_last)
+        ctx.set_option("split_push", args.split_push)
         ctx.map_peers(len(SPECIES), device=dev)          # NVLink peer memory for the slab-wise exchange (cudaIpc handles over torch.distributed)
     nloc = sum(ctx.num_local(k) for k in SPECIES)
     ntot_particles = len(SPECIES) * mx * my * mz * ppc if not args.slab_of else nloc
@@ -806,6 +812,7 @@ def run_ours(args):
 
     prep_stats = ctx.prep_stats()
     prep_stats["peer_pushes"] = int(ctx.peer_pushes())
+    prep_stats["split_launches"] = int(ctx.split_pushes())
     refpart = None
     if world > 1 and args.shard == "slab" and not args.slab_of and not args.no_reference_partition:
         ctx.close()
@@ -824,9 +831,10 @@ def run_ours(args):
         cfg["prep"] = prep_stats
         cfg["rank_sum"] = ("none (1 GPU)" if world == 1 else
                            "%d of %d moment sums went through the slab-wise exchange (%d of them finished by the fused add+push kernel over "
-                           "NVLink peer memory, the others by ncclAllGather), the rest through ncclAllReduce"
+                           "NVLink peer memory -- %d of those after a split launch that pushed part of the block under the rest of the "
+                           "particle kernel -- the others by ncclAllGather), the rest through ncclAllReduce"
                            % (cfg["prep"]["compact_sums"], len(SPECIES) * (args.steps + args.warmup + (e2e["steps"] + 1 if e2e else 0)),
-                              cfg["prep"]["peer_pushes"]))
+                              cfg["prep"]["peer_pushes"], cfg["prep"]["split_launches"]))
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if args.config == 5 else "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "roofline": roofline, "cpu_baseline": cpu,
@@ -929,6 +937,7 @@ def main():
     ap.add_argument("--hints", type=int, default=1, help="e2e leg: 1 = the host marks which members of COMMON /fields/ it changed")
     ap.add_argument("--peer-push", type=int, default=64, help="N > 1: CTAs of the fused add+push kernel that finishes the slab-wise exchange over NVLink peer memory (0 = ncclAllGather)")
     ap.add_argument("--peer-push-last", type=int, default=296, help="N > 1: CTAs of that kernel for the last species of the step, whose exchange nothing overlaps (0 = --peer-push)")
+    ap.add_argument("--split-push", type=int, default=1, help="N > 1: 1 = the last species' predictor runs as two launches and the planes final after the first are pushed to the peers under the second (0 = off, 2 = every species)")
     ap.add_argument("--numa-bind", type=int, default=1, help="N > 1: bind each rank to the CPUs next to its GPU before it allocates pinned host arrays")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")

@@ -309,6 +309,12 @@ int mrg_event_elapsed_ms(mrg_ctx* ctx, int32_t a, int32_t b, double* ms);
 int mrg_peer_export(mrg_ctx* ctx, int32_t ksp, unsigned char handle[MRG_IPC_HANDLE_BYTES]);
 int mrg_peer_import(mrg_ctx* ctx, int32_t ksp, int32_t rank, const unsigned char handle[MRG_IPC_HANDLE_BYTES]);
 int64_t mrg_peer_pushes(mrg_ctx* ctx, int32_t reset);
+/* Option "split_push" (default 1 = last species of the step, 2 = every species, 0 = off): in deferred mode with mapped
+ * peers the tiled predictor of such a call runs as two launches (the pencils of the first three quarters of the rank's z
+ * block, then the rest); the planes of the block no later pencil and no neighbour strip can touch are pushed to the peers
+ * while the second launch runs, the fused add+push kernel after it sends the remainder.  Needs the order of the fused
+ * sort (pencil = gather cell).  mrg_split_pushes counts the calls that did it.                                       */
+int64_t mrg_split_pushes(mrg_ctx* ctx, int32_t reset);
 
 /* Device time of the phases of the mrg_fulmov calls since the last reset, in
  * milliseconds, measured with CUDA events on the stream each phase runs on

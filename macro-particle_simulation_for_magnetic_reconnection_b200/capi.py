@@ -22,7 +22,7 @@ SYMBOLS = [
     "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_sort", "mrg_set_option",
     "mrg_get_counters", "mrg_last_kernel_ms", "mrg_event_record", "mrg_event_elapsed_ms",
     "mrg_synchronize", "mrg_bind_fields_device", "mrg_renew_fields", "mrg_pass_ms", "mrg_get_prep_stats",
-    "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak", "mrg_set_fields_lazy", "mrg_renew_fields_host", "mrg_phase_ms", "mrg_phase_detail", "mrg_peer_export", "mrg_peer_import", "mrg_peer_pushes",
+    "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak", "mrg_set_fields_lazy", "mrg_renew_fields_host", "mrg_phase_ms", "mrg_phase_detail", "mrg_peer_export", "mrg_peer_import", "mrg_peer_pushes", "mrg_split_pushes",
 ]
 
 
@@ -105,9 +105,11 @@ def load(build_if_missing=True):
     L.mrg_peer_import.argtypes = [vp, i32, i32, C.c_char_p]
     L.mrg_peer_pushes.argtypes = [vp, i32]
     L.mrg_peer_pushes.restype = i64
+    L.mrg_split_pushes.argtypes = [vp, i32]
+    L.mrg_split_pushes.restype = i64
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("mrg_last_error", "mrg_build_info", "mrg_num_local", "mrg_peer_pushes"):
+        if name not in ("mrg_last_error", "mrg_build_info", "mrg_num_local", "mrg_peer_pushes", "mrg_split_pushes"):
             fn.restype = C.c_int
     _lib = L
     return L

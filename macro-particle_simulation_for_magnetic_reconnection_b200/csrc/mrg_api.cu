@@ -98,6 +98,7 @@ struct Species {
   double* M4 = nullptr;    // raw moments [ntot][4] + 2 (wkix, wkih)
   double* peerM4[8] = {};  // the other ranks' M4 of this species, mapped through cudaIpc (mrg_peer_import); nullptr = not mapped
   int npeer = 0;
+  int early0 = 0, early_n = 0;   // extended planes of the own block already pushed to the peers by the split launch of this call
   double* out4[4] = {nullptr, nullptr, nullptr, nullptr};  // folded, reference layout
   bool have_moments = false;
   // cell index of the current slot order (built by mrg_sort): cell_end[c] = end slot of cell c
@@ -207,9 +208,12 @@ struct mrg_ctx {
   int opt_deposit = 2, opt_iters = 8, opt_group_min = 2, opt_tile = 1, opt_fused_keys = 1, opt_fused_sort = 1, opt_shard = 0;
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
+  int opt_split_push = 1;       // 0 = off, 1 = last species of the step, 2 = every species: particle kernel in two launches, the planes final after the first are pushed under the second
+  cudaEvent_t ev_split = nullptr;
   int opt_peer_push_last = 296; // CTAs for the LAST species of a step (nothing overlaps its exchange: emfild reads all moments next, F:762-771); 0 = same as peer_push
   int opt_peer_push = 64;   // CTAs of the fused add+push kernel (0 = off): slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
   long long push_count = 0;
+  long long split_count = 0;
   int opt_sink_share = 0;   // deferred D2H of the folded moments copies only this rank's z block (ranks of a node share the host arrays)
   int opt_kick = -1;     // drive-kick draws: -1 = by particle index when "shard" = 1 (no reference stream exists), else the reference's serial order; 0 / 1 force
   int opt_compact = -1;  // slab-wise moment exchange instead of the whole-grid allreduce: -1 = when possible, 0 = never
@@ -594,7 +598,8 @@ int compact_sum(mrg_ctx* c, Species& s, cudaStream_t ms) {
     // a small grid: 64 CTAs keep NVLink busy (fire-and-forget 128-bit peer stores) and leave the SMs to the other species'
     // particle kernel that runs next to this exchange in deferred mode (1184 CTAs cost that kernel 0.6 ms at 8 GPUs, measured)
     const int ctas = (ks == c->nspecies - 1 && c->opt_peer_push_last > 0) ? c->opt_peer_push_last : c->opt_peer_push;
-    k_add_push<<<std::max(1, ctas), 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp); CKL(c);
+    k_add_push<<<std::max(1, ctas), 256, 0, ms>>>(M4, e0 * P, (e1 - e0) * P, add_lo * P, c->halo_rx[0], add_hi * P, c->halo_rx[1], cnt, pp,
+                                                  (size_t)s.early0 * P, (size_t)s.early_n * P); CKL(c);
     c->push_count++;
     n = 0;
   } else {
@@ -797,6 +802,7 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
     CK(cudaStreamCreateWithPriority(&c->cstream, cudaStreamNonBlocking, hi));   // the moment sum must not queue behind particle CTAs
   }
   CK(cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_split, cudaEventDisableTiming));
   for (auto& sp : c->sp) CK(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&c->wk_pinned, MRG_MAX_SPECIES * 2 * sizeof(double)));
   CK(cudaMallocHost((void**)&c->slab_n_host, sizeof(int)));
@@ -858,6 +864,7 @@ int mrg_destroy(mrg_ctx* c) {
   if (c->slab_n_host) cudaFreeHost(c->slab_n_host);
   cudaFree(c->plane_lists);
   if (c->ev_kernel) cudaEventDestroy(c->ev_kernel);
+  if (c->ev_split) cudaEventDestroy(c->ev_split);
   if (c->cstream) cudaStreamDestroy(c->cstream);
   for (int k = 0; k < MRG_MAX_SPECIES; k++)
     for (int q = 0; q < 4; q++) if (c->pass_ev[k][q >> 1][q & 1]) cudaEventDestroy(c->pass_ev[k][q >> 1][q & 1]);
@@ -1141,6 +1148,7 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
 
   if (ipc >= 1) {
     PhaseScope ph_setup(c, ksp - 1, 1, MRG_PH_SETUP, c->stream);
+    s.early0 = 0; s.early_n = 0;
     if (c->nranks > 1 && s.compact_ok && compact_possible(c)) {
       // slab-wise exchange ahead: this rank deposits only into its own block and the two strips it sends, every other
       // plane is overwritten by the peers' blocks -- and must not be touched here once peers push into it
@@ -1187,7 +1195,40 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
         CUtensorMap tmP;
         rc = particle_map(s.d[0], s.cap, &tmP);
         if (rc) return rc;
-        k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(gl, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+        // Split launch: with the slab-wise exchange ahead and nothing else to hide it under (last species of the step), the
+        // pencils of the first three quarters of the block run first; the planes of the block that are final after them --
+        // no pencil of the rest deposits within 2 planes, no neighbour strip lands there -- are pushed to the peers on the
+        // communication stream while the last quarter runs (a pencil is a tile of GATHER cells, so this needs the fresh
+        // order of the fused sort; |vz| dt < hz is the precondition of the exchange itself)
+        int nA = 0;
+        const bool exch = c->nranks > 1 && s.compact_ok && compact_possible(c);
+        if (exch && c->opt_defer && c->opt_peer_push && s.npeer == c->nranks - 1 && s.hull_valid && s.fresh && s.fresh_lookahead == p->hdt &&
+            (c->opt_split_push == 2 || (c->opt_split_push == 1 && ksp == c->nspecies))) {
+          const int L = g.mz / c->nranks, lo = c->rank * L, split = lo + (3 * L) / 4;
+          const int na = ((split - gl.kz0) % g.mz + g.mz) % g.mz;
+          const int e_lo = lo + HALO_PLANES, e_hi = std::min(split - 2, lo + L - HALO_PLANES);
+          if (na > 0 && na < gl.nkz && e_hi > e_lo) { nA = na; s.early0 = e_lo + 2; s.early_n = e_hi - e_lo; }
+        }
+        if (nA) {
+          GP ga = gl, gb = gl;
+          ga.nkz = nA;
+          gb.kz0 = (gl.kz0 + nA) % g.mz; gb.nkz = gl.nkz - nA;
+          const int per_plane = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my;
+          k_predict_tile<<<per_plane * ga.nkz, B, PRED_SMEM_BYTES, c->stream>>>(ga, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist); CKL(c);
+          CK(cudaEventRecord(c->ev_split, c->stream));
+          k_predict_tile<<<per_plane * gb.nkz, B, PRED_SMEM_BYTES, c->stream>>>(gb, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+          CK(cudaStreamWaitEvent(c->cstream, c->ev_split, 0));
+          PeerPtrs peers;
+          peers.n = 0;
+          for (int q = 0; q < c->nranks; q++)
+            if (q != c->rank) peers.p[peers.n++] = s.peerM4[q];
+          for (int q = peers.n; q < 8; q++) peers.p[q] = nullptr;
+          const size_t PL = (size_t)g.nxy * 4;
+          k_add_push<<<std::max(1, c->opt_peer_push), 256, 0, c->cstream>>>(s.M4, (size_t)s.early0 * PL, (size_t)s.early_n * PL, 0, nullptr, 0, nullptr, 0, peers, 0, 0); CKL(c);
+          c->split_count++;
+        } else {
+          k_predict_tile<<<blocks, B, PRED_SMEM_BYTES, c->stream>>>(gl, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+        }
         s.prekeys_valid = prekey != nullptr;
         s.keys_valid = false;
         s.prescan_valid = false;
@@ -1599,6 +1640,9 @@ int mrg_set_option(mrg_ctx* c, const char* name, int64_t value) {
   } else if (n == "peer_push") {
     if (value < 0 || value > 4096) return fail(MRG_ERR_ARG, "peer_push must be 0 (ncclAllGather) or the number of CTAs of the push kernel");
     c->opt_peer_push = (int)value;
+  } else if (n == "split_push") {
+    if (value < 0 || value > 2) return fail(MRG_ERR_ARG, "split_push must be 0 (off), 1 (last species of the step) or 2 (every species)");
+    c->opt_split_push = (int)value;
   } else if (n == "peer_push_last") {
     if (value < 0 || value > 4096) return fail(MRG_ERR_ARG, "peer_push_last must be 0 (= peer_push) or the number of CTAs of the push kernel of the last species");
     c->opt_peer_push_last = (int)value;
@@ -1823,6 +1867,13 @@ int64_t mrg_peer_pushes(mrg_ctx* c, int32_t reset) {
   if (!c) return -1;
   const long long v = c->push_count;
   if (reset) c->push_count = 0;
+  return v;
+}
+
+int64_t mrg_split_pushes(mrg_ctx* c, int32_t reset) {
+  if (!c) return -1;
+  const long long v = c->split_count;
+  if (reset) c->split_count = 0;
   return v;
 }
 

@@ -215,11 +215,15 @@ __global__ void k_add_strips(double* __restrict__ lo, const double* __restrict__
 // [lo0, lo0 + strip) and [hi0, hi0 + strip) lie inside it.  The 2-double allreduce that follows on the same stream is the
 // barrier that tells every rank all blocks have landed.
 struct PeerPtrs { double* p[8]; int n; };
+// [hole0, hole0 + hole_cnt) inside the block is left out: an earlier launch of this kernel (strip = 0) already pushed it
+// while the last part of the particle kernel was still running (split launch, mrg_api.cu)
 __global__ void __launch_bounds__(256) k_add_push(double* __restrict__ M4, size_t g0, size_t cnt, size_t lo0, const double* __restrict__ rx_lo,
-                                                  size_t hi0, const double* __restrict__ rx_hi, size_t strip, PeerPtrs peers) {
-  const size_t n2 = cnt >> 1;
+                                                  size_t hi0, const double* __restrict__ rx_hi, size_t strip, PeerPtrs peers,
+                                                  size_t hole0, size_t hole_cnt) {
+  const size_t n2 = (cnt - hole_cnt) >> 1;
   for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n2; t += (size_t)gridDim.x * blockDim.x) {
-    const size_t g = g0 + 2 * t;
+    size_t g = g0 + 2 * t;
+    if (g >= hole0) g += hole_cnt;
     double2 v = *reinterpret_cast<const double2*>(M4 + g);
     bool changed = false;
     if (g - lo0 < strip) { const double2 a = *reinterpret_cast<const double2*>(rx_lo + (g - lo0)); v.x += a.x; v.y += a.y; changed = true; }

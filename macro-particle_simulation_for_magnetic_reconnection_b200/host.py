@@ -130,6 +130,10 @@ class MrgContext:
     def peer_pushes(self, reset=False):
         return self.lib.mrg_peer_pushes(self.h, 1 if reset else 0)
 
+    def split_pushes(self, reset=False):
+        """predictor calls that ran as a split launch with an early partial push (option split_push)"""
+        return self.lib.mrg_split_pushes(self.h, 1 if reset else 0)
+
     # -- particles ---------------------------------------------------------
     def upload(self, ksp, x, y, z, vx, vy, vz, first=1, stride=1):
         check(self.lib.mrg_upload_particles(self.h, ksp, *[as_dp(a) for a in (x, y, z, vx, vy, vz)],

@@ -101,7 +101,7 @@ def _worker_slab(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         uid = mrg.broadcast_unique_id(rank)
-        p = U.make_parm(12, 8, max(48, 16 * world), Ez00=0.0)   # Ez00 = 0: the kick draws its random numbers but changes nothing,
+        p = U.make_parm(12, 8, 32 * world, Ez00=0.0)   # Ez00 = 0: the kick draws its random numbers but changes nothing,
         ppc = 8                                    # so the particles do not depend on which rank owns them (Q4)
         sp, ranfb = U.load_species(p, ppc)
         npr = len(sp[1][0])
@@ -144,9 +144,11 @@ def _worker_slab(rank, world, port, q):
         stats = ctx.prep_stats()
         # every preparation restricted to the slab; after the first step (where the ranks vote) the moments of
         # both species are summed slab-wise (halo strips + in-place allgather) instead of by a whole-grid allreduce
-        ok = int(stats["restricted"] == stats["preps"] == 4 and stats["compact_sums"] == 2 and ctx.peer_pushes() == 2)
+        # ... and the electrons' predictor of step 2 (last species, fresh order) ran as a split launch whose first part's
+        # planes were pushed to the peers while the second part was still depositing
+        ok = int(stats["restricted"] == stats["preps"] == 4 and stats["compact_sums"] == 2 and ctx.peer_pushes() == 2 and ctx.split_pushes() == 1)
         if not ok:
-            print("rank", rank, stats)
+            print("rank", rank, stats, ctx.peer_pushes(), ctx.split_pushes())
         ctx.close()
         q.put((rank, max(errs), ok))
     finally:
