@@ -209,7 +209,8 @@ struct mrg_ctx {
   int opt_planes = -1;   // restricted field preparation: -1 = when nranks > 1, 0 = never, 1 = always
   int opt_defer = 0;
   int opt_split_push = 1;       // 0 = off, 1 = last species of the step, 2 = every species: particle kernel in two launches, the planes final after the first are pushed under the second
-  cudaEvent_t ev_split = nullptr;
+  cudaEvent_t ev_split = nullptr, ev_split_pre = nullptr, ev_split_b = nullptr;
+  cudaStream_t sstream = nullptr;   // second launch of a split predictor
   int opt_peer_push_last = 296; // CTAs for the LAST species of a step (nothing overlaps its exchange: emfild reads all moments next, F:762-771); 0 = same as peer_push
   int opt_peer_push = 64;   // CTAs of the fused add+push kernel (0 = off): slab-wise exchange pushes the finished block into the peers' arrays over NVLink (when mapped) instead of ncclAllGather
   long long push_count = 0;
@@ -803,6 +804,9 @@ int mrg_create(mrg_ctx** out, int32_t mx, int32_t my, int32_t mz, double xmax, d
   }
   CK(cudaEventCreateWithFlags(&c->ev_kernel, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_split, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_split_pre, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_split_b, cudaEventDisableTiming));
+  CK(cudaStreamCreateWithFlags(&c->sstream, cudaStreamNonBlocking));
   for (auto& sp : c->sp) CK(cudaEventCreateWithFlags(&sp.done, cudaEventDisableTiming));
   CK(cudaMallocHost((void**)&c->wk_pinned, MRG_MAX_SPECIES * 2 * sizeof(double)));
   CK(cudaMallocHost((void**)&c->slab_n_host, sizeof(int)));
@@ -865,6 +869,9 @@ int mrg_destroy(mrg_ctx* c) {
   cudaFree(c->plane_lists);
   if (c->ev_kernel) cudaEventDestroy(c->ev_kernel);
   if (c->ev_split) cudaEventDestroy(c->ev_split);
+  if (c->ev_split_pre) cudaEventDestroy(c->ev_split_pre);
+  if (c->ev_split_b) cudaEventDestroy(c->ev_split_b);
+  if (c->sstream) cudaStreamDestroy(c->sstream);
   if (c->cstream) cudaStreamDestroy(c->cstream);
   for (int k = 0; k < MRG_MAX_SPECIES; k++)
     for (int q = 0; q < 4; q++) if (c->pass_ev[k][q >> 1][q & 1]) cudaEventDestroy(c->pass_ev[k][q >> 1][q & 1]);
@@ -1214,9 +1221,15 @@ int mrg_fulmov(mrg_ctx* c, int32_t ksp, double qmult, double wmult, int32_t ipc,
           ga.nkz = nA;
           gb.kz0 = (gl.kz0 + nA) % g.mz; gb.nkz = gl.nkz - nA;
           const int per_plane = ((g.mx + TILE_CELLS - 1) / TILE_CELLS) * g.my;
+          // the second launch goes to a side stream right behind the first: no dependency between them, so its CTAs fill the
+          // SMs as the first launch drains (in one stream the drain + ramp-up bubble cost more than the early push saved)
+          CK(cudaEventRecord(c->ev_split_pre, c->stream));
+          CK(cudaStreamWaitEvent(c->sstream, c->ev_split_pre, 0));
           k_predict_tile<<<per_plane * ga.nkz, B, PRED_SMEM_BYTES, c->stream>>>(ga, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist); CKL(c);
           CK(cudaEventRecord(c->ev_split, c->stream));
-          k_predict_tile<<<per_plane * gb.nkz, B, PRED_SMEM_BYTES, c->stream>>>(gb, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+          k_predict_tile<<<per_plane * gb.nkz, B, PRED_SMEM_BYTES, c->sstream>>>(gb, pp, tmP, c->F6, s.M4, s.cell_end, c->wk_partial, gm, prekey, s.hist);
+          CK(cudaEventRecord(c->ev_split_b, c->sstream));
+          CK(cudaStreamWaitEvent(c->stream, c->ev_split_b, 0));
           CK(cudaStreamWaitEvent(c->cstream, c->ev_split, 0));
           PeerPtrs peers;
           peers.n = 0;
