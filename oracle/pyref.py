@@ -188,6 +188,39 @@ FIELD_NAMES = ("ex", "ey", "ez", "bx", "by", "bz", "ex0", "ey0", "ez0", "bx0", "
 MOMENT_NAMES = {1: ("qix", "qiy", "qiz", "qi"), 2: ("qex", "qey", "qez", "qe")}
 
 
+def reference_startup(grid, box, nranks=1, qspec=(1.0, -1.0), wspec=(100.0, 1.0), dt=1.2, aimpl=0.6, wce_by_wpe=0.2, Ez00=0.25e-2):
+    """The reference's own start-up (F:664-706): init (tables, constants, loadpt of both species at 32 per cell), then the
+    it = 0 block of trans -- dt = adt = hdt = 0, fulmov(ipc=1) for ions and electrons, emfld0 (static B by Ampere's law from
+    the accumulated moments + Poisson solve, F:3384-3703, 6596-7304) -- executed by `nranks` simulated ranks.  Returns the
+    particles as init left them, the it = 0 moments and wkix/wkih, and the twelve COMMON /fields/ arrays emfld0 defined: the
+    reference's own initial condition, for parity cases on real fields instead of synthetic ones."""
+    mx, my, mz = grid
+    np0 = 32 * mx * my * mz
+    with RefRun(mx, my, mz, np0, nranks=nranks) as R:
+        setup_run(R, box[0], box[1], box[2], dt=dt, aimpl=aimpl, wce_by_wpe=wce_by_wpe, Ez00=Ez00, qspec=qspec, wspec=wspec)
+        parts, npr, _ = ref_init(R)
+        ranfb = int(R.get("ranfb", "ir", unit="ranfp"))
+        particles = {k: [parts[0][k][c][:npr].copy() for c in range(6)] for k in (1, 2)}
+        sav = {nm: float(R.get("parm2", nm, unit="fulmov")) for nm in ("dt", "adt", "hdt")}
+        for nm in sav:                                                             # F:673-679
+            R.set("parm2", nm, 0.0, unit="fulmov")
+        R.set("parm1", "it", 0, unit="fulmov")
+        mom, wk = {}, {}
+        for k in (1, 2):                                                           # F:684-689
+            xs = [[parts[r][k][c] for r in range(nranks)] for c in range(6)]
+            R.call("fulmov", *xs, float(qspec[k - 1]), float(wspec[k - 1]), npr, 1, k, IPAR, SIZE)
+            mom[k] = [R.get("srimp7", nm, unit="fulmov") for nm in MOMENT_NAMES[k]]
+            wk[k] = (float(R.get("wkinel", "wkix", unit="fulmov")), float(R.get("wkinel", "wkih", unit="fulmov")))
+        R.call("emfld0")                                                           # F:694
+        for nm, v in sav.items():                                                  # F:700-702
+            R.set("parm2", nm, v, unit="fulmov")
+        fields = [R.get("fields", nm, unit="fulmov") for nm in FIELD_NAMES]
+        same = all(np.array_equal(R.get("fields", nm, rank=r, unit="fulmov"), f) for r in range(1, nranks) for nm, f in zip(FIELD_NAMES, fields))
+        unmoved = all(np.array_equal(parts[0][k][c][:npr], particles[k][c]) for k in (1, 2) for c in range(6))
+    return {"particles": particles, "npr": npr, "ranfb": ranfb, "mom0": mom, "wk0": wk, "fields": fields,
+            "ranks_agree": bool(same), "particles_unmoved": bool(unmoved)}
+
+
 def reference_steps(grid, box, particles, field_sets, nranks=1, ranfb_in=None, qspec=(1.0, -1.0), wspec=(100.0, 1.0),
                     dt=1.2, aimpl=0.6, wce_by_wpe=0.2, Ez00=0.25e-2, nha=5, it0=1):
     """The reference's own call sequence of trans (F:749-807) around the particle path, with the field solve replaced by

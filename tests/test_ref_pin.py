@@ -167,3 +167,54 @@ def test_oracle_reproduces_reference_golden(name):
         np.testing.assert_array_equal(np.stack([a[::sample] for a in orc["final"][k]]), G["out_%d" % k])
         np.testing.assert_array_equal(digest(orc["final"][k]), G["out_sha_%d" % k])     # every particle, not only the sample
     assert orc["ranfb"] == [int(v) for v in G["ranfb_out"]]
+
+
+# ---- the reference's own initial condition: init, the it = 0 moment pass, emfld0 (F:664-706) -------------------------------
+def startup_inputs(G):
+    grid = tuple(int(v) for v in G["grid"])
+    p = U.make_parm(*grid)
+    p0 = U.make_parm(*grid, dt=0.0)                      # F:673-679: dt = adt = hdt = 0 for the it = 0 pair of calls
+    sp, ranfb = U.load_species(p, int(G["ppc"][0]))      # init's loader, pinned above
+    return p, p0, sp, ranfb, [np.ascontiguousarray(f) for f in G["fields"]]
+
+
+def test_oracle_reproduces_reference_startup_golden():
+    """it = 0: fulmov with dt = 0 accumulates the moments emfld0 solves from; then one full step on the fields the
+    reference's emfld0 defined -- all of it reference output (tests/golden/ref_startup_2r.npz), reproduced bit for bit"""
+    G = np.load(os.path.join(GOLD, "ref_startup_2r.npz"))
+    p, p0, sp, ranfb, f12 = startup_inputs(G)
+    nranks, sample = int(G["nranks"][0]), int(G["sample"][0])
+    assert ranfb == int(G["ranfb_in"][0])
+    for k in (1, 2):
+        np.testing.assert_array_equal(digest(sp[k]), G["in_sha_%d" % k])
+    a6 = O.field_prep(p0, [np.zeros(O.mxyzA(p)) for _ in range(12)])      # COMMON /fields/ is still zero at it = 0
+    for k in (1, 2):
+        arrs = [a.copy() for a in sp[k]]
+        r = O.fulmov(p0, a6, *arrs, U.QSPEC[k], U.WSPEC[k], 1, nranks=nranks)
+        np.testing.assert_array_equal(np.stack(r["mom"]), G["mom0_%d" % k])
+        np.testing.assert_array_equal(np.array([r["wkix"], r["wkih"]]), G["wk0_%d" % k])
+        for a, b in zip(arrs, sp[k]):
+            np.testing.assert_array_equal(a, b)              # ipc = 1 moves nothing
+    orc = RC.oracle_steps(p, sp, ranfb, [(f12, f12)], nranks)
+    for k in (1, 2):
+        np.testing.assert_array_equal(np.stack(orc["mom"][0][k]), G["mom_0_%d" % k])
+        wk = list(orc["wk_pred"][0][k]) + list(orc["wk_corr"][0][k])
+        np.testing.assert_array_equal(np.array(wk), G["wk_0_%d" % k])
+        np.testing.assert_array_equal(np.stack([a[::sample] for a in orc["final"][k]]), G["out_%d" % k])
+        np.testing.assert_array_equal(digest(orc["final"][k]), G["out_sha_%d" % k])
+    assert orc["ranfb"] == [int(v) for v in G["ranfb_out"]]
+
+
+@needs_ref
+def test_reference_startup_is_what_the_golden_holds():
+    """the fixture is regenerated live from /root/reference: init + it = 0 pass + emfld0 by 2 simulated ranks"""
+    G = np.load(os.path.join(GOLD, "ref_startup_2r.npz"))
+    grid = tuple(int(v) for v in G["grid"])
+    S = PR.reference_startup(grid, tuple(float(v) for v in G["box"]), nranks=int(G["nranks"][0]))
+    assert S["ranks_agree"] and S["particles_unmoved"] and S["ranfb"] == int(G["ranfb_in"][0])
+    np.testing.assert_array_equal(np.stack(S["fields"]), G["fields"])
+    f = G["fields"]
+    assert np.all(f[:3] == 0.0) and np.abs(f[3:6]).max() > 1e-3          # emfld0: no E at t = 0, B from Ampere's law (F:3384-3390)
+    np.testing.assert_array_equal(f[6:], f[:6])                           # ex0..bz0 = ex..bz
+    for k in (1, 2):
+        np.testing.assert_array_equal(np.stack(S["mom0"][k]), G["mom0_%d" % k])
