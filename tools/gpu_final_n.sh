@@ -7,7 +7,7 @@ nvidia-smi -L > gpurun_out/${tag}_box.txt; nproc >> gpurun_out/${tag}_box.txt; f
 P=$((29500 + RANDOM % 400))
 run() { name=$1; shift; timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $P bench.py --gpus $N "$@" > gpurun_out/${tag}_bench_$name.log 2>&1; P=$((P+1)); }
 run default --steps 20 --warmup 5 --no-reference-partition
-run nosplit --steps 20 --warmup 5 --split-push 0 --no-e2e --no-rank-parity --no-reference-partition
+[ -z "$NOSPLIT_OFF" ] && run nosplit --steps 20 --warmup 5 --split-push 0 --no-e2e --no-rank-parity --no-reference-partition
 python - "$tag" <<'PY'
 import glob, json, sys
 for f in sorted(glob.glob("gpurun_out/%s_bench_*.log" % sys.argv[1])):
