@@ -115,6 +115,15 @@
           integer(C_INT) :: mrg_host_set_unique_id
           character(kind=C_CHAR) :: id(128)
         end function mrg_host_set_unique_id
+!
+!   A rank that stops alone leaves its peers inside NCCL / MPI: register a
+!   routine that calls mpi_abort; the shim calls it instead of exit.
+!     call mrg_host_set_abort (c_funloc(my_abort))   ! subroutine my_abort(code) bind(C); integer(C_INT),value :: code
+        subroutine mrg_host_set_abort (fn) &
+                     bind(C,name='mrg_host_set_abort')
+          import :: C_FUNPTR
+          type(C_FUNPTR),value :: fn
+        end subroutine mrg_host_set_abort
       end interface
 !
       end module mrg_gpu
