@@ -385,6 +385,7 @@ class Unit:
         self.sym = {}
         self.order = []           # declaration order of symbols
         self.commons = []         # list of (block, [names]) in declaration order
+        self.equiv = {}           # alias -> owner (EQUIVALENCE of local arrays from their first elements)
         self.entries = []         # (name, args) of ENTRY statements
 
 
@@ -447,6 +448,17 @@ class Translator:
         for u in split_units(stmts):
             if u.kind in ("subroutine", "function"):
                 self.units[u.name] = u
+        # ENTRY without arguments (`entry prefld` inside emfild, F:3820): a callable name that jumps into its host unit
+        self.entry_host = {}
+        for u in list(self.units.values()):
+            if u.kind != "subroutine":
+                continue
+            for n, label, t in u.stmts:
+                m = re.match(r"^entry\s+([a-z_][a-z0-9_]*)\s*(\(\s*\))?$", t)
+                if m and m.group(1) not in self.units:
+                    e = Unit("subroutine", m.group(1), [], None, n)
+                    self.units[e.name] = e
+                    self.entry_host[e.name] = u.name
         self.want = list(want)
         self.param_globals = {}      # name -> (type, value AST) of every PARAMETER seen in include files (emitted once)
         self.param_order = []
@@ -567,7 +579,25 @@ class Translator:
                     self.sym(u, nme).save = True
             return True
         if s.startswith("equivalence"):
-            raise SyntaxError("EQUIVALENCE is not supported: %r" % s)
+            # the one form the reference uses on the path: local arrays of one type overlaid from their first elements,
+            # equivalence (w0(1),w1(1,1)) -- the later names become aliases of the first
+            rest = s[len("equivalence"):].strip()
+            while rest:
+                if not rest.startswith("("):
+                    raise SyntaxError("EQUIVALENCE form is not supported: %r" % s)
+                j = match_paren(rest, 0)
+                ents = split_top(rest[1:j])
+                rest = rest[j + 1:].lstrip().lstrip(",").lstrip()
+                names = []
+                for ent in ents:
+                    ent = ent.strip()
+                    mm = re.match(r"^([a-z_][a-z0-9_]*)\s*(\((.*)\))?$", ent)
+                    if not mm or (mm.group(3) and any(x.strip() != "1" for x in mm.group(3).split(","))):
+                        raise SyntaxError("EQUIVALENCE with an offset is not supported: %r" % s)
+                    names.append(mm.group(1))
+                for nme in names[1:]:
+                    u.equiv[nme] = names[0]
+            return True
         if s.startswith("data "):
             # data name/value/ [, name/value/ ...]  (scalars only)
             for mm in re.finditer(r"([a-z_][a-z0-9_]*)\s*/\s*([^/]+)/", s[5:]):
@@ -908,7 +938,19 @@ class Translator:
                 params.append("void *%s" % self.cvar(a))
             else:
                 params.append("%s *%s" % (CTYPE[s.type], self.cvar(a)))
-        L.append("%s %s_f(%s)" % (rett, u.name, ", ".join(params) if params else "void"))
+        hosted = [e for e, h in self.entry_host.items() if h == u.name]
+        if hosted:
+            # wrappers first (the first line of the text is the unit's prototype): every callable name enters one body
+            # function with a selector; an entry without arguments passes null dummies
+            proto = "void %s_body(int ENTRY_SEL_%s)" % (u.name, "".join(", " + q for q in params))
+            L.append("%s %s_f(%s)" % (rett, u.name, ", ".join(params) if params else "void"))
+            L.append("{ %s; %s_body(0%s); }" % (proto, u.name, "".join(", " + self.cvar(a) for a in u.args)))
+            for k, e in enumerate(hosted):
+                L.append("void %s_f(void)" % e)
+                L.append("{ %s; %s_body(%d%s); }" % (proto, u.name, k + 1, ", 0" * len(u.args)))
+            L.append(proto)
+        else:
+            L.append("%s %s_f(%s)" % (rett, u.name, ", ".join(params) if params else "void"))
         L.append("{")
         # local parameters (not the run-time ones, not the globals)
         for name in u.order:
@@ -936,6 +978,7 @@ class Translator:
             L.append("  (void)CMO_%s;" % blk)
         # dummies with dimensions, locals
         frees = []
+        aliases = []
         for name in u.order:
             s = u.sym[name]
             if s.is_char or s.kind in ("param", "common"):
@@ -945,6 +988,13 @@ class Translator:
                     self.emit_dims(u, s, L, ctx)
                 continue
             ct = CTYPE[s.type]
+            if name in u.equiv:                  # storage-associated with an earlier local: same base address
+                own = u.sym[u.equiv[name]]
+                if own.kind in ("param", "common", "dummy") or own.type != s.type or not s.dims or not own.dims or own.name in u.equiv:
+                    raise SyntaxError("EQUIVALENCE (%s,%s): only same-type local arrays are supported" % (own.name, name))
+                self.emit_dims(u, s, L, ctx)
+                aliases.append("  %s *%s = %s;" % (ct, self.cvar(name), self.cvar(own.name)))
+                continue
             if s.dims:
                 cnt = self.emit_dims(u, s, L, ctx)
                 if s.save:
@@ -959,6 +1009,9 @@ class Translator:
                     L.append("  static __thread %s %s = %s;" % (ct, self.cvar(name), init))
                 else:
                     L.append("  %s %s = 0;" % (ct, self.cvar(name)))
+        L.extend(aliases)
+        for k, e in enumerate(hosted):
+            L.append("  if (ENTRY_SEL_ == %d) goto L_entry_%s;" % (k + 1, e))
         # executable part
         for idx in range(body_start, len(u.stmts)):
             n, label, s = u.stmts[idx]
@@ -1182,6 +1235,12 @@ class Translator:
                     self.emit_actual(u, args[3], None, 3, ctx), self.emit_expr(u, args[4], ctx), self.emit_expr(u, args[2], ctx)))
             elif name == "mpi_barrier":
                 L.append("  ref_mpi_barrier();")
+            elif name in ("mpi_isend", "mpi_irecv"):      # (buf, count, datatype, peer, tag, comm, request, ierror)
+                L.append("  ref_%s(%s, %s, %s, %s, %s);" % (
+                    name, self.emit_actual(u, args[0], None, 0, ctx), self.emit_expr(u, args[1], ctx), self.emit_expr(u, args[2], ctx),
+                    self.emit_expr(u, args[3], ctx), self.emit_actual(u, args[6], None, 6, ctx)))
+            elif name == "mpi_wait":                       # (request, status, ierror)
+                L.append("  ref_mpi_wait(%s);" % self.emit_actual(u, args[0], None, 0, ctx))
             else:
                 raise SyntaxError("MPI call %s is not supported" % name)
             return
@@ -1232,12 +1291,19 @@ class Translator:
         # transitive closure of the wanted units
         done, todo, bodies = set(), list(self.want), {}
         order = []
+        entries = []
         while todo:
             name = todo.pop(0)
             if name in done:
                 continue
             if name not in self.units:
                 raise SyntaxError("unit %r not found in %s" % (name, self.path))
+            if name in self.entry_host:          # translated with (and emitted by) its host unit
+                done.add(name)
+                entries.append(name)
+                if self.entry_host[name] not in done:
+                    todo.append(self.entry_host[name])
+                continue
             done.add(name)
             before = set(self.externals)
             u = self.units[name]
@@ -1293,6 +1359,9 @@ class Translator:
             u = self.units[name]
             body = bodies[name]
             out.append(body.split("\n", 1)[0] + ";")
+            for e, h in self.entry_host.items():
+                if h == name:
+                    out.append("void %s_f(void);" % e)
         # block sizes and member lookup: every unit's view, evaluated with the current parameters
         out.append(self.emit_block_tables(order))
         for name in order:
@@ -1306,6 +1375,9 @@ class Translator:
         for name in order:
             u = self.units[name]
             out.append("  {\"%s\", (void*)%s_f, %d, %d}," % (name, name, len(u.args), (RANK[u.sym[u.name].type] if u.kind == "function" else 0)))
+        for e in self.entry_host:
+            if self.entry_host[e] in order:
+                out.append("  {\"%s\", (void*)%s_f, 0, 0}," % (e, e))
         out.append("  {0, 0, 0, 0}};")
         return "\n".join(out) + "\n"
 

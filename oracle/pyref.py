@@ -279,3 +279,129 @@ def reference_steps(grid, box, particles, field_sets, nranks=1, ranfb_in=None, q
         out["edec"] = R.get("parm2", "edec", unit="fulmov")
         out["consts"] = {nm: float(R.get("parm2", nm, unit="fulmov")) for nm in ("hxi", "hyi", "hzi", "xmaxe", "zmaxe", "adt", "hdt", "bxc")}
     return out
+
+
+class ReferenceLoop:
+    """The reference's time cycle (trans, F:664-807) driven from Python around the translated units, by `nranks` >= 2
+    simulated ranks (the field solver's halo exchange needs a neighbour, F:6411-6501):
+
+        startup()                        init, the it = 0 moment pass with dt = 0, emfld0, renewal          F:664-706, 796-807
+        per step:  begin_step()          it = it + 1; prefld (B predicted from the last E)                 F:749-759
+                   fulmov(1)             the reference's own particle path, ions then electrons ...        F:761-766
+                   emfild()              implicit field solve: emcoef, cfpsol, bcgstb, wwstb*, sendrev*     F:771
+                   fulmov(0)             ... or any other particle path in their place (set_moments)       F:781-786
+                   renew()               ex0 <- ex ...                                                     F:796-807
+    What `program` sets up before trans is restated here as data: the namelist values (setup_run), the index tables of
+    COMMON /array1d/ (F:318-331) and the solver's block ranges np1, np2, nz1, nz2 (F:294-300).  The particle path is
+    pluggable: fulmov() runs the reference's; a test may instead compute the moments elsewhere (C oracle, CUDA) from
+    fields() and hand them to set_moments(), which is how a drop-in replacement of fulmov is exercised against the
+    reference's own field solver."""
+
+    def __init__(self, grid, box, nranks=2, qspec=(1.0, -1.0), wspec=(100.0, 1.0), dt=1.2, aimpl=0.6, wce_by_wpe=0.2,
+                 Ez00=0.25e-2, itermx=1, iterfx=150, itersx=150):
+        if nranks < 2:
+            raise ValueError("the reference's field solver exchanges halos with a neighbour rank: nranks >= 2")
+        mx, my, mz = grid
+        if mz % nranks:
+            raise ValueError("mz must be a multiple of the number of ranks (kd = mz/npc, param_080A.h)")
+        self.grid, self.nranks, self.qspec, self.wspec = grid, nranks, qspec, wspec
+        self.R = R = RefRun(mx, my, mz, 32 * mx * my * mz, nranks=nranks)
+        setup_run(R, box[0], box[1], box[2], dt=dt, aimpl=aimpl, wce_by_wpe=wce_by_wpe, Ez00=Ez00, qspec=qspec, wspec=wspec)
+        for nm, v in (("itermx", itermx), ("iterfx", iterfx), ("itersx", itersx)):      # rec_3d80A
+            R.set("parm1", nm, v, unit="fulmov")
+        self.parts, self.npr, _ = ref_init(R)
+        kk, jj, ii = np.meshgrid(np.arange(mz), np.arange(my + 1), np.arange(mx), indexing="ij")      # F:318-331
+        for r in range(nranks):
+            R.arr("array1d", "arrayx", r, "emfild")[:] = ii.ravel()
+            R.arr("array1d", "arrayy", r, "emfild")[:] = jj.ravel()
+            R.arr("array1d", "arrayz", r, "emfild")[:] = kk.ravel()
+        kd = mz // nranks                                                                             # F:294-300
+        self.np1 = np.array([k * 3 * mx * (my + 1) * kd + 1 for k in range(nranks)], dtype=np.int32)
+        self.np2 = np.array([(k + 1) * 3 * mx * (my + 1) * kd for k in range(nranks)], dtype=np.int32)
+        self.nz1 = np.array([k * kd + 1 for k in range(nranks)], dtype=np.int32)
+        self.nz2 = np.array([(k + 1) * kd for k in range(nranks)], dtype=np.int32)
+        self.it = 0
+
+    def close(self):
+        self.R.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state ---------------------------------------------------------------------------------------
+    def scalar(self, name):
+        return float(self.R.get("parm2", name, unit="fulmov"))
+
+    def ranfb(self):
+        return [int(self.R.get("ranfb", "ir", rank=r, unit="ranfp")) for r in range(self.nranks)]
+
+    def fields(self, rank=0):
+        return [self.R.get("fields", nm, rank=rank, unit="fulmov") for nm in FIELD_NAMES]
+
+    def ranks_agree(self):
+        f0 = self.fields(0)
+        return all(np.array_equal(a, b) for r in range(1, self.nranks) for a, b in zip(f0, self.fields(r)))
+
+    def moments(self, ksp):
+        return [self.R.get("srimp7", nm, unit="fulmov") for nm in MOMENT_NAMES[ksp]]
+
+    def set_moments(self, ksp, mom4):
+        """the summed, folded moments of one species into every rank's COMMON /srimp7/ (what fulmov leaves, F:1377-1386)"""
+        for nm, a in zip(MOMENT_NAMES[ksp], mom4):
+            self.R.set("srimp7", nm, a, unit="fulmov")
+
+    def particles(self):
+        """{ksp: [x,y,z,vx,vy,vz]} with every rank's owned subset l = rank+1, rank+1+N, ... merged (F:1162)"""
+        n, N = self.npr, self.nranks
+        out = {}
+        for k in (1, 2):
+            out[k] = [np.empty(n) for _ in range(6)]
+            for r in range(N):
+                for c in range(6):
+                    out[k][c][r::N] = self.parts[r][k][c][:n][r::N]
+        return out
+
+    # -- the cycle -----------------------------------------------------------------------------------
+    def fulmov(self, ipc):
+        R, N = self.R, self.nranks
+        wk = {}
+        for k in (1, 2):
+            xs = [[self.parts[r][k][c] for r in range(N)] for c in range(6)]
+            R.call("fulmov", *xs, float(self.qspec[k - 1]), float(self.wspec[k - 1]), self.npr, ipc, k, IPAR, SIZE)
+            wk[k] = (float(R.get("wkinel", "wkix", unit="fulmov")), float(R.get("wkinel", "wkih", unit="fulmov")))
+        return wk
+
+    def renew(self):
+        mx, my, mz = self.grid
+        for r in range(self.nranks):
+            for a, b in zip(FIELD_NAMES[:6], FIELD_NAMES[6:]):
+                src = self.R.arr("fields", a, r, "fulmov").reshape(mz + 4, my + 3, mx + 4)
+                dst = self.R.arr("fields", b, r, "fulmov").reshape(mz + 4, my + 3, mx + 4)
+                dst[2:mz + 2, 1:my + 2, 2:mx + 2] = src[2:mz + 2, 1:my + 2, 2:mx + 2]
+
+    def startup(self, particle_pass=None):
+        """F:664-706; particle_pass(loop) may replace the it = 0 pair of fulmov calls (it must call set_moments)"""
+        R = self.R
+        sav = {nm: self.scalar(nm) for nm in ("dt", "adt", "hdt")}
+        for nm in sav:
+            R.set("parm2", nm, 0.0, unit="fulmov")
+        R.set("parm1", "it", 0, unit="fulmov")
+        if particle_pass is None:
+            self.fulmov(1)
+        else:
+            particle_pass(self)
+        R.call("emfld0")
+        for nm, v in sav.items():
+            R.set("parm2", nm, v, unit="fulmov")
+        self.renew()
+
+    def begin_step(self):
+        self.it += 1
+        self.R.set("parm1", "it", self.it, unit="fulmov")
+        self.R.call("prefld")
+
+    def emfild(self):
+        self.R.call("emfild", self.np1, self.np2, self.nz1, self.nz2, IPAR)

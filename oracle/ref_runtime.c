@@ -22,6 +22,8 @@
 #define REF_MPI_INTEGER 2
 #define REF_MPI_SUM 1
 #define REF_MPI_COMM_WORLD 0
+#define REF_MPI_ANY_TAG (-1)
+#define REF_MPI_STATUS_SIZE 6
 #define REF_MAX_RANKS 64
 
 static inline double ref_powi(double x, int n) {
@@ -126,6 +128,59 @@ static void ref_mpi_allgather(void *s, int scount, void *r, int rcount, int dtyp
   pthread_barrier_wait(&g_bar);
   memcpy(r, tmp, esz * (size_t)scount * g_nranks);
   free(tmp);
+}
+
+/* ---- point to point (mpi_isend / mpi_irecv / mpi_wait of the solver's halo exchange, F:6411-6501) -------------------
+ * A send is buffered at once (a copy queued for the destination, FIFO per sender), so it is complete when it returns and
+ * its request is null; a receive is recorded in a request and satisfied by mpi_wait, which blocks until the sender's next
+ * message has arrived.  Tags are not matched: every exchange of the reference uses tag 0 / mpi_any_tag. */
+typedef struct ref_msg { struct ref_msg *next; size_t bytes; char data[]; } ref_msg_t;
+static ref_msg_t *g_q_head[REF_MAX_RANKS][REF_MAX_RANKS], *g_q_tail[REF_MAX_RANKS][REF_MAX_RANKS];   /* [dst][src] */
+static pthread_mutex_t g_q_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_cond_t g_q_cv = PTHREAD_COND_INITIALIZER;
+typedef struct { void *buf; size_t bytes; int src; int used; } ref_req_t;
+#define REF_MAX_REQ 16
+static __thread ref_req_t t_req[REF_MAX_REQ];
+
+static void ref_mpi_isend(const void *buf, int count, int dtype, int dst, int *request) {
+  const size_t bytes = ((dtype == REF_MPI_INTEGER) ? 4 : 8) * (size_t)count;
+  *request = 0;
+  if (dst < 0 || dst >= g_nranks) { fprintf(stderr, "ref_mpi_isend: rank %d sends to %d of %d ranks\n", t_rank, dst, g_nranks); abort(); }
+  ref_msg_t *m = (ref_msg_t *)malloc(sizeof(ref_msg_t) + bytes);
+  m->next = NULL; m->bytes = bytes;
+  memcpy(m->data, buf, bytes);
+  pthread_mutex_lock(&g_q_mu);
+  if (g_q_tail[dst][t_rank]) g_q_tail[dst][t_rank]->next = m; else g_q_head[dst][t_rank] = m;
+  g_q_tail[dst][t_rank] = m;
+  pthread_cond_broadcast(&g_q_cv);
+  pthread_mutex_unlock(&g_q_mu);
+}
+static void ref_mpi_irecv(void *buf, int count, int dtype, int src, int *request) {
+  if (src < 0 || src >= g_nranks) { fprintf(stderr, "ref_mpi_irecv: rank %d receives from %d of %d ranks\n", t_rank, src, g_nranks); abort(); }
+  for (int k = 0; k < REF_MAX_REQ; k++)
+    if (!t_req[k].used) {
+      t_req[k].used = 1; t_req[k].buf = buf; t_req[k].src = src;
+      t_req[k].bytes = ((dtype == REF_MPI_INTEGER) ? 4 : 8) * (size_t)count;
+      *request = k + 1;
+      return;
+    }
+  fprintf(stderr, "ref_mpi_irecv: too many pending requests\n"); abort();
+}
+static void ref_mpi_wait(int *request) {
+  if (*request <= 0) return;                 /* a completed (buffered) send */
+  ref_req_t *r = &t_req[*request - 1];
+  const double t0 = now_s();
+  pthread_mutex_lock(&g_q_mu);
+  while (!g_q_head[t_rank][r->src]) pthread_cond_wait(&g_q_cv, &g_q_mu);
+  ref_msg_t *m = g_q_head[t_rank][r->src];
+  g_q_head[t_rank][r->src] = m->next;
+  if (!m->next) g_q_tail[t_rank][r->src] = NULL;
+  pthread_mutex_unlock(&g_q_mu);
+  memcpy(r->buf, m->data, m->bytes < r->bytes ? m->bytes : r->bytes);
+  free(m);
+  r->used = 0;
+  *request = 0;
+  g_t_allreduce[t_rank] += now_s() - t0;
 }
 
 #include "mrgref_gen.c"

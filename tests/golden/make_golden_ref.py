@@ -73,11 +73,48 @@ def pack_startup(name, grid, nranks, sample):
     print(path, "%.0f KB" % (os.path.getsize(path) / 1024))
 
 
+def pack_trans(name, grid, nranks, steps, sample):
+    """the reference's own time cycle (oracle/pyref.ReferenceLoop: init, it = 0 pass, emfld0, then prefld -> fulmov x2 ->
+    emfild (emcoef, cfpsol, bcgstb) -> fulmov x2 -> renewal): the fields every fulmov call saw are the reference's own
+    self-consistent solution, not synthetic modes"""
+    p = U.make_parm(*grid)
+    out = {"grid": np.array(grid), "box": np.array([p.xmax, p.ymax, p.zmax]), "scalars": np.array([p.dt, p.aimpl, p.bxc, p.Ez00]),
+           "nranks": np.array([nranks]), "ppc": np.array([32]), "steps": np.array([steps]), "sample": np.array([sample])}
+    with PR.ReferenceLoop(grid, (p.xmax, p.ymax, p.zmax), nranks) as A:
+        A.startup()
+        out["ranfb_in"] = np.array([A.ranfb()[0]])
+        for k in (1, 2):
+            out["in_sha_%d" % k] = digest(A.particles()[k])
+        for s in range(steps):
+            A.begin_step()
+            out["fpred_%d" % s] = np.stack(A.fields())
+            wkp = A.fulmov(1)
+            for k in (1, 2):
+                out["mom_%d_%d" % (s, k)] = np.stack(A.moments(k))
+            A.emfild()
+            out["fcorr_%d" % s] = np.stack(A.fields())
+            wkc = A.fulmov(0)
+            for k in (1, 2):
+                out["wk_%d_%d" % (s, k)] = np.array(list(wkp[k]) + list(wkc[k]))
+            A.renew()
+            assert A.ranks_agree()
+        final = A.particles()
+        out["ranfb_out"] = np.array(A.ranfb())
+        out["e_max"] = np.array([max(float(np.abs(f).max()) for f in A.fields()[:3])])
+    for k in (1, 2):
+        out["out_sha_%d" % k] = digest(final[k])
+        out["out_%d" % k] = np.stack([a[::sample] for a in final[k]])
+    path = os.path.join(HERE, "ref_%s.npz" % name)
+    np.savez_compressed(path, **out)
+    print(path, "%.0f KB" % (os.path.getsize(path) / 1024), "max|E| %.3e" % out["e_max"][0])
+
+
 def main():
     pack("loader_4r", RC.loader_case(6, 4, 6, 32, 3), 4, store_inputs=False, sample=4)
     pack("loader_1r", RC.loader_case(6, 4, 6, 32, 2), 1, store_inputs=False, sample=16)
     pack("edge_2r", RC.edge_case(), 2, store_inputs=True, sample=1)
     pack_startup("startup_2r", (8, 6, 8), 2, sample=8)
+    pack_trans("trans_2r", (8, 6, 8), 2, steps=2, sample=8)
 
 
 if __name__ == "__main__":

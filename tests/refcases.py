@@ -72,29 +72,36 @@ def oracle_steps(p, sp, ranfb, fsets, nranks):
     return out
 
 
-def gpu_steps(mrg, p, sp, ranfb, fsets, nranks, tile=1):
-    """the same call sequence through the CUDA path, with `nranks` round-robin ranks emulated by one context per rank on
-    this GPU (l = rank+1, rank+1+N, ..., F:1162): the rank sum of the raw moments is done on the host in rank order
-    (mpi_allreduce, F:2379-2384, 2533), the fold by the oracle's vmesh3/vmesh1.  Returns the same dict as oracle_steps."""
-    n = len(sp[1][0])
-    par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
-    ctxs = [mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax) for _ in range(nranks)]
-    st = [ranfb] * nranks
-    for r, ctx in enumerate(ctxs):
-        ctx.set_option("tile", tile)
-        for k in (1, 2):
-            ctx.upload(k, *sp[k], first=r + 1, stride=nranks)
-            ctx.sort(k, p.hdt)
-    out = {"mom": [], "wk_pred": [], "wk_corr": []}
-    for f_pred, f_corr in fsets:
-        for ctx in ctxs:
-            ctx.set_fields(f_pred)
+class GpuRanks:
+    """`nranks` round-robin ranks of the CUDA path emulated by one context per rank on this GPU (l = rank+1, rank+1+N, ...,
+    F:1162): the rank sum of the raw moments is done on the host in rank order (mpi_allreduce, F:2379-2384, 2533), the fold by
+    the oracle's vmesh3/vmesh1; every rank keeps its own ranfp state."""
+
+    def __init__(self, mrg, p, sp, ranfb, nranks, tile=1, lookahead=None):
+        self.mrg, self.p, self.nranks, self.n = mrg, p, nranks, len(sp[1][0])
+        self.ctxs = [mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax) for _ in range(nranks)]
+        self.st = [ranfb] * nranks
+        for r, ctx in enumerate(self.ctxs):
+            ctx.set_option("tile", tile)
+            for k in (1, 2):
+                ctx.upload(k, *sp[k], first=r + 1, stride=nranks)
+                ctx.sort(k, p.hdt if lookahead is None else lookahead)
+
+    def params(self, p):
+        return self.mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
+
+    def predict(self, f12, p=None):
+        """ipc = 1 for ions then electrons on the fields f12: ({ksp: folded summed moments}, {ksp: (wkix, wkih)})"""
+        p = p or self.p
+        par = self.params(p)
+        for ctx in self.ctxs:
+            ctx.set_fields(f12)
         mom, wk = {}, {}
         for k in (1, 2):
             raw = [np.zeros(O.mxyzA(p)) for _ in range(4)]
             w = [0.0, 0.0]
-            for r, ctx in enumerate(ctxs):
-                wx, wh, _ = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 1, par, st[r])
+            for r, ctx in enumerate(self.ctxs):
+                wx, wh, _ = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 1, par, self.st[r])
                 part = ctx.moments(k, folded=False)
                 for c in range(4):
                     raw[c] += part[c]
@@ -103,27 +110,47 @@ def gpu_steps(mrg, p, sp, ranfb, fsets, nranks, tile=1):
             O.vmesh3(p, raw[0], raw[1], raw[2])
             O.vmesh1(p, raw[3])
             mom[k], wk[k] = raw, tuple(w)
-        out["mom"].append(mom)
-        out["wk_pred"].append(wk)
-        for ctx in ctxs:
-            ctx.set_fields(f_corr)
+        return mom, wk
+
+    def correct(self, f12, p=None):
+        p = p or self.p
+        par = self.params(p)
+        for ctx in self.ctxs:
+            ctx.set_fields(f12)
         wk = {}
         for k in (1, 2):
             w = [0.0, 0.0]
-            for r, ctx in enumerate(ctxs):
-                wx, wh, st[r] = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 0, par, st[r])
+            for r, ctx in enumerate(self.ctxs):
+                wx, wh, self.st[r] = ctx.fulmov(k, U.QSPEC[k], U.WSPEC[k], 0, par, self.st[r])
                 ctx.sort(k, p.hdt)
                 w[0] += wx
                 w[1] += wh
             wk[k] = tuple(w)
-        out["wk_corr"].append(wk)
-    final = {}
-    for k in (1, 2):
-        final[k] = [np.zeros(n) for _ in range(6)]
-        for r, ctx in enumerate(ctxs):
-            ctx.download(k, n, r + 1, nranks, out=final[k])
-    out["final"] = final
-    out["ranfb"] = list(st)
-    for ctx in ctxs:
-        ctx.close()
+        return wk
+
+    def download(self):
+        final = {}
+        for k in (1, 2):
+            final[k] = [np.zeros(self.n) for _ in range(6)]
+            for r, ctx in enumerate(self.ctxs):
+                ctx.download(k, self.n, r + 1, self.nranks, out=final[k])
+        return final
+
+    def close(self):
+        for ctx in self.ctxs:
+            ctx.close()
+
+
+def gpu_steps(mrg, p, sp, ranfb, fsets, nranks, tile=1):
+    """the same call sequence as oracle_steps through the CUDA path (GpuRanks).  Returns the same dict."""
+    G = GpuRanks(mrg, p, sp, ranfb, nranks, tile=tile)
+    out = {"mom": [], "wk_pred": [], "wk_corr": []}
+    for f_pred, f_corr in fsets:
+        mom, wk = G.predict(f_pred)
+        out["mom"].append(mom)
+        out["wk_pred"].append(wk)
+        out["wk_corr"].append(G.correct(f_corr))
+    out["final"] = G.download()
+    out["ranfb"] = list(G.st)
+    G.close()
     return out

@@ -88,3 +88,80 @@ def test_cuda_path_matches_reference_startup(tile):
         assert all(abs(a - b) <= 1e-10 * abs(b) for a, b in zip(got, G["wk_0_%d" % k]))
         assert U.particle_err([a[::sample] for a in gpu["final"][k]], list(G["out_%d" % k]), p.hx, U.vth(k)) < 1e-12
     assert gpu["ranfb"] == [int(v) for v in G["ranfb_out"]]
+
+
+@pytest.mark.parametrize("tile", [1, 0])
+def test_cuda_path_matches_reference_time_cycle(tile):
+    """tests/golden/ref_trans_2r.npz: the fields are the reference's own self-consistent solution (prefld + the implicit solve
+    of emfild between the fulmov pairs); the CUDA path, given the fields each call saw, must match every step."""
+    import mrg_b200 as mrg
+    G = np.load(os.path.join(GOLD, "ref_trans_2r.npz"))
+    grid = tuple(int(v) for v in G["grid"])
+    p = U.make_parm(*grid)
+    sp, ranfb = U.load_species(p, int(G["ppc"][0]))
+    nranks, steps, sample = int(G["nranks"][0]), int(G["steps"][0]), int(G["sample"][0])
+    fsets = [([np.ascontiguousarray(f) for f in G["fpred_%d" % s]], [np.ascontiguousarray(f) for f in G["fcorr_%d" % s]]) for s in range(steps)]
+    gpu = RC.gpu_steps(mrg, p, sp, ranfb, fsets, nranks, tile=tile)
+    for s in range(steps):
+        for k in (1, 2):
+            ref = G["mom_%d_%d" % (s, k)]
+            assert max(U.rel_l2(gpu["mom"][s][k][c], ref[c]) for c in range(4)) < 1e-10
+            got = gpu["wk_pred"][s][k] + gpu["wk_corr"][s][k]
+            assert all(abs(a - b) <= 1e-10 * abs(b) for a, b in zip(got, G["wk_%d_%d" % (s, k)]))
+    for k in (1, 2):
+        assert U.particle_err([a[::sample] for a in gpu["final"][k]], list(G["out_%d" % k]), p.hx, U.vth(k)) < 1e-12 * steps
+    assert gpu["ranfb"] == [int(v) for v in G["ranfb_out"]]
+
+
+def test_cuda_path_as_drop_in_inside_the_reference_time_cycle():
+    """The drop-in claim on the GPU: the reference's own time cycle with its own field solver (oracle/_ref: prefld, emfild ->
+    emcoef, cfpsol, bcgstb, emfld0; 2 simulated ranks), with the CUDA path in fulmov's place -- fields out of COMMON
+    /fields/, summed folded moments into COMMON /srimp7/, particles resident on the GPU -- against the same cycle run
+    entirely by the reference.  The closed loop goes through an iterative solver (Bi-CGSTAB, eps = 1e-5, F:4540), so the
+    tolerance is not the particle path's: rounding-level noise on the moments (4e-16, injected into the C oracle in the same
+    loop) moves E and B by ~1e-13 of their scale and the particles by ~4e-15 after three steps; the bound here is 1e-9, the
+    kicked sets and RNG states must be equal."""
+    from oracle import pyref as PR
+    if not PR.available():
+        pytest.skip("oracle/_ref is not built and /root/reference is not here")
+    import mrg_b200 as mrg
+    grid, nranks, steps = (8, 6, 8), 2, 3
+    p, p0 = U.make_parm(*grid), U.make_parm(*grid, dt=0.0)
+    box = (p.xmax, p.ymax, p.zmax)
+    with PR.ReferenceLoop(grid, box, nranks) as A:
+        A.startup()
+        for _ in range(steps):
+            A.begin_step(); A.fulmov(1); A.emfild(); A.fulmov(0); A.renew()
+        fa, pa, ra = A.fields(), A.particles(), A.ranfb()
+    sp, ranfb = U.load_species(p, 32)
+    gpu = RC.GpuRanks(mrg, p, sp, ranfb, nranks, lookahead=0.0)
+    with PR.ReferenceLoop(grid, box, nranks) as B:
+        def it0(L):
+            mom, _ = gpu.predict(L.fields(), p0)
+            for k in (1, 2):
+                L.set_moments(k, mom[k])
+        B.startup(it0)
+        for k in (1, 2):
+            for ctx in gpu.ctxs:
+                ctx.sort(k, p.hdt)
+        for _ in range(steps):
+            B.begin_step()
+            mom, _ = gpu.predict(B.fields())
+            for k in (1, 2):
+                B.set_moments(k, mom[k])
+            B.emfild()
+            gpu.correct(B.fields())
+            B.renew()
+        fb = B.fields()
+    got = gpu.download()
+    st = list(gpu.st)
+    gpu.close()
+    e_scale = max(float(np.abs(f).max()) for f in fa[:3])
+    b_scale = max(float(np.abs(f).max()) for f in fa[3:6])
+    assert e_scale > 1e-3
+    err_e = max(float(np.abs(a - b).max()) for a, b in zip(fa[:3], fb[:3])) / e_scale
+    err_b = max(float(np.abs(a - b).max()) for a, b in zip(fa[3:6], fb[3:6])) / b_scale
+    err_p = max(U.particle_err(got[k], pa[k], p.hx, U.vth(k)) for k in (1, 2))
+    print("closed loop after %d steps: E %.2e  B %.2e  particles %.2e" % (steps, err_e, err_b, err_p))
+    assert err_e < 1e-9 and err_b < 1e-9 and err_p < 1e-9, (err_e, err_b, err_p)
+    assert st == ra

@@ -218,3 +218,75 @@ def test_reference_startup_is_what_the_golden_holds():
     np.testing.assert_array_equal(f[6:], f[:6])                           # ex0..bz0 = ex..bz
     for k in (1, 2):
         np.testing.assert_array_equal(np.stack(S["mom0"][k]), G["mom0_%d" % k])
+
+
+# ---- the reference's own time cycle, field solve included (oracle/pyref.ReferenceLoop) ---------------------------------------
+def trans_inputs(G):
+    grid = tuple(int(v) for v in G["grid"])
+    p = U.make_parm(*grid)
+    sp, ranfb = U.load_species(p, int(G["ppc"][0]))
+    steps = int(G["steps"][0])
+    fsets = [([np.ascontiguousarray(f) for f in G["fpred_%d" % s]], [np.ascontiguousarray(f) for f in G["fcorr_%d" % s]]) for s in range(steps)]
+    return p, sp, ranfb, fsets
+
+
+def test_oracle_reproduces_reference_time_cycle_golden():
+    """tests/golden/ref_trans_2r.npz: two full steps of the reference (prefld -> fulmov x2 -> emfild with its implicit
+    solver -> fulmov x2 -> renewal, 2 ranks) after its own start-up.  Every fulmov call of it saw the reference's own
+    self-consistent fields; the oracle, given those fields, reproduces moments, wk, particles and RNG states bit for bit."""
+    G = np.load(os.path.join(GOLD, "ref_trans_2r.npz"))
+    p, sp, ranfb, fsets = trans_inputs(G)
+    nranks, steps, sample = int(G["nranks"][0]), int(G["steps"][0]), int(G["sample"][0])
+    assert ranfb == int(G["ranfb_in"][0]) and float(G["e_max"][0]) > 1e-3          # the solve did produce a field
+    for k in (1, 2):
+        np.testing.assert_array_equal(digest(sp[k]), G["in_sha_%d" % k])
+    orc = RC.oracle_steps(p, sp, ranfb, fsets, nranks)
+    for s in range(steps):
+        for k in (1, 2):
+            np.testing.assert_array_equal(np.stack(orc["mom"][s][k]), G["mom_%d_%d" % (s, k)])
+            wk = list(orc["wk_pred"][s][k]) + list(orc["wk_corr"][s][k])
+            np.testing.assert_array_equal(np.array(wk), G["wk_%d_%d" % (s, k)])
+    for k in (1, 2):
+        np.testing.assert_array_equal(np.stack([a[::sample] for a in orc["final"][k]]), G["out_%d" % k])
+        np.testing.assert_array_equal(digest(orc["final"][k]), G["out_sha_%d" % k])
+    assert orc["ranfb"] == [int(v) for v in G["ranfb_out"]]
+
+
+@needs_ref
+@pytest.mark.parametrize("nranks", [2, 4])
+def test_oracle_as_drop_in_inside_the_reference_time_cycle(nranks):
+    """The drop-in claim itself, on the CPU: the reference's own cycle with its own field solver, once with its own fulmov
+    and once with the C oracle in fulmov's place (fields out of COMMON /fields/, moments into COMMON /srimp7/).  After
+    three steps the two runs hold the same fields, particles and RNG states -- bit for bit."""
+    grid = (8, 6, 8)
+    p, p0 = U.make_parm(*grid), U.make_parm(*grid, dt=0.0)
+    box = (p.xmax, p.ymax, p.zmax)
+    with PR.ReferenceLoop(grid, box, nranks) as A:
+        A.startup()
+        for _ in range(3):
+            A.begin_step(); A.fulmov(1); A.emfild(); A.fulmov(0); A.renew()
+        fa, pa, ra = A.fields(), A.particles(), A.ranfb()
+        assert A.ranks_agree()
+    sp, ranfb = U.load_species(p, 32)
+    arrs = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.full(nranks, ranfb, dtype=np.int32)
+
+    def particle_pass(L, parm, ipc):
+        a6 = O.field_prep(parm, L.fields())
+        for k in (1, 2):
+            r = O.fulmov(parm, a6, *arrs[k], U.QSPEC[k], U.WSPEC[k], ipc, nranks=nranks, ranfb=st)
+            if ipc:
+                L.set_moments(k, r["mom"])
+
+    with PR.ReferenceLoop(grid, box, nranks) as B:
+        B.startup(lambda L: particle_pass(L, p0, 1))
+        for _ in range(3):
+            B.begin_step(); particle_pass(B, p, 1); B.emfild(); particle_pass(B, p, 0); B.renew()
+        fb = B.fields()
+    assert max(float(np.abs(f).max()) for f in fa[:3]) > 1e-3
+    for a, b in zip(fa, fb):
+        np.testing.assert_array_equal(a, b)
+    for k in (1, 2):
+        for c in range(6):
+            np.testing.assert_array_equal(pa[k][c], arrs[k][c])
+    assert ra == [int(v) for v in st]
