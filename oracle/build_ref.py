@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Recipe for oracle/_ref/: the reference's own routines of the /fulmov/ path, compiled from the source where it
-lies (/root/reference/@mrg37-080A.f03 + param_080A.h) -- TEST INFRASTRUCTURE, see oracle/f03c.py.
+"""Recipe for oracle/_ref/: the reference's own routines of the /fulmov/ path -- and, around it, the rest of its time
+cycle: init/loadpt, the t = 0 solve emfld0/poissn, prefld and the implicit field solve emfild/emcoef/cfpsol/bcgstb --
+compiled from the source where it lies (/root/reference/@mrg37-080A.f03 + param_080A.h) -- TEST INFRASTRUCTURE, see
+oracle/f03c.py.
 
 The image has no Fortran compiler, so the compile step is  Fortran --(oracle/f03c.py)--> C --(gcc)--> .so :
     oracle/_ref/mrgref_gen.c     generated, derived from the GPL-3.0 reference: git-ignored, never committed

@@ -14,7 +14,10 @@ declarations real(C_DOUBLE) | real(C_float) | integer(C_INT) | logical | charact
 dimension(...) / save / parameter attributes and initialisers, COMMON, PARAMETER, DATA (scalars),
 include files; executable statements: assignment (scalar, whole-array fill), block and logical IF, DO
 (with or without label, with step), DO WHILE, labelled CONTINUE, GO TO, CALL, RETURN, CYCLE, EXIT, STOP;
-I/O statements (write/read/open/close/print/format/rewind) are dropped.  Expressions follow Fortran
+EQUIVALENCE of local arrays overlaid from their first elements (the one form on the path, F:6107); ENTRY without
+arguments (`entry prefld` inside emfild, F:3820: one body function with a selector, one wrapper per callable
+name); mpi_allreduce / mpi_allgather / mpi_isend / mpi_irecv / mpi_wait map onto the simulated ranks of
+oracle/ref_runtime.c.  I/O statements (write/read/open/close/print/format/rewind) are dropped.  Expressions follow Fortran
 typing: integer division truncates, default-real literals (no `d` exponent) are single precision,
 mixed-mode promotion as in Fortran (which C's usual arithmetic conversions reproduce), x**n by the
 multiplication chain gcc/gfortran use (__powidf2 order), left-to-right association of equal-precedence
