@@ -168,41 +168,42 @@ def cpu_reference_rate(steps, warmup, nthreads=None):
         have_ref = PR.available()
     except Exception:
         have_ref = False
-    fa = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 1, dtype=np.float64)]
-    fb = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 2, dtype=np.float64)]
     t_pred, t_corr = [], []
+    t_em = []
     if have_ref:
-        np0 = ppc * mx * my * mz
-        per_rank_gb = 18 * np0 * 8 / 1e9 + 0.2
-        nranks = int(max(1, min(nthreads, 0.6 * _mem_available_gb() / per_rank_gb)))
-        with PR.RefRun(mx, my, mz, np0, nranks=nranks) as R:
-            PR.setup_run(R, HX * mx, HY * my, HZ * mz, dt=DT, aimpl=AIMPL, wce_by_wpe=WCE, Ez00=EZ00, veth=VETH,
-                         qspec=(QSPEC[1], QSPEC[2]), wspec=(WSPEC[1], WSPEC[2]), vbeam=(VBEAM[1], VBEAM[2]))
-            parts, npr, _ = PR.ref_init(R)             # the reference's own loader
+        # the reference's own time cycle (oracle/pyref.ReferenceLoop): start-up solve, then per step prefld -> fulmov x2 ->
+        # emfild (implicit field solve) -> fulmov x2 -> renewal, so every fulmov call sees the reference's own fields and the
+        # step splits into the reference's three timers ful(1), em, ful(0) (F:813-822).  Only the two ful() parts are the path.
+        np0 = 32 * mx * my * mz                          # init loads 32 per cell (F:8941)
+        per_rank_gb = 18 * np0 * 8 / 1e9 + 60 * 3 * mx * (my + 1) * mz * 8 / 1e9 + 0.2      # particles + the solver's band arrays
+        limit = int(max(2, min(nthreads, 0.6 * _mem_available_gb() / per_rank_gb)))
+        nranks = max(d for d in range(2, limit + 1) if mz % d == 0) if any(mz % d == 0 for d in range(2, limit + 1)) else 2
+        with PR.ReferenceLoop((mx, my, mz), (HX * mx, HY * my, HZ * mz), nranks, qspec=(QSPEC[1], QSPEC[2]), wspec=(WSPEC[1], WSPEC[2]),
+                              dt=DT, aimpl=AIMPL, wce_by_wpe=WCE, Ez00=EZ00, veth=VETH, vbeam=(VBEAM[1], VBEAM[2])) as A:
+            npr = A.npr
+            A.startup()
             for s in range(warmup + steps):
-                R.set("parm1", "it", s + 1, unit="fulmov")
-                for name, a in zip(PR.FIELD_NAMES, fa):
-                    R.set("fields", name, a, unit="fulmov")
+                A.begin_step()
                 t0 = time.perf_counter()
-                for ksp in (1, 2):
-                    xs = [[parts[r][ksp][c] for r in range(nranks)] for c in range(6)]
-                    R.call("fulmov", *xs, QSPEC[ksp], WSPEC[ksp], npr, 1, ksp, PR.IPAR, PR.SIZE)
+                A.fulmov(1)
                 t1 = time.perf_counter()
-                for name, a in zip(PR.FIELD_NAMES, fb):
-                    R.set("fields", name, a, unit="fulmov")
+                A.emfild()
                 t2 = time.perf_counter()
-                for ksp in (1, 2):
-                    xs = [[parts[r][ksp][c] for r in range(nranks)] for c in range(6)]
-                    R.call("fulmov", *xs, QSPEC[ksp], WSPEC[ksp], npr, 0, ksp, PR.IPAR, PR.SIZE)
+                A.fulmov(0)
                 t3 = time.perf_counter()
+                A.renew()
                 if s >= warmup:
                     t_pred.append(t1 - t0)
+                    t_em.append(t2 - t1)
                     t_corr.append(t3 - t2)
         npart, kind, nthreads = 2 * npr, "reference", nranks
-        what = ("the reference's own fulmov (+init/loadpt, partbc, srimp1/2, outmesh3, filt3e, vmesh) from @mrg37-080A.f03, translated "
-                "to C (oracle/f03c.py: no Fortran compiler in the image), gcc -O2, %d simulated MPI ranks = %d threads" % (nranks, nranks))
+        what = ("the reference's own time cycle from @mrg37-080A.f03 (init/loadpt, emfld0, prefld, fulmov with partbc, srimp1/2, outmesh3, "
+                "filt3e, vmesh, and emfild/cfpsol/bcgstb between the fulmov pairs), translated to C (oracle/f03c.py: no Fortran compiler "
+                "in the image), gcc -O2, %d simulated MPI ranks = %d threads; timed: the four fulmov calls of a step" % (nranks, nranks))
     else:
         from oracle import pyoracle as O
+        fa = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 1, dtype=np.float64)]
+        fb = [np.ascontiguousarray(a, dtype=np.float64) for a in synth_fields(np, mx, my, mz, 2, dtype=np.float64)]
         O.set_num_threads(nthreads)
         nthreads = min(O.num_threads(), nthreads)
         p = O.make_parm(mx, my, mz, HX * mx, HY * my, HZ * mz, DT, AIMPL, WCE, EZ00)
@@ -231,13 +232,15 @@ def cpu_reference_rate(steps, warmup, nthreads=None):
     rate = npart * len(times) / sum(times)
     desc = "%dx%dx%d grid, %d ppc, 2 species = %d particles, %d steps; %s" % (mx, my, mz, ppc, npart, len(times), what)
     return {"value": rate, "times": times, "cores": nthreads, "kind": kind, "sample": desc,
-            "ful1_s_per_step": float(np.mean(t_pred)), "ful0_s_per_step": float(np.mean(t_corr))}
+            "ful1_s_per_step": float(np.mean(t_pred)), "ful0_s_per_step": float(np.mean(t_corr)),
+            "em_s_per_step": float(np.mean(t_em)) if t_em else None}
 
 
 def cpu_baseline_record(r):
     return {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"],
-            "ful(1)_s_per_step": r["ful1_s_per_step"], "ful(0)_s_per_step": r["ful0_s_per_step"],
-            "note": "ful(1), ful(0) = the reference's own timer split of a step (F:813-822); 'em' (field solve) is not on this path"}
+            "ful(1)_s_per_step": r["ful1_s_per_step"], "em_s_per_step": r.get("em_s_per_step"), "ful(0)_s_per_step": r["ful0_s_per_step"],
+            "note": "ful(1), em, ful(0) = the reference's own timer split of a step (F:813-822); value counts ful(1) + ful(0) only: "
+                    "'em' (the implicit field solve) is not on this path"}
 
 
 def run_reference(args):

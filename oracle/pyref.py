@@ -298,7 +298,7 @@ class ReferenceLoop:
     reference's own field solver."""
 
     def __init__(self, grid, box, nranks=2, qspec=(1.0, -1.0), wspec=(100.0, 1.0), dt=1.2, aimpl=0.6, wce_by_wpe=0.2,
-                 Ez00=0.25e-2, itermx=1, iterfx=150, itersx=150):
+                 Ez00=0.25e-2, itermx=1, iterfx=150, itersx=150, **setup):
         if nranks < 2:
             raise ValueError("the reference's field solver exchanges halos with a neighbour rank: nranks >= 2")
         mx, my, mz = grid
@@ -306,7 +306,7 @@ class ReferenceLoop:
             raise ValueError("mz must be a multiple of the number of ranks (kd = mz/npc, param_080A.h)")
         self.grid, self.nranks, self.qspec, self.wspec = grid, nranks, qspec, wspec
         self.R = R = RefRun(mx, my, mz, 32 * mx * my * mz, nranks=nranks)
-        setup_run(R, box[0], box[1], box[2], dt=dt, aimpl=aimpl, wce_by_wpe=wce_by_wpe, Ez00=Ez00, qspec=qspec, wspec=wspec)
+        setup_run(R, box[0], box[1], box[2], dt=dt, aimpl=aimpl, wce_by_wpe=wce_by_wpe, Ez00=Ez00, qspec=qspec, wspec=wspec, **setup)
         for nm, v in (("itermx", itermx), ("iterfx", iterfx), ("itersx", itersx)):      # rec_3d80A
             R.set("parm1", nm, v, unit="fulmov")
         self.parts, self.npr, _ = ref_init(R)
