@@ -26,25 +26,34 @@ def available():
     return build_ref.available() or build_ref.can_build()
 
 
+def load_library(path):
+    """bind one translated library (oracle/_ref's, or a test's own translation of other Fortran sources)"""
+    L = C.CDLL(path)
+    _bind(L)
+    return L
+
+
 def load():
     global _lib
     if _lib is None:
         path = build_ref.build()
         if not path or not os.path.exists(path):
             raise RuntimeError("oracle/_ref/libmrg_ref.so is missing and /root/reference is not here to build it from")
-        L = C.CDLL(path)
-        L.ref_set_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_long]
-        L.ref_param.argtypes = [C.c_char_p]
-        L.ref_param.restype = C.c_long
-        L.ref_pool_start.argtypes = [C.c_int]
-        L.ref_common.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_int)]
-        L.ref_common.restype = C.c_void_p
-        L.ref_call.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]
-        L.ref_has_unit.argtypes = [C.c_char_p]
-        L.ref_collective_seconds.argtypes = [C.c_int, C.c_int]
-        L.ref_collective_seconds.restype = C.c_double
-        _lib = L
+        _lib = load_library(path)
     return _lib
+
+
+def _bind(L):
+    L.ref_set_params.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_long]
+    L.ref_param.argtypes = [C.c_char_p]
+    L.ref_param.restype = C.c_long
+    L.ref_pool_start.argtypes = [C.c_int]
+    L.ref_common.argtypes = [C.c_int, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_long), C.POINTER(C.c_int)]
+    L.ref_common.restype = C.c_void_p
+    L.ref_call.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.ref_has_unit.argtypes = [C.c_char_p]
+    L.ref_collective_seconds.argtypes = [C.c_int, C.c_int]
+    L.ref_collective_seconds.restype = C.c_double
 
 
 _NP = {1: np.int32, 2: np.float32, 3: np.float64}
@@ -54,8 +63,8 @@ class RefRun:
     """One run of the translated reference: sizes of param_080A.h + a pool of simulated MPI ranks.  Only one can be
     alive at a time (the reference's sizes are process-wide, as its PARAMETERs are)."""
 
-    def __init__(self, mx, my, mz, np0, nranks=1, npc=None):
-        self.L = load()
+    def __init__(self, mx, my, mz, np0, nranks=1, npc=None, lib=None):
+        self.L = lib or load()
         self.L.ref_pool_stop()
         npc = npc or nranks
         if self.L.ref_set_params(npc, mx, my, mz, np0):
