@@ -740,7 +740,10 @@ def run_ours(args):
             new = hsets[(estate["n"] + 1) % 2]
             for i in (3, 4, 5):
                 setattr(c, FN[i], new[i])
-            fm.fields_changed(fm.MASK_B)
+            if args.device_prefld:
+                fm.prefld_done()        # whole device arrays (N = 1): prefld is repeated on the device, no upload; else = MASK_B
+            else:
+                fm.fields_changed(fm.MASK_B)
             for ksp in SPECIES:
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 1, ksp)
             fm.finish_moments()
@@ -796,7 +799,9 @@ def run_ours(args):
                           "own z block of the moments into host arrays shared by the ranks of the node (POSIX shm, option sink_share); "
                           if (lazy or share) else "")
                        + ("the host marks its field updates (prefld: bx..bz, emfild: ex..bz, renewal on the device)"
-                          if args.hints else "no field hints: all of COMMON /fields/ is uploaded in both phases")}
+                          if args.hints else "no field hints: all of COMMON /fields/ is uploaded in both phases")
+                       + ("; prefld is repeated on the device (mrg_prefld, bit-identical to the host's), so bx,by,bz are not uploaded"
+                          if (args.hints and args.device_prefld and not lazy) else "")}
         barrier()
         for t, path in shm_keep:
             torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
@@ -942,6 +947,7 @@ def main():
     ap.add_argument("--peer-push-last", type=int, default=296, help="N > 1: CTAs of that kernel for the last species of the step, whose exchange nothing overlaps (0 = --peer-push)")
     ap.add_argument("--split-push", type=int, default=1, help="N > 1: 1 = the last species' predictor runs as two launches and the planes final after the first are pushed to the peers under the second (0 = off, 2 = every species)")
     ap.add_argument("--numa-bind", type=int, default=1, help="N > 1: bind each rank to the CPUs next to its GPU before it allocates pinned host arrays")
+    ap.add_argument("--device-prefld", type=int, default=1, help="e2e leg: 1 = after the host's prefld the entry is repeated on the device instead of uploading bx,by,bz (whole device arrays only: N = 1)")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")
     ap.add_argument("--cpu-steps", type=int, default=4)

@@ -123,6 +123,17 @@ int mrg_set_fields_lazy(mrg_ctx* ctx, uint32_t mask, const double* const f12[12]
  * field is held lazily.                                                      */
 int mrg_renew_fields_host(mrg_ctx* ctx, const double* const old6[6]);
 
+/* entry prefld of emfild (F:3820-3873) on the device copies of COMMON /fields/:
+ * bx,by,bz = b0 - dt*curl(aimpl*e + (1-aimpl)*e0) on the interior nodes, with
+ * the reference's wall rows (j = 0, my: one-sided, by = 0).  Bit-identical to
+ * the host's prefld (tests), so a host that keeps calling its own prefld need
+ * not upload bx,by,bz before the ipc >= 1 calls: SURVEY 8(f1), the first piece
+ * of the field-side assembly that reads only what the particle path already
+ * holds on the device.  Needs whole (not lazily held) ex..ez, ex0..bz0.      */
+int mrg_prefld(mrg_ctx* ctx, double dt, double aimpl);
+/* The device copies of the selected members of COMMON /fields/, to the host.  */
+int mrg_get_fields(mrg_ctx* ctx, uint32_t mask, double* const f12[12]);
+
 /* "Renewal: ex0 <- ex" of trans, F:796-807, on the device copies: after the
  * host has done that loop on its own arrays it calls this instead of
  * uploading ex0..bz0 again (they equal the ex..bz the device already has).  */

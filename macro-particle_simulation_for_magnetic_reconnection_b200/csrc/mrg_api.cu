@@ -1097,6 +1097,27 @@ int mrg_set_fields_lazy(mrg_ctx* c, uint32_t mask, const double* const f12[12]) 
   return MRG_OK;
 }
 
+// entry prefld of emfild (F:3820-3873) on the device copies: bx, by, bz from ex..ez, ex0..ez0, bx0..bz0 -- bit-identical to
+// the host's prefld, which therefore need not upload the three arrays in front of the predictor pass.
+int mrg_prefld(mrg_ctx* c, double dt, double aimpl) {
+  if (!c) return fail(MRG_ERR_ARG, "null context");
+  if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
+  for (int k = 0; k < 12; k++)
+    if (c->flazy[k] && !(k >= 3 && k <= 5))
+      return fail(MRG_ERR_STATE, "fields are held lazily: the device does not hold the whole arrays prefld reads");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < c->nspecies; k++)
+    if (c->sp[k].pending) CK(cudaStreamWaitEvent(c->stream, c->sp[k].done, 0));
+  const GP& g = c->g;
+  CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->fcur[k];
+  const long long n = (long long)g.mx * (g.my + 1) * g.mz;
+  k_prefld<<<grid_for(n, 256), 256, 0, c->stream>>>(g, f, c->f12[3], c->f12[4], c->f12[5], aimpl, 1.0 - aimpl, dt,
+                                                     2.0 * g.hx, 2.0 * g.hy, 2.0 * g.hz); CKL(c);
+  for (int k = 3; k <= 5; k++) { c->fcur[k] = c->f12[k]; c->flazy[k] = false; }
+  c->field_version++;
+  return MRG_OK;
+}
+
 // F:796-807 ("Renewal: ex0 <- ex") on the device copies of the fields.
 int mrg_renew_fields_host(mrg_ctx* c, const double* const old6[6]) {
   if (!c) return fail(MRG_ERR_ARG, "null context");
@@ -1548,6 +1569,24 @@ int mrg_get_prepared_fields(mrg_ctx* c, const mrg_step_params* p, double* const 
   for (int k = 0; k < 6; k++) {
     if (!a6[k]) continue;
     CK(cudaMemcpyAsync(a6[k], c->tmp6[k], gb, cudaMemcpyDeviceToHost, c->stream));
+    c->d2h += (long long)gb;
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  return MRG_OK;
+}
+
+// the device copies of COMMON /fields/ (what mrg_set_fields, mrg_renew_fields and mrg_prefld left there)
+int mrg_get_fields(mrg_ctx* c, uint32_t mask, double* const f12[12]) {
+  if (!c || !f12) return fail(MRG_ERR_ARG, "null argument");
+  if (mask >> 12) return fail(MRG_ERR_ARG, "mask has bits above 11");
+  if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
+  CK(cudaSetDevice(c->device));
+  const size_t gb = (size_t)c->g.ntot * sizeof(double);
+  for (int k = 0; k < 12; k++) {
+    if (!((mask >> k) & 1u)) continue;
+    if (!f12[k]) return fail(MRG_ERR_ARG, "selected field pointer is null");
+    if (c->flazy[k]) return fail(MRG_ERR_STATE, "this field is held lazily: the device has only some of its planes");
+    CK(cudaMemcpyAsync(f12[k], c->fcur[k], gb, cudaMemcpyDeviceToHost, c->stream));
     c->d2h += (long long)gb;
   }
   CK(cudaStreamSynchronize(c->stream));

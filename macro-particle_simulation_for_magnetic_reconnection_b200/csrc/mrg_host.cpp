@@ -21,6 +21,7 @@ struct HostState {
   bool auto_fields = true;
   unsigned dirty = 0xFFFu;     // members of COMMON /fields/ the device copy is stale for
   bool renew = false;          // ex0 <- ex still to be repeated on the device
+  bool prefld = false;         // the host ran prefld: repeat it on the device instead of uploading bx,by,bz
   bool it0 = false;            // the it = 0 pair of calls has been seen and emfld0 may have rewritten every field since
   int sort_interval = 1;
   bool exit_on_error = true;
@@ -66,6 +67,10 @@ void mrg_host_fields_changed_mask(uint32_t mask) { H.dirty |= (mask & 0xFFFu); }
 void mrg_host_fields_renewed(void) {
   if (H.auto_fields) H.dirty |= 0xFC0u;
   else H.renew = true;
+}
+void mrg_host_prefld_done(void) {                 // after `call prefld` (F:759)
+  if (H.auto_fields) H.dirty |= 0x038u;
+  else H.prefld = true;
 }
 void mrg_host_set_auto_fields(int32_t on) { H.auto_fields = on != 0; }
 int mrg_host_set_nspecies(int32_t n) {
@@ -127,18 +132,24 @@ void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, do
   // call after the it = 0 pair uploads everything and drops the pending device renewal (it would copy the pre-emfld0
   // ex..bz into ex0..bz0).
   if (*v.it == 0) H.it0 = true;
-  else if (H.it0) { H.it0 = false; H.dirty = 0xFFFu; H.renew = false; }
+  else if (H.it0) { H.it0 = false; H.dirty = 0xFFFu; H.renew = false; }   // a pending prefld stays: E, e0, b0 arrive with this upload
   if (H.renew) {                                          // F:796-807 on the device copies
     rc = mrg_renew_fields(H.ctx);
     if (rc) return die("mrg_renew_fields", rc);
     H.renew = false;
     H.dirty &= ~0xFC0u;
   }
+  if (H.prefld) H.dirty &= ~0x038u;                       // bx,by,bz are computed below from what the device holds
   if (H.dirty) {
     const double* f12[12] = {v.ex, v.ey, v.ez, v.bx, v.by, v.bz, v.ex0, v.ey0, v.ez0, v.bx0, v.by0, v.bz0};
     rc = mrg_set_fields(H.ctx, H.dirty, f12);
     if (rc) return die("mrg_set_fields", rc);
     H.dirty = 0;
+  }
+  if (H.prefld) {                                         // entry prefld (F:3820-3873) on the device copies
+    rc = mrg_prefld(H.ctx, *v.dt, *v.aimpl);
+    if (rc) return die("mrg_prefld", rc);
+    H.prefld = false;
   }
   mrg_step_params p;
   p.dt = *v.dt; p.adt = *v.adt; p.hdt = *v.hdt; p.aimpl = *v.aimpl;

@@ -60,6 +60,9 @@ int mrg_host_bind_extra_moments(int32_t ksp, double* qjx, double* qjy, double* q
  * renewed = the host ran the loop ex0 <- ex (F:796-807), which is then
  * repeated on the device copies instead of uploading ex0..bz0. */
 void mrg_host_fields_changed_mask(uint32_t mask);
+/* After `call prefld` (F:759): with auto fields off the entry is repeated on the device (mrg_prefld, bit-identical to the
+ * host's) instead of uploading bx,by,bz; with auto fields on this is mrg_host_fields_changed_mask(0x038).                */
+void mrg_host_prefld_done(void);
 void mrg_host_fields_renewed(void);
 /* Cell-sort every n-th corrector call of a species (0 = never). */
 void mrg_host_set_sort_interval(int32_t n);

@@ -108,6 +108,45 @@ __global__ void k_blend_filter_z(GP g, CPtr12 f, Ptr6 D, double aimpl, double om
   }
 }
 
+// entry prefld of emfild (F:3820-3873): b = b0 + dt*(-curl ea) on the interior nodes, ea = aimpl*e + (1-aimpl)*e0 blended
+// on the fly at the four neighbours each component reads.  One-sided differences with the mirror rows folded in (the
+// factor 2) on the walls j = 0 and j = my, where by = 0.  Every operation is the source's, in its order, with _rn
+// intrinsics (true division): the result is bit-identical to the host's prefld, so the host need not upload bx, by, bz.
+__device__ __forceinline__ double blend_E(const CPtr12& f, int c, int m, double aimpl, double om) {
+  return __dadd_rn(__dmul_rn(aimpl, f.p[c][m]), __dmul_rn(om, f.p[c + 6][m]));
+}
+__global__ void k_prefld(GP g, CPtr12 f, double* __restrict__ bx, double* __restrict__ by, double* __restrict__ bz,
+                         double aimpl, double om, double dt, double hx2, double hy2, double hz2) {
+  int i, j, k;
+  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, nullptr, g.mz, i, j, k)) return;
+  const int kr = (k == g.mz - 1) ? 0 : k + 1, kl = (k == 0) ? g.mz - 1 : k - 1;      // pzr, pzl (F:8399-8422)
+  const int ir = (i == g.mx - 1) ? 0 : i + 1, il = (i == 0) ? g.mx - 1 : i - 1;      // pxr, pxl (F:8341-8364)
+  const int m = node_of(g, i, j, k);
+  const double dey_z = __dsub_rn(blend_E(f, 1, node_of(g, i, j, kr), aimpl, om), blend_E(f, 1, node_of(g, i, j, kl), aimpl, om));
+  const double dey_x = __dsub_rn(blend_E(f, 1, node_of(g, ir, j, k), aimpl, om), blend_E(f, 1, node_of(g, il, j, k), aimpl, om));
+  double tx, tz;
+  if (j >= 1 && j <= g.my - 1) {                                                     // F:3834-3853
+    const double dez_y = __dsub_rn(blend_E(f, 2, node_of(g, i, j + 1, k), aimpl, om), blend_E(f, 2, node_of(g, i, j - 1, k), aimpl, om));
+    const double dez_x = __dsub_rn(blend_E(f, 2, node_of(g, ir, j, k), aimpl, om), blend_E(f, 2, node_of(g, il, j, k), aimpl, om));
+    const double dex_z = __dsub_rn(blend_E(f, 0, node_of(g, i, j, kr), aimpl, om), blend_E(f, 0, node_of(g, i, j, kl), aimpl, om));
+    const double dex_y = __dsub_rn(blend_E(f, 0, node_of(g, i, j + 1, k), aimpl, om), blend_E(f, 0, node_of(g, i, j - 1, k), aimpl, om));
+    tx = __dsub_rn(__ddiv_rn(dey_z, hz2), __ddiv_rn(dez_y, hy2));
+    const double ty = __dsub_rn(__ddiv_rn(dez_x, hx2), __ddiv_rn(dex_z, hz2));
+    tz = __dsub_rn(__ddiv_rn(dex_y, hy2), __ddiv_rn(dey_x, hx2));
+    by[m] = __dadd_rn(f.p[10][m], __dmul_rn(dt, ty));
+  } else {                                                                           // F:3856-3880
+    const int j1 = (j == 0) ? 1 : g.my;               // the row the one-sided term reads: (i,1,k) at j = 0, (i,my,k) at j = my
+    const double ez2 = __ddiv_rn(__dmul_rn(2.0, blend_E(f, 2, node_of(g, i, j1, k), aimpl, om)), hy2);
+    const double ex2 = __ddiv_rn(__dmul_rn(2.0, blend_E(f, 0, node_of(g, i, j1, k), aimpl, om)), hy2);
+    const double qz = __ddiv_rn(dey_z, hz2), qx = -__ddiv_rn(dey_x, hx2);
+    tx = (j == 0) ? __dsub_rn(qz, ez2) : __dadd_rn(qz, ez2);
+    tz = (j == 0) ? __dadd_rn(qx, ex2) : __dsub_rn(qx, ex2);
+    by[m] = 0.0;
+  }
+  bx[m] = __dadd_rn(f.p[9][m], __dmul_rn(dt, tx));
+  bz[m] = __dadd_rn(f.p[11][m], __dmul_rn(dt, tz));
+}
+
 // One (-1,4,10,4,-1)/16 sweep, F:7365-7395 (AXIS=2, z), F:7401-7434 (AXIS=0, x),
 // F:7438-7492 (AXIS=1, y with wall mirror rows; rows j=0 and j=my are copied).
 // y sweep of one node (F:7438-7492): rows j = 0 and j = my are copied; mirror rows a(-1) = sg*e(1), a(my+1) = sg*e(my-1)

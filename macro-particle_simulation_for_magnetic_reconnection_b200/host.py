@@ -176,6 +176,17 @@ class MrgContext:
             arr = (capi.dp * 6)(*[as_dp(a) for a in old6])
             check(self.lib.mrg_renew_fields_host(self.h, arr))
 
+    def prefld(self, dt, aimpl):
+        """entry prefld of emfild (F:3820-3873) on the device copies: bx,by,bz <- b0 - dt curl(ea)"""
+        check(self.lib.mrg_prefld(self.h, dt, aimpl))
+
+    def get_fields(self, mask=0xFFF):
+        """the device copies of COMMON /fields/ ({index: array} for the members in mask)"""
+        out = {k: np.zeros(self.n_grid) for k in range(12) if (mask >> k) & 1}
+        arr = (capi.dp * 12)(*[as_dp(out[k]) if k in out else None for k in range(12)])
+        check(self.lib.mrg_get_fields(self.h, mask, arr))
+        return out
+
     def prepared_fields(self, params):
         out = [np.zeros(self.n_grid) for _ in range(6)]
         arr = (capi.dp * 6)(*[as_dp(a) for a in out])
@@ -327,6 +338,7 @@ class Fulmov:
         self.ctx.set_option("sink_share", 1 if share_moments else 0)
         self.dirty = self.MASK_ALL
         self.renew = False
+        self.prefld_pending = False
         self.it0 = False
         self.sort_interval = sort_interval
         self.ncorr = {k: 0 for k in range(1, 5)}
@@ -337,6 +349,15 @@ class Fulmov:
 
     def fields_changed(self, mask=0xFFF):
         self.dirty |= mask
+
+    def prefld_done(self):
+        """The host has called prefld (F:759, rewrites bx,by,bz).  With hints on and whole device arrays the same entry is
+        repeated on the device (mrg_prefld, bit-identical) instead of uploading the three arrays; otherwise this is
+        fields_changed(MASK_B)."""
+        if self.hints and not self.lazy:
+            self.prefld_pending = True
+        else:
+            self.dirty |= self.MASK_B
 
     def fields_renewed(self):
         """The host has copied ex..bz into ex0..bz0 (F:796-807)."""
@@ -370,9 +391,14 @@ class Fulmov:
             self.ctx.renew_fields(self.c.fields()[6:] if self.lazy else None)
             self.renew = False
             self.dirty &= ~self.MASK_OLD
+        if self.prefld_pending:
+            self.dirty &= ~self.MASK_B               # computed below from what the device holds
         if self.dirty:
             (self.ctx.set_fields_lazy if self.lazy else self.ctx.set_fields)(self.c.fields(), mask=self.dirty)
             self.dirty = 0
+        if self.prefld_pending:
+            self.ctx.prefld(self.c.dt, self.c.aimpl)
+            self.prefld_pending = False
 
     def _record_wk(self, ksp, wkix, wkih):
         c = self.c

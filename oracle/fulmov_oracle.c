@@ -254,6 +254,54 @@ void orc_field_prep(const orc_parm* p, const double* const f12[12],
   orc_filt3e(p, a6[3], a6[4], a6[5], p->bxc, p->byc, p->bzc, p->ifilx, p->ifily, p->ifilz, +1);
 }
 
+/* entry prefld of emfild, F:3820-3873: the magnetic field predicted from the time-decentred electric field,
+ * b = b0 + dt * (-curl ea), written into f12[3..5] on the interior nodes.  The y walls (j = 0, my) take one-sided
+ * differences with the mirror rows folded in (the factor 2) and by = 0.  hx2 = 2 hx etc. (F:8563-8565), the periodic
+ * neighbours come from the tables pxl/pxr, pzl/pzr (F:8341-8364, 8399-8422).  SURVEY 8(f1): the first piece of the
+ * field-side assembly that reads and writes only what the particle path already holds on the device. */
+void orc_prefld(const orc_parm* p, double* const f12[12]) {
+  const int mx = p->mx, my = p->my, mz = p->mz;
+  const double aimpl = p->aimpl, dt = p->dt;
+  const double hx2 = 2.0 * p->hx, hy2 = 2.0 * p->hy, hz2 = 2.0 * p->hz;
+  const int64_t n = orc_mxyzA(p);
+  double* ea[3];
+  for (int c = 0; c < 3; c++) {
+    ea[c] = (double*)malloc(sizeof(double) * (size_t)n);
+    for (int64_t m = 0; m < n; m++) ea[c][m] = NAN;           /* only interior nodes are defined and read */
+  }
+  for (int k = 0; k <= mz - 1; k++)                           /* F:3823-3831 */
+    for (int j = 0; j <= my; j++)
+      for (int i = 0; i <= mx - 1; i++) {
+        const int64_t m = IDX(p, i, j, k);
+        for (int c = 0; c < 3; c++) ea[c][m] = aimpl * f12[c][m] + (1.0 - aimpl) * f12[c + 6][m];
+      }
+  const double *exa = ea[0], *eya = ea[1], *eza = ea[2];
+  double *bx = f12[3], *by = f12[4], *bz = f12[5];
+  const double *bx0 = f12[9], *by0 = f12[10], *bz0 = f12[11];
+  for (int k = 0; k <= mz - 1; k++) {
+    const int kr = (k == mz - 1) ? 0 : k + 1, kl = (k == 0) ? mz - 1 : k - 1;
+    for (int i = 0; i <= mx - 1; i++) {
+      const int ir = (i == mx - 1) ? 0 : i + 1, il = (i == 0) ? mx - 1 : i - 1;
+      for (int j = 1; j <= my - 1; j++) {                     /* F:3834-3853 */
+        const int64_t m = IDX(p, i, j, k);
+        bx[m] = bx0[m] + dt * ((eya[IDX(p, i, j, kr)] - eya[IDX(p, i, j, kl)]) / hz2 - (eza[IDX(p, i, j + 1, k)] - eza[IDX(p, i, j - 1, k)]) / hy2);
+        by[m] = by0[m] + dt * ((eza[IDX(p, ir, j, k)] - eza[IDX(p, il, j, k)]) / hx2 - (exa[IDX(p, i, j, kr)] - exa[IDX(p, i, j, kl)]) / hz2);
+        bz[m] = bz0[m] + dt * ((exa[IDX(p, i, j + 1, k)] - exa[IDX(p, i, j - 1, k)]) / hy2 - (eya[IDX(p, ir, j, k)] - eya[IDX(p, il, j, k)]) / hx2);
+      }
+      {                                                       /* F:3856-3880 */
+        const int64_t m0 = IDX(p, i, 0, k), m1 = IDX(p, i, my, k);
+        bx[m0] = bx0[m0] + dt * ((eya[IDX(p, i, 0, kr)] - eya[IDX(p, i, 0, kl)]) / hz2 - 2 * eza[IDX(p, i, 1, k)] / hy2);
+        by[m0] = 0;
+        bz[m0] = bz0[m0] + dt * (-(eya[IDX(p, ir, 0, k)] - eya[IDX(p, il, 0, k)]) / hx2 + 2 * exa[IDX(p, i, 1, k)] / hy2);
+        bx[m1] = bx0[m1] + dt * ((eya[IDX(p, i, my, kr)] - eya[IDX(p, i, my, kl)]) / hz2 + 2 * eza[IDX(p, i, my, k)] / hy2);
+        by[m1] = 0;
+        bz[m1] = bz0[m1] + dt * (-(eya[IDX(p, ir, my, k)] - eya[IDX(p, il, my, k)]) / hx2 - 2 * exa[IDX(p, i, my, k)] / hy2);
+      }
+    }
+  }
+  for (int c = 0; c < 3; c++) free(ea[c]);
+}
+
 /* ------------------------------------------------------------------------ */
 /* partbc F:1856-1879 (vy != NULL) / partbcEST F:1928-1949 (vy == NULL) */
 static void wrap_one(const orc_parm* p, double* x, double* y, double* z, double* vy) {

@@ -114,6 +114,14 @@ def field_prep(p, f12):
     return a6
 
 
+def prefld(p, f12):
+    """entry prefld of emfild (F:3820-3873) in place: f12[3..5] (bx,by,bz) from ex..ez, ex0..ez0, bx0..bz0"""
+    for a in f12:
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    lib().orc_prefld(C.byref(p), _parr(f12))
+    return f12
+
+
 def filt3e(p, ex, ey, ez, dc, sym, ifil=None):
     fx, fy, fz = ifil if ifil is not None else (p.ifilx, p.ifily, p.ifilz)
     lib().orc_filt3e(C.byref(p), _p(ex), _p(ey), _p(ez), dc[0], dc[1], dc[2], fx, fy, fz, sym)

@@ -187,3 +187,65 @@ def test_cpp_fulmov_mirror(case):
         assert lib.mrg_host_pull_particles(k, *[a.ctypes.data_as(dp) for a in host[k]], npr.value, 1, 1) == 0
         assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < PTOL
     lib.mrg_host_unbind()
+
+
+def test_device_prefld_bit_exact(case):
+    """mrg_prefld = entry prefld of emfild (F:3820-3873) on the device copies of COMMON /fields/: every interior node of bx, by,
+    bz bit-identical to the oracle's restatement (which tests/test_ref_pin.py holds bit for bit to the reference's own);
+    nothing else is written."""
+    import mrg_b200 as mrg
+    p = case[0]
+    rng = np.random.default_rng(11)
+    f12 = [rng.normal(scale=0.01, size=O.mxyzA(p)) for _ in range(12)]
+    want = O.prefld(p, [a.copy() for a in f12])
+    ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax)
+    ctx.set_fields(f12)
+    ctx.prefld(p.dt, p.aimpl)
+    got = ctx.get_fields()
+    ctx.close()
+    sh = (p.mz + 4, p.my + 3, p.mx + 4)
+    inner = (slice(2, p.mz + 2), slice(1, p.my + 2), slice(2, p.mx + 2))
+    for c in range(12):
+        if 3 <= c <= 5:
+            np.testing.assert_array_equal(got[c].reshape(sh)[inner], want[c].reshape(sh)[inner])
+        else:
+            np.testing.assert_array_equal(got[c], f12[c])
+
+
+def test_prefld_mark_replaces_the_upload_of_b(case):
+    """hints mode: after the host's prefld the mirror repeats the entry on the device (prefld_done) instead of uploading
+    bx, by, bz -- the prepared fields the predictor gathers from are bit-identical either way, 3 grid arrays less H2D"""
+    import mrg_b200 as mrg
+    p, sp, ranfb, f_a, f_b = case
+    npr = len(sp[1][0])
+    FN = mrg.host.FIELD_NAMES
+    out = {}
+    for mode in ("upload", "device"):
+        c = mrg.Common(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, dt=p.dt, aimpl=p.aimpl, wce_by_wpe=p.bxc, Ez00=p.Ez00)
+        c.ranfb, c.it = ranfb, 1
+        fm = mrg.Fulmov(c, ipar=1, size=1, hints=True)
+        host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+        for name, arr in zip(FN, f_a):
+            getattr(c, name)[:] = arr
+        for k in (1, 2):                                   # a first pair of calls: everything is uploaded
+            fm(*host[k], U.QSPEC[k], U.WSPEC[k], npr, 1, k)
+        fm.finish_moments()
+        fm.ctx.counters(reset=True)
+        hostf = O.prefld(p, [np.ascontiguousarray(a, dtype=np.float64).copy() for a in c.fields()])      # the host's own prefld
+        for i in (3, 4, 5):
+            getattr(c, FN[i])[:] = hostf[i]
+        if mode == "upload":
+            fm.fields_changed(fm.MASK_B)
+        else:
+            fm.prefld_done()
+        fm(*host[1], U.QSPEC[1], U.WSPEC[1], npr, 1, 1)
+        fm.finish_moments()
+        cnt = fm.ctx.counters()
+        par = c.step_params()
+        out[mode] = (fm.ctx.prepared_fields(par), cnt["h2d_bytes"], [a.copy() for a in (c.qix, c.qiy, c.qiz, c.qi)])
+        fm.ctx.close()
+    for a, b in zip(out["upload"][0], out["device"][0]):
+        np.testing.assert_array_equal(a, b)
+    assert out["upload"][1] - out["device"][1] == 3 * 8 * O.mxyzA(p)
+    for a, b in zip(out["upload"][2], out["device"][2]):
+        assert U.rel_l2(a, b) < 1e-13

@@ -290,3 +290,33 @@ def test_oracle_as_drop_in_inside_the_reference_time_cycle(nranks):
         for c in range(6):
             np.testing.assert_array_equal(pa[k][c], arrs[k][c])
     assert ra == [int(v) for v in st]
+
+
+@needs_ref
+@pytest.mark.parametrize("grid", [(8, 6, 8), (6, 4, 10)])
+def test_prefld_bit_identical(grid):
+    """entry prefld of emfild (F:3820-3873), the B predictor in front of the predictor pass: the C oracle's restatement against
+    the reference's own, on random fields, every interior node of bx, by, bz"""
+    mx, my, mz = grid
+    p = U.make_parm(*grid)
+    rng = np.random.default_rng(5)
+    f12 = [rng.normal(scale=0.01, size=O.mxyzA(p)) for _ in range(12)]
+    with PR.RefRun(mx, my, mz, 32 * mx * my * mz, nranks=2) as R:
+        PR.setup_run(R, p.xmax, p.ymax, p.zmax)
+        PR.ref_init(R)                                  # tables pxl/pxr/pzl/pzr, hx2.., aimpl, dt
+        for nm, a in zip(PR.FIELD_NAMES, f12):
+            R.set("fields", nm, a, unit="fulmov")
+        R.call("prefld")
+        ref = [R.get("fields", nm, unit="fulmov") for nm in PR.FIELD_NAMES]
+    mine = O.prefld(p, [a.copy() for a in f12])
+    sh = (mz + 4, my + 3, mx + 4)
+    inner = (slice(2, mz + 2), slice(1, my + 2), slice(2, mx + 2))
+    for c in range(12):
+        a, b = ref[c].reshape(sh), mine[c].reshape(sh)
+        if 3 <= c <= 5:
+            np.testing.assert_array_equal(a[inner], b[inner])
+            assert np.abs(a[inner] - f12[c].reshape(sh)[inner]).max() > 0      # it did change B
+        else:
+            np.testing.assert_array_equal(a, b)                                 # nothing else is written
+    np.testing.assert_array_equal(mine[4].reshape(sh)[2:mz + 2, 1, 2:mx + 2], 0.0)          # by = 0 on the walls
+    np.testing.assert_array_equal(mine[4].reshape(sh)[2:mz + 2, my + 1, 2:mx + 2], 0.0)
