@@ -21,7 +21,8 @@
 !*   6. (optional, saves 3/4 of the host->device field traffic) mark    *
 !*      the three places where trans changes COMMON /fields/:           *
 !*        call mrg_host_set_auto_fields(0)         ! once, before trans *
-!*        call mrg_host_fields_changed_mask(56)    ! after prefld F:759 *
+!*        call mrg_host_prefld_done()              ! after prefld F:759 *
+!*          (the entry is repeated on the device; ..._mask(56) uploads) *
 !*        call mrg_host_fields_changed_mask(63)    ! after emfild F:771 *
 !*        call mrg_host_fields_renewed()           ! after F:796-807    *
 !***********************************************************************
@@ -93,6 +94,10 @@
         end subroutine mrg_host_fields_changed_mask
 !
 !  the host has run the renewal loop ex0 <- ex (F:796-807)
+        subroutine mrg_host_prefld_done () &
+                     bind(C,name='mrg_host_prefld_done')
+        end subroutine mrg_host_prefld_done
+!
         subroutine mrg_host_fields_renewed () &
                      bind(C,name='mrg_host_fields_renewed')
         end subroutine mrg_host_fields_renewed
