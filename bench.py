@@ -751,7 +751,11 @@ def run_ours(args):
                 dist.barrier()          # every rank's block of the shared COMMON /srimp7/ arrays has landed (MPI_Barrier in a Fortran host)
             for i in (0, 1, 2):
                 setattr(c, FN[i], new[i])
-            fm.fields_changed(fm.MASK_NEW)
+            if args.device_prefld:
+                c.it = estate["n"] + 2     # emfild_done looks at mod(it,5): every fifth step smooths B on the device too (F:4298)
+                fm.emfild_done()           # whole device arrays (N = 1): only ex,ey,ez are uploaded; else = MASK_NEW
+            else:
+                fm.fields_changed(fm.MASK_NEW)
             for ksp in SPECIES:
                 fm(*dummy, QSPEC[ksp], WSPEC[ksp], npr, 0, ksp)
             for i in range(6):
@@ -800,7 +804,7 @@ def run_ours(args):
                           if (lazy or share) else "")
                        + ("the host marks its field updates (prefld: bx..bz, emfild: ex..bz, renewal on the device)"
                           if args.hints else "no field hints: all of COMMON /fields/ is uploaded in both phases")
-                       + ("; prefld is repeated on the device (mrg_prefld, bit-identical to the host's), so bx,by,bz are not uploaded"
+                       + ("; prefld and emfild's B update are repeated on the device (mrg_update_b, bit-identical to the host's), so bx,by,bz are never uploaded"
                           if (args.hints and args.device_prefld and not lazy) else "")}
         barrier()
         for t, path in shm_keep:
@@ -947,7 +951,7 @@ def main():
     ap.add_argument("--peer-push-last", type=int, default=296, help="N > 1: CTAs of that kernel for the last species of the step, whose exchange nothing overlaps (0 = --peer-push)")
     ap.add_argument("--split-push", type=int, default=1, help="N > 1: 1 = the last species' predictor runs as two launches and the planes final after the first are pushed to the peers under the second (0 = off, 2 = every species)")
     ap.add_argument("--numa-bind", type=int, default=1, help="N > 1: bind each rank to the CPUs next to its GPU before it allocates pinned host arrays")
-    ap.add_argument("--device-prefld", type=int, default=1, help="e2e leg: 1 = after the host's prefld the entry is repeated on the device instead of uploading bx,by,bz (whole device arrays only: N = 1)")
+    ap.add_argument("--device-prefld", type=int, default=1, help="e2e leg: 1 = prefld and emfild's B update are repeated on the device instead of uploading bx,by,bz (whole device arrays only: N = 1)")
     ap.add_argument("--lazy-fields", type=int, default=1, help="e2e leg at N > 1: upload only the z planes each rank's preparation reads")
     ap.add_argument("--share-moments", type=int, default=1, help="e2e leg at N > 1: ranks share the host moment arrays, each delivers its z block")
     ap.add_argument("--cpu-steps", type=int, default=4)

@@ -131,6 +131,12 @@ int mrg_renew_fields_host(mrg_ctx* ctx, const double* const old6[6]);
  * of the field-side assembly that reads only what the particle path already
  * holds on the device.  Needs whole (not lazily held) ex..ez, ex0..bz0.      */
 int mrg_prefld(mrg_ctx* ctx, double dt, double aimpl);
+/* bx,by,bz as emfild leaves them behind its solve (F:4238-4302): the same
+ * update from the NEW ex,ey,ez (uploaded first), and with smooth != 0 -- the
+ * steps with mod(it,5) = 1 -- outmesh3 + filt3e(sym=+1) of the three arrays
+ * (F:4298-4302).  Bit-identical to the host's emfild, so only ex,ey,ez cross
+ * PCIe after the field solve.  Needs ifilx = ifily = ifilz = 1 (F:368-370). */
+int mrg_update_b(mrg_ctx* ctx, double dt, double aimpl, int32_t smooth);
 /* The device copies of the selected members of COMMON /fields/, to the host.  */
 int mrg_get_fields(mrg_ctx* ctx, uint32_t mask, double* const f12[12]);
 

@@ -19,7 +19,7 @@ SYMBOLS = [
     "mrg_create", "mrg_destroy", "mrg_last_error", "mrg_build_info", "mrg_comm_unique_id",
     "mrg_comm_init", "mrg_upload_particles", "mrg_download_particles", "mrg_num_local",
     "mrg_loadpt", "mrg_set_fields", "mrg_set_fields_device", "mrg_fulmov", "mrg_get_moments",
-    "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_prefld", "mrg_get_fields", "mrg_sort", "mrg_set_option",
+    "mrg_get_moments_device", "mrg_get_prepared_fields", "mrg_prefld", "mrg_update_b", "mrg_get_fields", "mrg_sort", "mrg_set_option",
     "mrg_get_counters", "mrg_last_kernel_ms", "mrg_event_record", "mrg_event_elapsed_ms",
     "mrg_synchronize", "mrg_bind_fields_device", "mrg_renew_fields", "mrg_pass_ms", "mrg_get_prep_stats",
     "mrg_set_moment_sink", "mrg_plane_sets", "mrg_compact_layout", "mrg_self_check", "mrg_dfma_peak", "mrg_set_fields_lazy", "mrg_renew_fields_host", "mrg_phase_ms", "mrg_phase_detail", "mrg_peer_export", "mrg_peer_import", "mrg_peer_pushes", "mrg_split_pushes",
@@ -91,6 +91,7 @@ def load(build_if_missing=True):
     L.mrg_get_moments_device.argtypes = [vp, i32, C.POINTER(vp)]
     L.mrg_get_prepared_fields.argtypes = [vp, C.POINTER(StepParams), C.POINTER(dp)]
     L.mrg_prefld.argtypes = [vp, C.c_double, C.c_double]
+    L.mrg_update_b.argtypes = [vp, C.c_double, C.c_double, i32]
     L.mrg_get_fields.argtypes = [vp, C.c_uint32, C.POINTER(dp)]
     L.mrg_sort.argtypes = [vp, i32, C.c_double]
     L.mrg_set_option.argtypes = [vp, C.c_char_p, i64]

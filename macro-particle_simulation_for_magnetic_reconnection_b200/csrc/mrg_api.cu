@@ -1118,6 +1118,28 @@ int mrg_prefld(mrg_ctx* c, double dt, double aimpl) {
   return MRG_OK;
 }
 
+// bx,by,bz as emfild leaves them after its solve (F:4238-4302): prefld's update from the new E (already on the device),
+// then -- on the steps with mod(it,5) = 1 -- outmesh3 + filt3e(sym = +1, no dc), i.e. one z, x and y sweep of the
+// preparation's filter kernels on the three arrays (channels 3..5 carry the B signs of the wall mirror rows).
+int mrg_update_b(mrg_ctx* c, double dt, double aimpl, int32_t smooth) {
+  int rc = mrg_prefld(c, dt, aimpl);
+  if (rc || !smooth) return rc;
+  const GP& g = c->g;
+  const long long n = (long long)g.mx * (g.my + 1) * g.mz;
+  // channels 0..2 ride along on scratch (their results are not used): the sweeps are the 6-channel kernels of ensure_prep
+  CPtr6 s0; Ptr6 d1, d2, d3; CPtr6 c1, c2;
+  for (int k = 0; k < 3; k++) {
+    s0.p[k] = c->T2[k]; d1.p[k] = c->T1[k]; c1.p[k] = c->T1[k]; d2.p[k] = c->T2[k]; c2.p[k] = c->T2[k]; d3.p[k] = c->T1[k];
+    s0.p[k + 3] = c->f12[k + 3]; d1.p[k + 3] = c->T1[k + 3]; c1.p[k + 3] = c->T1[k + 3];
+    d2.p[k + 3] = c->T2[k + 3]; c2.p[k + 3] = c->T2[k + 3]; d3.p[k + 3] = c->f12[k + 3];
+  }
+  k_filter<2><<<grid_for(n, 256), 256, 0, c->stream>>>(g, s0, d1, nullptr, g.mz); CKL(c);
+  k_filter<0><<<grid_for(n, 256), 256, 0, c->stream>>>(g, c1, d2, nullptr, g.mz); CKL(c);
+  k_filter<1><<<grid_for(n, 256), 256, 0, c->stream>>>(g, c2, d3, nullptr, g.mz); CKL(c);
+  c->prep_valid = false;      // T1 / T2 are the preparation's scratch
+  return MRG_OK;
+}
+
 // F:796-807 ("Renewal: ex0 <- ex") on the device copies of the fields.
 int mrg_renew_fields_host(mrg_ctx* c, const double* const old6[6]) {
   if (!c) return fail(MRG_ERR_ARG, "null context");

@@ -21,7 +21,7 @@ struct HostState {
   bool auto_fields = true;
   unsigned dirty = 0xFFFu;     // members of COMMON /fields/ the device copy is stale for
   bool renew = false;          // ex0 <- ex still to be repeated on the device
-  bool prefld = false;         // the host ran prefld: repeat it on the device instead of uploading bx,by,bz
+  int b_pending = -1;          // -1 none; 0 = the host ran prefld, 1 = emfild on a smoothing step: bx,by,bz are recomputed on the device
   bool it0 = false;            // the it = 0 pair of calls has been seen and emfld0 may have rewritten every field since
   int sort_interval = 1;
   bool exit_on_error = true;
@@ -70,7 +70,12 @@ void mrg_host_fields_renewed(void) {
 }
 void mrg_host_prefld_done(void) {                 // after `call prefld` (F:759)
   if (H.auto_fields) H.dirty |= 0x038u;
-  else H.prefld = true;
+  else H.b_pending = 0;
+}
+void mrg_host_emfild_done(void) {                 // after `call emfild` (F:771): only ex,ey,ez cross PCIe
+  if (H.auto_fields || !H.bound) { H.dirty |= 0x03Fu; return; }
+  H.dirty |= 0x007u;
+  H.b_pending = (*H.v.it % 5 == 1) ? 1 : 0;       // F:4298: the smoothing steps
 }
 void mrg_host_set_auto_fields(int32_t on) { H.auto_fields = on != 0; }
 int mrg_host_set_nspecies(int32_t n) {
@@ -132,24 +137,24 @@ void mrg_host_fulmov(double* x, double* y, double* z, double* vx, double* vy, do
   // call after the it = 0 pair uploads everything and drops the pending device renewal (it would copy the pre-emfld0
   // ex..bz into ex0..bz0).
   if (*v.it == 0) H.it0 = true;
-  else if (H.it0) { H.it0 = false; H.dirty = 0xFFFu; H.renew = false; }   // a pending prefld stays: E, e0, b0 arrive with this upload
+  else if (H.it0) { H.it0 = false; H.dirty = 0xFFFu; H.renew = false; }   // a pending B update stays: E, e0, b0 arrive with this upload
   if (H.renew) {                                          // F:796-807 on the device copies
     rc = mrg_renew_fields(H.ctx);
     if (rc) return die("mrg_renew_fields", rc);
     H.renew = false;
     H.dirty &= ~0xFC0u;
   }
-  if (H.prefld) H.dirty &= ~0x038u;                       // bx,by,bz are computed below from what the device holds
+  if (H.b_pending >= 0) H.dirty &= ~0x038u;               // bx,by,bz are computed below from what the device holds
   if (H.dirty) {
     const double* f12[12] = {v.ex, v.ey, v.ez, v.bx, v.by, v.bz, v.ex0, v.ey0, v.ez0, v.bx0, v.by0, v.bz0};
     rc = mrg_set_fields(H.ctx, H.dirty, f12);
     if (rc) return die("mrg_set_fields", rc);
     H.dirty = 0;
   }
-  if (H.prefld) {                                         // entry prefld (F:3820-3873) on the device copies
-    rc = mrg_prefld(H.ctx, *v.dt, *v.aimpl);
-    if (rc) return die("mrg_prefld", rc);
-    H.prefld = false;
+  if (H.b_pending >= 0) {                                 // prefld (F:3820-3873) / emfild's B update (F:4238-4302) on the device copies
+    rc = mrg_update_b(H.ctx, *v.dt, *v.aimpl, H.b_pending);
+    if (rc) return die("mrg_update_b", rc);
+    H.b_pending = -1;
   }
   mrg_step_params p;
   p.dt = *v.dt; p.adt = *v.adt; p.hdt = *v.hdt; p.aimpl = *v.aimpl;

@@ -63,6 +63,9 @@ void mrg_host_fields_changed_mask(uint32_t mask);
 /* After `call prefld` (F:759): with auto fields off the entry is repeated on the device (mrg_prefld, bit-identical to the
  * host's) instead of uploading bx,by,bz; with auto fields on this is mrg_host_fields_changed_mask(0x038).                */
 void mrg_host_prefld_done(void);
+/* After `call emfild` (F:771): with auto fields off only ex,ey,ez are uploaded and bx,by,bz are recomputed on the device as
+ * emfild does behind its solve (mrg_update_b; smoothed when mod(it,5) = 1); else mrg_host_fields_changed_mask(0x03F).   */
+void mrg_host_emfild_done(void);
 void mrg_host_fields_renewed(void);
 /* Cell-sort every n-th corrector call of a species (0 = never). */
 void mrg_host_set_sort_interval(int32_t n);

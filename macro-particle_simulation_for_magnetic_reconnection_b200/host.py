@@ -180,6 +180,10 @@ class MrgContext:
         """entry prefld of emfild (F:3820-3873) on the device copies: bx,by,bz <- b0 - dt curl(ea)"""
         check(self.lib.mrg_prefld(self.h, dt, aimpl))
 
+    def update_b(self, dt, aimpl, smooth):
+        """bx,by,bz as emfild leaves them after its solve (F:4238-4302), from the device's new ex,ey,ez"""
+        check(self.lib.mrg_update_b(self.h, dt, aimpl, 1 if smooth else 0))
+
     def get_fields(self, mask=0xFFF):
         """the device copies of COMMON /fields/ ({index: array} for the members in mask)"""
         out = {k: np.zeros(self.n_grid) for k in range(12) if (mask >> k) & 1}
@@ -338,7 +342,7 @@ class Fulmov:
         self.ctx.set_option("sink_share", 1 if share_moments else 0)
         self.dirty = self.MASK_ALL
         self.renew = False
-        self.prefld_pending = False
+        self.b_pending = None
         self.it0 = False
         self.sort_interval = sort_interval
         self.ncorr = {k: 0 for k in range(1, 5)}
@@ -355,9 +359,19 @@ class Fulmov:
         repeated on the device (mrg_prefld, bit-identical) instead of uploading the three arrays; otherwise this is
         fields_changed(MASK_B)."""
         if self.hints and not self.lazy:
-            self.prefld_pending = True
+            self.b_pending = False
         else:
             self.dirty |= self.MASK_B
+
+    def emfild_done(self):
+        """The host has called emfild (F:771, rewrites ex..bz).  With hints on and whole device arrays only ex,ey,ez are
+        uploaded; bx,by,bz are recomputed on the device exactly as emfild does behind its solve (F:4238-4302, smoothed on
+        the steps with mod(it,5) = 1); otherwise this is fields_changed(MASK_NEW)."""
+        if self.hints and not self.lazy:
+            self.dirty |= 0x007
+            self.b_pending = (self.c.it % 5 == 1)
+        else:
+            self.dirty |= self.MASK_NEW
 
     def fields_renewed(self):
         """The host has copied ex..bz into ex0..bz0 (F:796-807)."""
@@ -391,14 +405,14 @@ class Fulmov:
             self.ctx.renew_fields(self.c.fields()[6:] if self.lazy else None)
             self.renew = False
             self.dirty &= ~self.MASK_OLD
-        if self.prefld_pending:
+        if self.b_pending is not None:
             self.dirty &= ~self.MASK_B               # computed below from what the device holds
         if self.dirty:
             (self.ctx.set_fields_lazy if self.lazy else self.ctx.set_fields)(self.c.fields(), mask=self.dirty)
             self.dirty = 0
-        if self.prefld_pending:
-            self.ctx.prefld(self.c.dt, self.c.aimpl)
-            self.prefld_pending = False
+        if self.b_pending is not None:               # None = nothing to do, False = prefld, True = + the smoothing of emfild
+            self.ctx.update_b(self.c.dt, self.c.aimpl, self.b_pending)
+            self.b_pending = None
 
     def _record_wk(self, ksp, wkix, wkih):
         c = self.c

@@ -302,6 +302,17 @@ void orc_prefld(const orc_parm* p, double* const f12[12]) {
   for (int c = 0; c < 3; c++) free(ea[c]);
 }
 
+/* The magnetic field emfild leaves behind its solve, F:4238-4302: the same update as prefld from the NEW electric field,
+ * and on the steps with mod(it,5) = 1 the smoothing outmesh3 + filt3e(sym = +1, no dc) of bx,by,bz (F:4298-4302).  The
+ * electric field is whatever cfpsol (and, on those steps, its own smoothing F:4225-4229) left in f12[0..2]. */
+void orc_update_b(const orc_parm* p, double* const f12[12], int smooth) {
+  orc_prefld(p, f12);
+  if (smooth) {
+    orc_outmesh3(p, f12[3], f12[4], f12[5]);
+    orc_filt3e(p, f12[3], f12[4], f12[5], 0.0, 0.0, 0.0, p->ifilx, p->ifily, p->ifilz, +1);
+  }
+}
+
 /* ------------------------------------------------------------------------ */
 /* partbc F:1856-1879 (vy != NULL) / partbcEST F:1928-1949 (vy == NULL) */
 static void wrap_one(const orc_parm* p, double* x, double* y, double* z, double* vy) {

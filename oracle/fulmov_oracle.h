@@ -74,6 +74,8 @@ void orc_field_prep(const orc_parm* p, const double* const f12[12],
                     double* const a6[6]);
 /* entry prefld of emfild (F:3820-3873): bx,by,bz <- b0 - dt curl(ea) on the interior nodes; writes f12[3..5] */
 void orc_prefld(const orc_parm* p, double* const f12[12]);
+/* bx,by,bz as emfild leaves them after its solve (F:4238-4302): prefld's update from the new E, smoothed when mod(it,5) = 1 */
+void orc_update_b(const orc_parm* p, double* const f12[12], int smooth);
 
 /* F:1811-1882 and F:1886-1952 on the strided subset l = first, first+stride..*/
 void orc_partbc(const orc_parm* p, double* x, double* y, double* z,

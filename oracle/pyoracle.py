@@ -122,6 +122,14 @@ def prefld(p, f12):
     return f12
 
 
+def update_b(p, f12, smooth):
+    """bx,by,bz as emfild leaves them after its solve (F:4238-4302), in place"""
+    for a in f12:
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+    lib().orc_update_b(C.byref(p), _parr(f12), 1 if smooth else 0)
+    return f12
+
+
 def filt3e(p, ex, ey, ez, dc, sym, ifil=None):
     fx, fy, fz = ifil if ifil is not None else (p.ifilx, p.ifily, p.ifilz)
     lib().orc_filt3e(C.byref(p), _p(ex), _p(ey), _p(ez), dc[0], dc[1], dc[2], fx, fy, fz, sym)

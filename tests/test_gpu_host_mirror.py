@@ -249,3 +249,32 @@ def test_prefld_mark_replaces_the_upload_of_b(case):
     assert out["upload"][1] - out["device"][1] == 3 * 8 * O.mxyzA(p)
     for a, b in zip(out["upload"][2], out["device"][2]):
         assert U.rel_l2(a, b) < 1e-13
+
+
+@pytest.mark.parametrize("smooth", [0, 1])
+def test_device_b_update_after_emfild_bit_exact(case, smooth):
+    """mrg_update_b: bx,by,bz as emfild leaves them behind its solve (F:4238-4302) -- prefld's update from the new E, and on
+    the smoothing steps (mod(it,5) = 1) outmesh3 + filt3e -- against the oracle's orc_update_b, which tests/test_ref_pin.py
+    holds bit for bit to the reference's emfild"""
+    import mrg_b200 as mrg
+    p = case[0]
+    rng = np.random.default_rng(12)
+    f12 = [rng.normal(scale=0.01, size=O.mxyzA(p)) for _ in range(12)]
+    want = O.update_b(p, [a.copy() for a in f12], smooth)
+    ctx = mrg.MrgContext(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax)
+    ctx.set_fields(f12)
+    ctx.update_b(p.dt, p.aimpl, smooth)
+    got = ctx.get_fields(0x038)
+    # the scratch of the sweeps is the preparation's: a preparation afterwards must still be right
+    par = mrg.StepParams(p.dt, p.adt, p.hdt, p.aimpl, p.bxc, p.byc, p.bzc, 1, 1, 1, 1, p.Ez00, p.zcent, p.ycent1, p.ycent2)
+    a6 = ctx.prepared_fields(par)
+    ctx.close()
+    sh = (p.mz + 4, p.my + 3, p.mx + 4)
+    inner = (slice(2, p.mz + 2), slice(1, p.my + 2), slice(2, p.mx + 2))
+    for c in (3, 4, 5):
+        np.testing.assert_array_equal(got[c].reshape(sh)[inner], want[c].reshape(sh)[inner])
+    full = [a.copy() for a in f12]
+    for c in (3, 4, 5):
+        full[c].reshape(sh)[inner] = want[c].reshape(sh)[inner]
+    for a, b in zip(a6, O.field_prep(p, full)):
+        np.testing.assert_array_equal(a, b)

@@ -320,3 +320,30 @@ def test_prefld_bit_identical(grid):
             np.testing.assert_array_equal(a, b)                                 # nothing else is written
     np.testing.assert_array_equal(mine[4].reshape(sh)[2:mz + 2, 1, 2:mx + 2], 0.0)          # by = 0 on the walls
     np.testing.assert_array_equal(mine[4].reshape(sh)[2:mz + 2, my + 1, 2:mx + 2], 0.0)
+
+
+@needs_ref
+def test_b_after_emfild_is_prefld_of_the_new_e():
+    """What emfild leaves in bx,by,bz behind its solve (F:4238-4302) is prefld's update from the new ex,ey,ez, smoothed by
+    outmesh3 + filt3e(sym=+1) on the steps with mod(it,5) = 1: the oracle's orc_update_b reproduces the reference's own
+    arrays bit for bit on six consecutive steps of the reference's time cycle (two of them smoothing steps)."""
+    grid = (8, 6, 8)
+    p = U.make_parm(*grid)
+    sh = (grid[2] + 4, grid[1] + 3, grid[0] + 4)
+    inner = (slice(2, grid[2] + 2), slice(1, grid[1] + 2), slice(2, grid[0] + 2))
+    smoothed = 0
+    with PR.ReferenceLoop(grid, (p.xmax, p.ymax, p.zmax), 2) as A:
+        A.startup()
+        for _ in range(6):
+            A.begin_step(); A.fulmov(1); A.emfild()
+            f = A.fields()
+            smooth = A.it % 5 == 1
+            smoothed += smooth
+            mine = O.update_b(p, [a.copy() for a in f], smooth)
+            for c in (3, 4, 5):
+                np.testing.assert_array_equal(mine[c].reshape(sh)[inner], f[c].reshape(sh)[inner])
+            if smooth:                                          # ... and the smoothing is not a no-op
+                plain = O.prefld(p, [a.copy() for a in f])
+                assert np.abs(plain[3].reshape(sh)[inner] - f[3].reshape(sh)[inner]).max() > 0
+            A.fulmov(0); A.renew()
+    assert smoothed == 2
