@@ -23,7 +23,8 @@
 !*        call mrg_host_set_auto_fields(0)         ! once, before trans *
 !*        call mrg_host_prefld_done()              ! after prefld F:759 *
 !*          (the entry is repeated on the device; ..._mask(56) uploads) *
-!*        call mrg_host_fields_changed_mask(63)    ! after emfild F:771 *
+!*        call mrg_host_emfild_done()              ! after emfild F:771 *
+!*          (only ex,ey,ez are uploaded; ..._mask(63) uploads all six)  *
 !*        call mrg_host_fields_renewed()           ! after F:796-807    *
 !***********************************************************************
       module mrg_gpu
@@ -97,6 +98,10 @@
         subroutine mrg_host_prefld_done () &
                      bind(C,name='mrg_host_prefld_done')
         end subroutine mrg_host_prefld_done
+!
+        subroutine mrg_host_emfild_done () &
+                     bind(C,name='mrg_host_emfild_done')
+        end subroutine mrg_host_emfild_done
 !
         subroutine mrg_host_fields_renewed () &
                      bind(C,name='mrg_host_fields_renewed')
