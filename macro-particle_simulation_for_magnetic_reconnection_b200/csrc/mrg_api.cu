@@ -168,6 +168,7 @@ struct mrg_ctx {
   // device copy f12[k] already holds; ensure_prep fetches the planes a preparation reads and nothing else
   const double* fhost[12] = {};
   bool flazy[12] = {};
+  double b_dt = 0.0, b_aimpl = 0.0;   // lazily held fields with fhost[3..5] == nullptr: bx,by,bz planes are COMPUTED (k_prefld) when a preparation needs them
   std::vector<char> fplane[12];
   double* T1[6] = {};
   double* T2[6] = {};
@@ -678,22 +679,37 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   const int B = 256;
   const int *dB = nullptr, *dGI = nullptr, *dG = nullptr;
   int nB = mz, nGI = mz, nG = nz;
-  if (restricted) {
-    if (!c->plane_lists) CK(cudaMalloc((void**)&c->plane_lists, (size_t)(3 * (nz + 4)) * sizeof(int)));
-    std::vector<int> all(3 * (nz + 4), 0);
+  auto in_b = [&](int k) { return restricted ? std::binary_search(listB.begin(), listB.end(), k) : true; };
+  // bx,by,bz held as "to be computed" (mrg_update_b on lazily held fields): the planes the blend needs and the device has not made yet
+  const bool bcomp = c->flazy[3] && !c->fhost[3];
+  std::vector<int> bmiss;
+  std::vector<char> bm(mz, 0);
+  if (bcomp)
+    for (int k = 0; k < mz; k++)
+      if (in_b(k) && !c->fplane[3][k]) { bmiss.push_back(k); bm[k] = 1; }
+  const int* dBm = nullptr;
+  if (restricted || !bmiss.empty()) {
+    if (!c->plane_lists) CK(cudaMalloc((void**)&c->plane_lists, (size_t)(4 * (nz + 4)) * sizeof(int)));
+    std::vector<int> all(4 * (nz + 4), 0);
     std::copy(listB.begin(), listB.end(), all.begin());
     std::copy(listGI.begin(), listGI.end(), all.begin() + (nz + 4));
     std::copy(listG.begin(), listG.end(), all.begin() + 2 * (nz + 4));
+    std::copy(bmiss.begin(), bmiss.end(), all.begin() + 3 * (nz + 4));
     CK(cudaMemcpyAsync(c->plane_lists, all.data(), all.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     CK(cudaStreamSynchronize(c->stream));   // `all` is pageable and goes out of scope
+    dBm = c->plane_lists + 3 * (nz + 4);
+  }
+  if (restricted) {
     dB = c->plane_lists; dGI = c->plane_lists + (nz + 4); dG = c->plane_lists + 2 * (nz + 4);
     nB = (int)listB.size(); nGI = (int)listGI.size(); nG = (int)listG.size();
   }
-  // lazily held host fields: fetch the interior planes the blend is about to read (F:1127-1139 reads k = 0..mz-1 only)
+  // lazily held host fields: fetch the interior planes the blend is about to read (F:1127-1139 reads k = 0..mz-1 only) --
+  // and, for ex..ez / ex0..ez0, the planes k, k+-1 (periodic) the B update of the missing bx,by,bz planes reads (F:3834-3880)
   for (int a = 0; a < 12; a++) {
-    if (!c->flazy[a]) continue;
+    if (!c->flazy[a] || !c->fhost[a]) continue;
     std::vector<char>& have = c->fplane[a];
-    auto need = [&](int k) { return restricted ? std::binary_search(listB.begin(), listB.end(), k) : true; };
+    const bool for_b = !bmiss.empty() && (a <= 2 || (a >= 6 && a <= 8));
+    auto need = [&](int k) { return in_b(k) || (for_b && (bm[k] || bm[k + 1 < mz ? k + 1 : 0] || bm[k > 0 ? k - 1 : mz - 1])); };
     for (int k = 0; k < mz;) {
       if (have[k] || !need(k)) { k++; continue; }
       int k1 = k;
@@ -706,6 +722,11 @@ int ensure_prep(mrg_ctx* c, const mrg_step_params* p, int ksp) {
   }
   const long long per = (long long)g.mx * (g.my + 1);
   CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->fcur[k];
+  if (!bmiss.empty()) {      // prefld / emfild's B update on exactly those planes (bit-identical to the host's arrays)
+    k_prefld<<<grid_for(per * (long long)bmiss.size(), B), B, 0, c->stream>>>(g, f, c->f12[3], c->f12[4], c->f12[5], c->b_aimpl, 1.0 - c->b_aimpl,
+                                                                       c->b_dt, 2.0 * g.hx, 2.0 * g.hy, 2.0 * g.hz, dBm, (int)bmiss.size()); CKL(c);
+    for (int k : bmiss) c->fplane[3][k] = c->fplane[4][k] = c->fplane[5][k] = 1;
+  }
   Ptr6 T1, T2; for (int k = 0; k < 6; k++) { T1.p[k] = c->T1[k]; T2.p[k] = c->T2[k]; }
   const double om = 1.0 - p->aimpl;
   // blend (+ first z sweep) -> remaining sweeps -> finalize (+ last y sweep): three kernels for the usual ifil* = 1
@@ -1098,34 +1119,39 @@ int mrg_set_fields_lazy(mrg_ctx* c, uint32_t mask, const double* const f12[12]) 
 }
 
 // entry prefld of emfild (F:3820-3873) on the device copies: bx, by, bz from ex..ez, ex0..ez0, bx0..bz0 -- bit-identical to
-// the host's prefld, which therefore need not upload the three arrays in front of the predictor pass.
-int mrg_prefld(mrg_ctx* c, double dt, double aimpl) {
+// the host's prefld, which therefore need not upload the three arrays in front of the predictor pass -- and
+// the same update as emfild performs it behind its solve (F:4238-4302): from the new E, and on the steps with
+// mod(it,5) = 1 followed by outmesh3 + filt3e(sym = +1, no dc), i.e. one z, x and y sweep of the preparation's filter
+// kernels on the three arrays (channels 3..5 carry the B signs of the wall mirror rows).
+// With lazily held fields (each rank has only the planes its preparations fetched) nothing is computed here: bx,by,bz
+// become "to be computed", and every preparation makes exactly the planes it reads after fetching the planes of ex..ez,
+// ex0..ez0 around them (ensure_prep).  The smoothing needs whole arrays and is refused in that mode (the host uploads).
+int mrg_update_b(mrg_ctx* c, double dt, double aimpl, int32_t smooth) {
   if (!c) return fail(MRG_ERR_ARG, "null context");
   if (!c->fields_set) return fail(MRG_ERR_STATE, "mrg_set_fields has not been called");
-  for (int k = 0; k < 12; k++)
-    if (c->flazy[k] && !(k >= 3 && k <= 5))
-      return fail(MRG_ERR_STATE, "fields are held lazily: the device does not hold the whole arrays prefld reads");
   CK(cudaSetDevice(c->device));
   for (int k = 0; k < c->nspecies; k++)
     if (c->sp[k].pending) CK(cudaStreamWaitEvent(c->stream, c->sp[k].done, 0));
   const GP& g = c->g;
+  bool lazy = false;
+  for (int k = 0; k < 12; k++)
+    if (c->flazy[k] && !(k >= 3 && k <= 5)) lazy = true;
+  if (lazy) {
+    if (smooth) return fail(MRG_ERR_STATE, "fields are held lazily: the smoothing of bx,by,bz needs whole arrays (upload them instead)");
+    for (int k = 3; k <= 5; k++) {
+      c->flazy[k] = true; c->fhost[k] = nullptr; c->fplane[k].assign(g.mz, 0); c->fcur[k] = c->f12[k];
+    }
+    c->b_dt = dt; c->b_aimpl = aimpl;
+    c->field_version++;
+    return MRG_OK;
+  }
   CPtr12 f; for (int k = 0; k < 12; k++) f.p[k] = c->fcur[k];
   const long long n = (long long)g.mx * (g.my + 1) * g.mz;
   k_prefld<<<grid_for(n, 256), 256, 0, c->stream>>>(g, f, c->f12[3], c->f12[4], c->f12[5], aimpl, 1.0 - aimpl, dt,
-                                                     2.0 * g.hx, 2.0 * g.hy, 2.0 * g.hz); CKL(c);
+                                                     2.0 * g.hx, 2.0 * g.hy, 2.0 * g.hz, nullptr, g.mz); CKL(c);
   for (int k = 3; k <= 5; k++) { c->fcur[k] = c->f12[k]; c->flazy[k] = false; }
   c->field_version++;
-  return MRG_OK;
-}
-
-// bx,by,bz as emfild leaves them after its solve (F:4238-4302): prefld's update from the new E (already on the device),
-// then -- on the steps with mod(it,5) = 1 -- outmesh3 + filt3e(sym = +1, no dc), i.e. one z, x and y sweep of the
-// preparation's filter kernels on the three arrays (channels 3..5 carry the B signs of the wall mirror rows).
-int mrg_update_b(mrg_ctx* c, double dt, double aimpl, int32_t smooth) {
-  int rc = mrg_prefld(c, dt, aimpl);
-  if (rc || !smooth) return rc;
-  const GP& g = c->g;
-  const long long n = (long long)g.mx * (g.my + 1) * g.mz;
+  if (!smooth) return MRG_OK;
   // channels 0..2 ride along on scratch (their results are not used): the sweeps are the 6-channel kernels of ensure_prep
   CPtr6 s0; Ptr6 d1, d2, d3; CPtr6 c1, c2;
   for (int k = 0; k < 3; k++) {
@@ -1139,6 +1165,7 @@ int mrg_update_b(mrg_ctx* c, double dt, double aimpl, int32_t smooth) {
   c->prep_valid = false;      // T1 / T2 are the preparation's scratch
   return MRG_OK;
 }
+int mrg_prefld(mrg_ctx* c, double dt, double aimpl) { return mrg_update_b(c, dt, aimpl, 0); }
 
 // F:796-807 ("Renewal: ex0 <- ex") on the device copies of the fields.
 int mrg_renew_fields_host(mrg_ctx* c, const double* const old6[6]) {

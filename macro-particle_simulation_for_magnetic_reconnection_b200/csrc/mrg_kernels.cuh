@@ -116,9 +116,10 @@ __device__ __forceinline__ double blend_E(const CPtr12& f, int c, int m, double 
   return __dadd_rn(__dmul_rn(aimpl, f.p[c][m]), __dmul_rn(om, f.p[c + 6][m]));
 }
 __global__ void k_prefld(GP g, CPtr12 f, double* __restrict__ bx, double* __restrict__ by, double* __restrict__ bz,
-                         double aimpl, double om, double dt, double hx2, double hy2, double hz2) {
+                         double aimpl, double om, double dt, double hx2, double hy2, double hz2,
+                         const int* __restrict__ planes, int nplanes) {
   int i, j, k;
-  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, nullptr, g.mz, i, j, k)) return;
+  if (!interior_ijk(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, planes, nplanes, i, j, k)) return;
   const int kr = (k == g.mz - 1) ? 0 : k + 1, kl = (k == 0) ? g.mz - 1 : k - 1;      // pzr, pzl (F:8399-8422)
   const int ir = (i == g.mx - 1) ? 0 : i + 1, il = (i == 0) ? g.mx - 1 : i - 1;      // pxr, pxl (F:8341-8364)
   const int m = node_of(g, i, j, k);

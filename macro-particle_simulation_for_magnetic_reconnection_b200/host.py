@@ -356,9 +356,9 @@ class Fulmov:
 
     def prefld_done(self):
         """The host has called prefld (F:759, rewrites bx,by,bz).  With hints on and whole device arrays the same entry is
-        repeated on the device (mrg_prefld, bit-identical) instead of uploading the three arrays; otherwise this is
-        fields_changed(MASK_B)."""
-        if self.hints and not self.lazy:
+        repeated on the device (mrg_prefld, bit-identical) instead of uploading the three arrays -- with lazily held fields on
+        exactly the planes each preparation reads; without hints this is fields_changed(MASK_B)."""
+        if self.hints:
             self.b_pending = False
         else:
             self.dirty |= self.MASK_B
@@ -367,9 +367,10 @@ class Fulmov:
         """The host has called emfild (F:771, rewrites ex..bz).  With hints on and whole device arrays only ex,ey,ez are
         uploaded; bx,by,bz are recomputed on the device exactly as emfild does behind its solve (F:4238-4302, smoothed on
         the steps with mod(it,5) = 1); otherwise this is fields_changed(MASK_NEW)."""
-        if self.hints and not self.lazy:
+        smooth = self.c.it % 5 == 1
+        if self.hints and not (self.lazy and smooth):      # the smoothing needs whole arrays: lazily held fields upload B then
             self.dirty |= 0x007
-            self.b_pending = (self.c.it % 5 == 1)
+            self.b_pending = smooth
         else:
             self.dirty |= self.MASK_NEW
 

@@ -346,3 +346,63 @@ def test_fast_particles_disable_the_plane_record(mrg):
     assert st_gpu == int(st[0])
     assert sum(restricted[2:]) == 0, restricted        # after the first corrector reported the violation: full preparations only
     ctx.close()
+
+
+@pytest.mark.parametrize("planes", [0, 1])
+def test_lazy_fields_with_the_b_updates_on_the_device(mrg, planes):
+    """The same protocol with the two marks that keep bx,by,bz off PCIe (Fulmov.prefld_done / emfild_done): with lazily held
+    fields every preparation computes exactly the planes of bx,by,bz it reads, after fetching the planes of ex..ez, ex0..ez0
+    around them.  The host's arrays are what its own prefld / emfild would hold (the oracle's orc_update_b, pinned to the
+    reference); results match the oracle on whole arrays, and on the steps without smoothing no plane of bx,by,bz is uploaded."""
+    p = U.make_parm(12, 10, 24)
+    sp_all, ranfb = U.load_species(p, 10)
+    sp = slab_subset(p, sp_all, 7.0, 12.0)
+    n = {k: len(sp[k][0]) for k in (1, 2)}
+    ref = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.array([ranfb], dtype=np.int32)
+    c = mrg.Common(p.mx, p.my, p.mz, p.xmax, p.ymax, p.zmax, dt=p.dt, aimpl=p.aimpl, wce_by_wpe=p.bxc, Ez00=p.Ez00)
+    c.ranfb, c.it = ranfb, 4                                   # steps it = 4, 5, 6: the last one smooths (mod(it,5) = 1)
+    fm = mrg.Fulmov(c, ipar=1, size=1, hints=True, lazy=True)
+    fm.ctx.set_option("planes", planes)
+    FN = mrg.host.FIELD_NAMES
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    for name, a in zip(FN, U.smooth_fields(p, seed=500, ghost_nan=False)):
+        setattr(c, name, a.copy())
+    per_step = []
+    for step in range(3):
+        fm.ctx.counters(reset=True)
+        hb = O.update_b(p, [np.ascontiguousarray(a).copy() for a in c.fields()], 0)           # the host's prefld
+        for i in (3, 4, 5):
+            setattr(c, FN[i], hb[i])
+        fm.prefld_done()
+        a6 = O.field_prep(p, c.fields())
+        for k in (1, 2):
+            r = O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 1, nranks=1, ranfb=st)
+            fm(*host[k], U.QSPEC[k], U.WSPEC[k], n[k], 1, k)
+            got = (c.qix, c.qiy, c.qiz, c.qi) if k == 1 else (c.qex, c.qey, c.qez, c.qe)
+            for ci in range(4):
+                assert U.rel_l2(got[ci], r["mom"][ci]) < MTOL, (step, k, ci)
+        f_n = U.smooth_fields(p, seed=520 + step, ghost_nan=False)                             # the host's emfild: new E ...
+        for i in range(3):
+            setattr(c, FN[i], f_n[i].copy())
+        hb = O.update_b(p, [np.ascontiguousarray(a).copy() for a in c.fields()], c.it % 5 == 1)   # ... and the B it leaves
+        for i in (3, 4, 5):
+            setattr(c, FN[i], hb[i])
+        fm.emfild_done()
+        a6 = O.field_prep(p, c.fields())
+        for k in (1, 2):
+            O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 0, nranks=1, ranfb=st)
+            fm(*host[k], U.QSPEC[k], U.WSPEC[k], n[k], 0, k)
+        assert c.ranfb == int(st[0])
+        for i in range(6):
+            setattr(c, FN[i + 6], getattr(c, FN[i]).copy())
+        fm.fields_renewed()
+        per_step.append(fm.ctx.counters()["h2d_bytes"] - (48 * (n[1] + n[2]) if step == 0 else 0))
+        c.it += 1
+    for k in (1, 2):
+        fm.pull(k, *host[k], n[k])
+        assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < 30 * PTOL, k
+    # step 2 (it = 5): nothing but planes of ex,ey,ez (+ what the widened halo of the B update asks of the old arrays)
+    assert per_step[1] <= 8 * O.mxyzA(p) * 3 * 1.35, per_step
+    assert per_step[2] > per_step[1]                           # the smoothing step uploads bx,by,bz as well
+    fm.ctx.close()
