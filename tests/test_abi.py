@@ -41,6 +41,14 @@ def test_host_mirror_exports_reference_signature():
     for n in ("mrg_host_fulmov", "mrg_host_bind", "mrg_host_pull_particles", "mrg_host_particles_changed",
               "mrg_host_fields_changed", "mrg_host_set_unique_id"):
         assert hasattr(lib, n), n
+    # ... and everything else the two host headers declare (the marks of the hint protocol, the abort hook, the restart records)
+    csrc = os.path.join(ROOT, "macro-particle_simulation_for_magnetic_reconnection_b200", "csrc")
+    for hdr in ("mrg_host.h", "mrg_restart.h"):
+        txt = re.sub(r"/\*.*?\*/", "", open(os.path.join(csrc, hdr)).read(), flags=re.S)
+        names = sorted(set(re.findall(r"\b(mrg_(?:host|f77|restart)_[a-z_0-9]+)\s*\(", txt)))
+        assert len(names) >= 4, hdr
+        for n in names:
+            assert hasattr(lib, n), (hdr, n)
 
 
 @pytest.mark.skipif(HAS_GPU, reason="checks the CPU-only failure mode")
