@@ -4,7 +4,7 @@
       subroutine arith (iout,rout)
       use, intrinsic :: iso_c_binding
       implicit none
-      include 'param_080A.h'
+      include 'case_sizes.h'
       integer(C_INT) iout(10),i,j
       real(C_DOUBLE) rout(10),x,y
       real(C_float)  s
@@ -84,7 +84,7 @@
       subroutine blocks_a
       use, intrinsic :: iso_c_binding
       implicit none
-      include 'param_080A.h'
+      include 'case_sizes.h'
       real(C_DOUBLE) a(-2:mx+1,0:my),b(3)
       integer(C_INT) kk
       common/blk/ a,b,kk
@@ -107,7 +107,7 @@
 !  another view of the same storage sequence: one long vector + the tail
       use, intrinsic :: iso_c_binding
       implicit none
-      include 'param_080A.h'
+      include 'case_sizes.h'
       real(C_DOUBLE) v((mx+4)*(my+1)),c1,c2,c3,sout(4)
       integer(C_INT) kk
       common/blk/ v,c1,c2,c3,kk
@@ -207,7 +207,7 @@
       use, intrinsic :: iso_c_binding
       implicit none
       include 'mpif.h'
-      include 'param_080A.h'
+      include 'case_sizes.h'
       integer(C_INT) rank,up,dn,ierror
       real(C_DOUBLE) rout(3),sbuf(2),rbuf(2),part(1),tot(1)
       integer(kind=4),dimension(MPI_STATUS_SIZE) :: st1,st2

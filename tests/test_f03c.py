@@ -23,7 +23,7 @@ UNITS = ["arith", "loops", "blocks_a", "blocks_b", "caller", "overlay", "twodoor
 def lib(tmp_path_factory):
     import f03c
     out = tmp_path_factory.mktemp("f03c")
-    src, _ = f03c.translate(os.path.join(CASES, "semantics.f03"), [CASES], UNITS)
+    src, _ = f03c.translate(os.path.join(CASES, "semantics.f03"), [CASES], UNITS, param_include="case_sizes.h")
     with open(os.path.join(out, "mrgref_gen.c"), "w") as f:
         f.write(src)
     so = os.path.join(out, "libcases.so")
