@@ -347,3 +347,20 @@ def test_b_after_emfild_is_prefld_of_the_new_e():
                 assert np.abs(plain[3].reshape(sh)[inner] - f[3].reshape(sh)[inner]).max() > 0
             A.fulmov(0); A.renew()
     assert smoothed == 2
+
+
+@needs_ref
+def test_bench_reference_arm_on_a_tiny_sample(monkeypatch):
+    """bench.py --impl reference / cpu_baseline: the reference's own time cycle timed with its three timers (F:813-822);
+    here on an 8 x 6 x 8 sample with 2 ranks so that the leg the driver runs on the GPU box is exercised on every CPU run"""
+    import importlib
+    import sys as _sys
+    _sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    monkeypatch.setitem(bench.CPU_SAMPLE, "grid", (8, 6, 8))
+    r = bench.cpu_reference_rate(2, 1, nthreads=2)
+    assert r["kind"] == "reference" and r["cores"] == 2
+    assert r["value"] > 0 and r["ful1_s_per_step"] > 0 and r["ful0_s_per_step"] > 0 and r["em_s_per_step"] > 0
+    rec = bench.cpu_baseline_record(r)
+    assert rec["unit"] == bench.UNIT and "ful(1)_s_per_step" in rec and "em_s_per_step" in rec
+    assert "2 species = %d particles" % (2 * 32 * 8 * 6 * 8) in rec["sample"]
