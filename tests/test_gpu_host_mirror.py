@@ -278,3 +278,90 @@ def test_device_b_update_after_emfild_bit_exact(case, smooth):
         full[c].reshape(sh)[inner] = want[c].reshape(sh)[inner]
     for a, b in zip(a6, O.field_prep(p, full)):
         np.testing.assert_array_equal(a, b)
+
+
+def test_cpp_mirror_marks_keep_b_on_the_device(case):
+    """The C++ mirror in hints mode with the marks a Fortran host would place (mrg_host_prefld_done, mrg_host_emfild_done,
+    mrg_host_fields_renewed): bx,by,bz are never uploaded after the first call, yet two steps (the second one a smoothing
+    step of emfild, it = 6) match the oracle run on the host's whole arrays."""
+    import mrg_b200 as mrg
+    p, sp, ranfb, f_a, _ = case
+    mrg.build.build_host()
+    lib = C.CDLL(mrg.build.HOSTLIB)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    lib.mrg_host_fulmov.argtypes = [dp] * 8 + [ip] * 5
+    lib.mrg_host_fulmov.restype = None
+    lib.mrg_host_pull_particles.argtypes = [C.c_int32] + [dp] * 6 + [C.c_int32] * 3
+    lib.mrg_host_context.restype = C.c_void_p
+    n = O.mxyzA(p)
+    store = {}
+    v = View()
+    v.mx, v.my, v.mz = p.mx, p.my, p.mz
+    fnames = ("ex", "ey", "ez", "bx", "by", "bz", "ex0", "ey0", "ez0", "bx0", "by0", "bz0")
+    f_start = U.smooth_fields(p, seed=31, ghost_nan=False)
+    for name, arr in zip(fnames, f_start):
+        store[name] = arr.copy()
+        setattr(v, name, store[name].ctypes.data_as(dp))
+    for name in ("qix", "qiy", "qiz", "qex", "qey", "qez", "qi", "qe"):
+        store[name] = np.zeros(n)
+        setattr(v, name, store[name].ctypes.data_as(dp))
+    for name, val in (("it", 5), ("ldec", 2), ("ifilx", 1), ("ifily", 1), ("ifilz", 1), ("nha", 5), ("ranfb", ranfb), ("io_pe", 0)):
+        store[name] = np.array([val], dtype=np.int32)
+        setattr(v, name, store[name].ctypes.data_as(ip))
+    for name, val in (("xmax", p.xmax), ("ymax", p.ymax), ("zmax", p.zmax), ("dt", p.dt), ("aimpl", p.aimpl),
+                      ("adt", p.adt), ("hdt", p.hdt), ("bxc", p.bxc), ("byc", p.byc), ("bzc", p.bzc),
+                      ("wkix", 0.0), ("wkih", 0.0), ("zcent", p.zcent), ("ycent1", p.ycent1), ("ycent2", p.ycent2), ("Ez00", p.Ez00)):
+        store[name] = np.array([val])
+        setattr(v, name, store[name].ctypes.data_as(dp))
+    store["edec"] = np.zeros(3000 * 12)
+    v.edec = store["edec"].ctypes.data_as(dp)
+    assert lib.mrg_host_bind(C.byref(v), 0) == 0
+    lib.mrg_host_set_exit_on_error(0)
+    lib.mrg_host_set_auto_fields(0)
+    host = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    ref = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.array([ranfb], dtype=np.int32)
+    npr = C.c_int32(len(sp[1][0]))
+    one, size = C.c_int32(1), C.c_int32(1)
+
+    def call(k, ipc):
+        q, w = C.c_double(U.QSPEC[k]), C.c_double(U.WSPEC[k])
+        lib.mrg_host_fulmov(*[a.ctypes.data_as(dp) for a in host[k]], C.byref(q), C.byref(w), C.byref(npr),
+                            C.byref(C.c_int32(ipc)), C.byref(C.c_int32(k)), C.byref(one), C.byref(size))
+        assert lib.mrg_host_status() == 0
+
+    def fields():
+        return [store[nm] for nm in fnames]
+
+    for it in (5, 6):
+        store["it"][0] = it
+        hb = O.update_b(p, [a.copy() for a in fields()], 0)                    # the host's prefld
+        for i in (3, 4, 5):
+            store[fnames[i]][:] = hb[i]
+        lib.mrg_host_prefld_done()
+        a6 = O.field_prep(p, fields())
+        for k in (1, 2):
+            r = O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 1, nranks=1, ranfb=st)
+            call(k, 1)
+            names = ("qix", "qiy", "qiz", "qi") if k == 1 else ("qex", "qey", "qez", "qe")
+            for cidx, name in enumerate(names):
+                assert U.rel_l2(store[name], r["mom"][cidx]) < MTOL, (it, name)
+        f_n = U.smooth_fields(p, seed=40 + it, ghost_nan=False)               # the host's emfild: new E and the B it leaves
+        for i in range(3):
+            store[fnames[i]][:] = f_n[i]
+        hb = O.update_b(p, [a.copy() for a in fields()], it % 5 == 1)
+        for i in (3, 4, 5):
+            store[fnames[i]][:] = hb[i]
+        lib.mrg_host_emfild_done()
+        a6 = O.field_prep(p, fields())
+        for k in (1, 2):
+            O.fulmov(p, a6, *ref[k], U.QSPEC[k], U.WSPEC[k], 0, nranks=1, ranfb=st)
+            call(k, 0)
+        assert int(store["ranfb"][0]) == int(st[0])
+        for i in range(6):                                                     # renewal + its mark
+            store[fnames[i + 6]][:] = store[fnames[i]]
+        lib.mrg_host_fields_renewed()
+    for k in (1, 2):
+        assert lib.mrg_host_pull_particles(k, *[a.ctypes.data_as(dp) for a in host[k]], npr.value, 1, 1) == 0
+        assert U.particle_err(host[k], ref[k], p.hx, U.vth(k)) < 4 * PTOL
+    lib.mrg_host_unbind()
