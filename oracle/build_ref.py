@@ -23,7 +23,7 @@ GEN = os.path.join(OUT, "mrgref_gen.c")
 LIB = os.path.join(OUT, "libmrg_ref.so")
 
 # entry units; everything they call is pulled in by the translator
-UNITS = ["fulmov", "rantbl", "ranf", "ranfp", "loadpt", "init", "emfld0", "emfild", "prefld"]
+UNITS = ["fulmov", "rantbl", "ranf", "ranfp", "loadpt", "init", "emfld0", "emfild", "prefld", "restrt"]
 # out-of-scope callees whose calls are dropped: PostScript plots, labels, wall clocks
 STUBS = ["fplot3", "cplot3", "lblbot", "lbltop", "clocks", "clocki", "lplots", "lplot1", "hplot1", "lplmax", "lplmax1"]
 

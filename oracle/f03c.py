@@ -442,6 +442,7 @@ IO_RE = re.compile(r"^(write|read|open|close|print|format|rewind|backspace|flush
 class Translator:
     def __init__(self, path, include_dirs, runtime_params, want, stubs=()):
         self.stubs = set(stubs)
+        self.unf_units = set()     # unit numbers opened with form='unformatted' somewhere in the translated units
         self.path = path
         self.include_dirs = include_dirs
         self.runtime_params = set(runtime_params)     # parameter names that become run-time globals
@@ -1080,8 +1081,68 @@ class Translator:
         if label:
             self.close_dos(label, L, ctx)
 
+    # -- unformatted sequential I/O (the restart file of restrt, F:9696-9726 / 9731-9751) ----------------------------------
+    UNF_RE = re.compile(r"^(write|read)\s*\(\s*(\d+)\s*\)\s*(.*)$")
+
+    def emit_io_item(self, u, item, L, ctx, ind):
+        """one io-list item: a scalar, an array element, a whole array, or an implied DO (item, ..., v = lo, hi)"""
+        item = item.strip()
+        if item.startswith("(") and match_paren(item, 0) == len(item) - 1:
+            parts = split_top(item[1:-1])
+            m = re.match(r"^([a-z_][a-z0-9_]*)\s*=\s*(.+)$", parts[-2].strip()) if len(parts) >= 3 else None
+            if m:                                        # implied DO
+                var, lo, hi = m.group(1), m.group(2), parts[-1]
+                cv = self.emit_var(u, var, ctx)
+                L.append("%sfor (%s = %s; %s <= %s; %s++) {" % (ind, cv, self.emit_expr(u, parse_expr(lo), ctx), cv,
+                                                              self.emit_expr(u, parse_expr(hi), ctx), cv))
+                for sub in parts[:-2]:
+                    self.emit_io_item(u, sub, L, ctx, ind + "  ")
+                L.append("%s}" % ind)
+                return
+        e = parse_expr(item)
+        if e[0] == "var":
+            sy = u.sym.get(e[1])
+            if sy is None or sy.kind == "param" or sy.is_char:
+                raise SyntaxError("io-list item %r" % item)
+            if sy.dims:
+                L.append("%sref_rec_item((void*)%s, %d * (long)(%s));" % (ind, self.cvar(e[1]), BYTES[sy.type], self.array_count(u, sy, ctx)))
+            else:
+                L.append("%sref_rec_item(%s, %d);" % (ind, self.emit_actual(u, e, None, 0, ctx), BYTES[sy.type]))
+            return
+        if e[0] == "call":
+            sy = u.sym.get(e[1])
+            if sy and sy.dims:
+                L.append("%sref_rec_item((void*)&%s[%s], %d);" % (ind, self.cvar(e[1]), self.emit_index(u, sy, e[2], ctx), BYTES[sy.type]))
+                return
+        raise SyntaxError("io-list item %r is not a variable" % item)
+
+    def translate_unformatted(self, u, s, L, ctx):
+        """write(u) list / read(u) list / open(unit=u,...form='unformatted') / close(u): True when the statement was one"""
+        m = self.UNF_RE.match(s)
+        if m:
+            L.append("  ref_rec_begin(%s, %d);" % (m.group(2), 1 if m.group(1) == "write" else 0))
+            for item in split_top(m.group(3)):
+                if item.strip():
+                    self.emit_io_item(u, item, L, ctx, "  ")
+            L.append("  ref_rec_end();")
+            return True
+        m = re.match(r"^open\s*\((.*)\)$", s)
+        if m and re.search(r"form\s*=\s*'unformatted'", m.group(1)):
+            mu = re.search(r"unit\s*=\s*(\d+)", m.group(1))
+            if mu:
+                L.append("  ref_unit_open(%s, %d);" % (mu.group(1), 1 if re.search(r"status\s*=\s*'replace'", m.group(1)) else 0))
+                self.unf_units.add(mu.group(1))
+                return True
+        m = re.match(r"^close\s*\(\s*(?:unit\s*=\s*)?(\d+)\s*\)$", s)
+        if m and m.group(1) in self.unf_units:
+            L.append("  ref_unit_close(%s);" % m.group(1))
+            return True
+        return False
+
     def translate_simple(self, u, n, s, L, ctx):
         if IO_RE.match(s) and not re.match(r"^(write|read|open|close|print|format|rewind|backspace|flush)\s*=", s):
+            if self.translate_unformatted(u, s, L, ctx):
+                return
             L.append("  /* F:%d I/O statement dropped */" % n)
             return
         if s == "continue":

@@ -52,6 +52,8 @@ def _bind(L):
     L.ref_common.restype = C.c_void_p
     L.ref_call.argtypes = [C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.ref_has_unit.argtypes = [C.c_char_p]
+    L.ref_set_unit_path.argtypes = [C.c_int, C.c_char_p]
+    L.ref_set_max_subrecord.argtypes = [C.c_ulonglong]
     L.ref_collective_seconds.argtypes = [C.c_int, C.c_int]
     L.ref_collective_seconds.restype = C.c_double
 

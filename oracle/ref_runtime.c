@@ -183,6 +183,66 @@ static void ref_mpi_wait(int *request) {
   g_t_allreduce[t_rank] += now_s() - t0;
 }
 
+/* ---- unformatted sequential files (write(u) list / read(u) list of restrt, F:9696-9751) ----------------------------
+ * What a Fortran run-time library does for form='unformatted': the items of one statement form one record, framed by two
+ * 4-byte length markers; a record longer than the sub-record limit (gfortran: 2^31 - 9 bytes) is split, a negative leading
+ * marker saying "continued", a negative trailing marker "has a predecessor".  File names are character expressions the
+ * translator does not evaluate: the test sets the path of a unit with ref_set_unit_path.  One open file per unit and rank. */
+#define REF_MAX_UNIT 100
+static char g_unit_path[REF_MAX_UNIT][512];
+static __thread FILE *t_unit[REF_MAX_UNIT];
+static __thread struct { int unit, writing; char *buf; size_t len, cap, pos; } t_rec;
+static unsigned long long g_max_sub = 2147483639ull;
+void ref_set_unit_path(int unit, const char *path) { if (unit >= 0 && unit < REF_MAX_UNIT) snprintf(g_unit_path[unit], sizeof g_unit_path[unit], "%s", path); }
+void ref_set_max_subrecord(unsigned long long bytes) { g_max_sub = bytes ? bytes : 2147483639ull; }
+static void ref_unit_open(int unit, int replace) {
+  if (t_unit[unit]) fclose(t_unit[unit]);
+  t_unit[unit] = fopen(g_unit_path[unit], replace ? "wb" : "rb");
+  if (!t_unit[unit]) { fprintf(stderr, "ref_unit_open: cannot open unit %d (%s)\n", unit, g_unit_path[unit]); abort(); }
+}
+static void ref_unit_close(int unit) { if (t_unit[unit]) { fclose(t_unit[unit]); t_unit[unit] = NULL; } }
+static void ref_rec_begin(int unit, int writing) {
+  t_rec.unit = unit; t_rec.writing = writing; t_rec.len = 0; t_rec.pos = 0;
+  if (!t_unit[unit]) { fprintf(stderr, "ref_rec_begin: unit %d is not open\n", unit); abort(); }
+  if (writing) return;
+  for (;;) {                                    /* gather the sub-records of one record */
+    int m0 = 0, m1 = 0;
+    if (fread(&m0, 4, 1, t_unit[unit]) != 1) { fprintf(stderr, "ref read: end of file on unit %d\n", unit); abort(); }
+    const size_t n = (size_t)(m0 < 0 ? -(long)m0 : m0);
+    if (t_rec.len + n > t_rec.cap) { t_rec.cap = (t_rec.len + n) * 2 + 64; t_rec.buf = (char *)realloc(t_rec.buf, t_rec.cap); }
+    if (n && fread(t_rec.buf + t_rec.len, 1, n, t_unit[unit]) != n) { fprintf(stderr, "ref read: short record\n"); abort(); }
+    t_rec.len += n;
+    if (fread(&m1, 4, 1, t_unit[unit]) != 1) { fprintf(stderr, "ref read: missing trailing marker\n"); abort(); }
+    if (m0 >= 0) break;
+  }
+}
+static void ref_rec_item(void *p, long bytes) {
+  if (t_rec.writing) {
+    if (t_rec.len + (size_t)bytes > t_rec.cap) { t_rec.cap = (t_rec.len + (size_t)bytes) * 2 + 64; t_rec.buf = (char *)realloc(t_rec.buf, t_rec.cap); }
+    memcpy(t_rec.buf + t_rec.len, p, (size_t)bytes);
+    t_rec.len += (size_t)bytes;
+  } else {
+    if (t_rec.pos + (size_t)bytes > t_rec.len) { fprintf(stderr, "ref read: io-list longer than the record\n"); abort(); }
+    memcpy(p, t_rec.buf + t_rec.pos, (size_t)bytes);
+    t_rec.pos += (size_t)bytes;
+  }
+}
+static void ref_rec_end(void) {
+  if (!t_rec.writing) return;
+  FILE *f = t_unit[t_rec.unit];
+  size_t off = 0;
+  int first = 1;
+  do {
+    const size_t n = (t_rec.len - off > g_max_sub) ? (size_t)g_max_sub : t_rec.len - off;
+    const int more = off + n < t_rec.len;
+    const int lead = more ? -(int)n : (int)n, trail = first ? (int)n : -(int)n;
+    fwrite(&lead, 4, 1, f);
+    if (n) fwrite(t_rec.buf + off, 1, n, f);
+    fwrite(&trail, 4, 1, f);
+    off += n; first = 0;
+  } while (off < t_rec.len);
+}
+
 #include "mrgref_gen.c"
 
 /* ---- pool of ranks --------------------------------------------------------------------------------- */
