@@ -15,9 +15,13 @@
  * section; a rank of a multi-rank job writes its owned subset into its own file (first / stride are stored in a trailing
  * record of this library, not of the reference) -- merging them is host work.
  *
- * PARITY UNPINNED for this file format: the record layout is restated from F:9696-9728 and gfortran's documented
- * framing; no Fortran compiler exists here to write a reference file (tests check the framing, a round trip, and that the
- * payload equals mrg_download_particles).
+ * PARITY: pinned to the reference's own restrt.  The image has no Fortran compiler, so the reference's restrt runs through
+ * the translated code (oracle/f03c.py turns its write(12)/read(12) statements into record calls of oracle/ref_runtime.c,
+ * an independent implementation of the same framing).  tests/test_restart_records.py: the file that restrt(iresrt=2)
+ * writes after a step of the reference's time cycle holds 12 records; the last four are byte-identical to what this
+ * library writes for the same particles -- from host arrays and from particles resident (and sorted) in HBM -- and the
+ * reference's restrt(iresrt=1) reads a file whose particle records came from here.  What stays a convention is the
+ * marker format itself (gfortran's documented one); both implementations of it agree byte for byte, sub-records included.
  */
 #ifndef MRG_RESTART_H
 #define MRG_RESTART_H

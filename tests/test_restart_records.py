@@ -1,7 +1,9 @@
 """The particle records of the reference's restart file (F:9722-9725), written from HBM by libmrg_host (csrc/mrg_restart.*).
-CPU part: the Fortran unformatted framing (4-byte markers, subrecord split with signed markers).  GPU part: the four records
-round-trip through a second context and carry exactly what mrg_download_particles returns.  The reference cannot be run to
-produce a file here (its restrt I/O needs a Fortran run time), so this format is restated, not pinned: see the header."""
+CPU part: the Fortran unformatted framing (4-byte markers, subrecord split with signed markers), and the pin: the
+reference's own restrt (translated, oracle/_ref) writes its unit 12 after a step of its time cycle -- the last four records
+of that file are byte-identical to what the product-side writer produces, and the reference's restrt(iresrt=1) reads a file
+whose particle records came from that writer.  GPU part: the four records round-trip through a second context, carry exactly
+what mrg_download_particles returns, and the device-written file equals the reference-written file byte for byte."""
 import ctypes as C
 import os
 import struct
