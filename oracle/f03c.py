@@ -17,7 +17,9 @@ include files; executable statements: assignment (scalar, whole-array fill), blo
 EQUIVALENCE of local arrays overlaid from their first elements (the one form on the path, F:6107); ENTRY without
 arguments (`entry prefld` inside emfild, F:3820: one body function with a selector, one wrapper per callable
 name); mpi_allreduce / mpi_allgather / mpi_isend / mpi_irecv / mpi_wait map onto the simulated ranks of
-oracle/ref_runtime.c.  I/O statements (write/read/open/close/print/format/rewind) are dropped.  Expressions follow Fortran
+oracle/ref_runtime.c; unformatted sequential I/O on a numbered unit (`write(12) list`, `read(12) list` with implied
+DO lists, `open(...,form='unformatted')`, `close`: the restart file of restrt) becomes record calls of that run time.
+Formatted I/O statements (write/read/open/close/print/format/rewind on the log and plot units) are dropped.  Expressions follow Fortran
 typing: integer division truncates, default-real literals (no `d` exponent) are single precision,
 mixed-mode promotion as in Fortran (which C's usual arithmetic conversions reproduce), x**n by the
 multiplication chain gcc/gfortran use (__powidf2 order), left-to-right association of equal-precedence
