@@ -230,3 +230,39 @@
       rout(3)= tot(1)
       return
       end subroutine ring
+!
+!
+      subroutine dump (iwhat)
+!  iwhat = 2 writes two unformatted records, iwhat = 1 reads them back into other variables
+      use, intrinsic :: iso_c_binding
+      implicit none
+      integer(C_INT) iwhat,i,j,n,kk(4),ll(4),nback
+      real(C_DOUBLE) a(2,3),b(2,3),s,sback
+      real(C_float)  r4(3),q4(3)
+      common/dumpc/ b,sback,q4,ll,nback
+!
+      if(iwhat.eq.1) go to 100
+      n= 7
+      s= 2.5d0
+      do i= 1,4
+      kk(i)= 10*i
+      end do
+      do j= 1,3
+      do i= 1,2
+      a(i,j)= i +10*j
+      end do
+      r4(j)= 0.5*j
+      end do
+      open (unit=31,file='ignored'//'.bin',status='replace',form='unformatted')
+      write(31) n,(kk(i),i=1,4),s
+      write(31) ((a(i,j),i=1,2),j=1,3),r4
+      close(31)
+      return
+!
+  100 continue
+      open (unit=31,file='ignored'//'.bin',form='unformatted')
+      read(31) nback,(ll(i),i=1,4),sback
+      read(31) b,q4
+      close(31)
+      return
+      end subroutine dump

@@ -3,7 +3,8 @@ Fortran semantics on small sources written for this purpose (tests/f03c_cases/se
 default-real literals, x**n, parentheses, DO trip counts and the value of the DO variable afterwards, shared terminal labels,
 GO TO, COMMON blocks viewed through different member lists, by-reference arguments (array elements, expression
 temporaries), functions, SAVE/DATA, EQUIVALENCE, ENTRY, and the simulated MPI ranks (isend/irecv/wait ring, rank-ordered
-allreduce).  Expected values are worked out by hand from the Fortran standard's rules.  Needs gcc only."""
+allreduce), and unformatted sequential records.  Expected values are worked out by hand from the Fortran standard's
+rules.  Needs gcc only."""
 import os
 import subprocess
 import sys
@@ -16,7 +17,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 from oracle import pyref as PR          # noqa: E402
 
 CASES = os.path.join(ROOT, "tests", "f03c_cases")
-UNITS = ["arith", "loops", "blocks_a", "blocks_b", "caller", "overlay", "twodoors", "sidedoor", "ring"]
+UNITS = ["arith", "loops", "blocks_a", "blocks_b", "caller", "overlay", "twodoors", "sidedoor", "ring", "dump"]
 
 
 @pytest.fixture(scope="module")
@@ -101,3 +102,25 @@ def test_simulated_ranks_exchange_and_reduce_in_rank_order(lib):
     tot = 0.0 + 0.1 * 1
     tot = tot + 0.1 * 2
     assert outs[0][2] == outs[1][2] == tot
+
+
+def test_unformatted_records(lib, tmp_path):
+    """write(u) list / read(u) list: one record per statement, implied DO lists in storage order, mixed kinds; the file is
+    what a Fortran run time writes (4-byte markers)"""
+    import struct
+    path = str(tmp_path / "unit31.bin")
+    lib.ref_set_unit_path(31, path.encode())
+    with PR.RefRun(4, 3, 4, 10, nranks=1, npc=2, lib=lib) as R:
+        R.call("dump", 2)
+        raw = open(path, "rb").read()
+        n1 = 4 + 16 + 8                       # n, kk(1:4), s
+        n2 = 6 * 8 + 3 * 4                    # a(2,3) in column-major order, r4(3)
+        assert len(raw) == n1 + n2 + 16
+        assert struct.unpack("<i", raw[:4])[0] == n1 == struct.unpack("<i", raw[4 + n1:8 + n1])[0]
+        assert struct.unpack("<i5id", raw[:8 + n1 - 4])[1:] == (7, 10, 20, 30, 40, 2.5)
+        rec2 = raw[8 + n1 + 4:8 + n1 + 4 + n2]
+        assert struct.unpack("<6d3f", rec2) == (11.0, 12.0, 21.0, 22.0, 31.0, 32.0, 0.5, 1.0, 1.5)
+        R.call("dump", 1)
+        assert R.arr("dumpc", "b", unit="dump").tolist() == [11.0, 12.0, 21.0, 22.0, 31.0, 32.0]
+        assert float(R.get("dumpc", "sback", unit="dump")) == 2.5 and int(R.get("dumpc", "nback", unit="dump")) == 7
+        assert R.arr("dumpc", "q4", unit="dump").tolist() == [0.5, 1.0, 1.5] and R.arr("dumpc", "ll", unit="dump").tolist() == [10, 20, 30, 40]
