@@ -364,3 +364,42 @@ def test_bench_reference_arm_on_a_tiny_sample(monkeypatch):
     rec = bench.cpu_baseline_record(r)
     assert rec["unit"] == bench.UNIT and "ful(1)_s_per_step" in rec and "em_s_per_step" in rec
     assert "2 species = %d particles" % (2 * 32 * 8 * 6 * 8) in rec["sample"]
+
+
+@needs_ref
+def test_drop_in_at_baseline_config1_scale():
+    """BASELINE configs[0] in size and rank count -- 32 x 32 x 32 cells, 4 ranks, 10 steps (at the 32 particles per cell the
+    reference's loader hard-codes, F:8941: 2.1 M particles) -- through the reference's whole time cycle, once with its own
+    fulmov and once with the C oracle in fulmov's place: fields, particles and every rank's RNG state bit-identical after
+    the ten steps (two of them smoothing steps of emfild)."""
+    grid, nranks, steps = (32, 32, 32), 4, 10
+    p, p0 = U.make_parm(*grid), U.make_parm(*grid, dt=0.0)
+    box = (p.xmax, p.ymax, p.zmax)
+    with PR.ReferenceLoop(grid, box, nranks) as A:
+        A.startup()
+        for _ in range(steps):
+            A.begin_step(); A.fulmov(1); A.emfild(); A.fulmov(0); A.renew()
+        fa, pa, ra = A.fields(), A.particles(), A.ranfb()
+        assert A.ranks_agree()
+    sp, ranfb = U.load_species(p, 32)
+    arrs = {k: [a.copy() for a in sp[k]] for k in (1, 2)}
+    st = np.full(nranks, ranfb, dtype=np.int32)
+
+    def particle_pass(L, parm, ipc):
+        a6 = O.field_prep(parm, L.fields())
+        for k in (1, 2):
+            r = O.fulmov(parm, a6, *arrs[k], U.QSPEC[k], U.WSPEC[k], ipc, nranks=nranks, ranfb=st)
+            if ipc:
+                L.set_moments(k, r["mom"])
+
+    with PR.ReferenceLoop(grid, box, nranks) as B:
+        B.startup(lambda L: particle_pass(L, p0, 1))
+        for _ in range(steps):
+            B.begin_step(); particle_pass(B, p, 1); B.emfild(); particle_pass(B, p, 0); B.renew()
+        fb = B.fields()
+    for a, b in zip(fa, fb):
+        np.testing.assert_array_equal(a, b)
+    for k in (1, 2):
+        for c in range(6):
+            np.testing.assert_array_equal(pa[k][c], arrs[k][c])
+    assert ra == [int(v) for v in st]
