@@ -113,7 +113,8 @@ def test_cuda_path_matches_reference_time_cycle(tile):
     assert gpu["ranfb"] == [int(v) for v in G["ranfb_out"]]
 
 
-def test_cuda_path_as_drop_in_inside_the_reference_time_cycle():
+@pytest.mark.parametrize("grid,nranks,steps", [((8, 6, 8), 2, 3), ((32, 32, 32), 4, 10)], ids=["small", "config1_scale"])
+def test_cuda_path_as_drop_in_inside_the_reference_time_cycle(grid, nranks, steps):
     """The drop-in claim on the GPU: the reference's own time cycle with its own field solver (oracle/_ref: prefld, emfild ->
     emcoef, cfpsol, bcgstb, emfld0; 2 simulated ranks), with the CUDA path in fulmov's place -- fields out of COMMON
     /fields/, summed folded moments into COMMON /srimp7/, particles resident on the GPU -- against the same cycle run
@@ -125,7 +126,6 @@ def test_cuda_path_as_drop_in_inside_the_reference_time_cycle():
     if not PR.available():
         pytest.skip("oracle/_ref is not built and /root/reference is not here")
     import mrg_b200 as mrg
-    grid, nranks, steps = (8, 6, 8), 2, 3
     p, p0 = U.make_parm(*grid), U.make_parm(*grid, dt=0.0)
     box = (p.xmax, p.ymax, p.zmax)
     with PR.ReferenceLoop(grid, box, nranks) as A:
@@ -162,6 +162,6 @@ def test_cuda_path_as_drop_in_inside_the_reference_time_cycle():
     err_e = max(float(np.abs(a - b).max()) for a, b in zip(fa[:3], fb[:3])) / e_scale
     err_b = max(float(np.abs(a - b).max()) for a, b in zip(fa[3:6], fb[3:6])) / b_scale
     err_p = max(U.particle_err(got[k], pa[k], p.hx, U.vth(k)) for k in (1, 2))
-    print("closed loop after %d steps: E %.2e  B %.2e  particles %.2e" % (steps, err_e, err_b, err_p))
+    print("closed loop %s x %d ranks after %d steps: E %.2e  B %.2e  particles %.2e" % (grid, nranks, steps, err_e, err_b, err_p))
     assert err_e < 1e-9 and err_b < 1e-9 and err_p < 1e-9, (err_e, err_b, err_p)
     assert st == ra
