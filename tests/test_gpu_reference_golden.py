@@ -163,5 +163,10 @@ def test_cuda_path_as_drop_in_inside_the_reference_time_cycle(grid, nranks, step
     err_b = max(float(np.abs(a - b).max()) for a, b in zip(fa[3:6], fb[3:6])) / b_scale
     err_p = max(U.particle_err(got[k], pa[k], p.hx, U.vth(k)) for k in (1, 2))
     print("closed loop %s x %d ranks after %d steps: E %.2e  B %.2e  particles %.2e" % (grid, nranks, steps, err_e, err_b, err_p))
-    assert err_e < 1e-9 and err_b < 1e-9 and err_p < 1e-9, (err_e, err_b, err_p)
+    # 8 x 6 x 8: the solve converges hard and the loop stays at rounding level.  32^3: the reference's Bi-CGSTAB stops at
+    # eps = 1e-5 (F:4540) and turns 4e-16 of noise on the moments into 2e-7 .. 2e-6 on E within ten steps -- measured with the
+    # C oracle in the same loop (tests/test_ref_pin.py::test_closed_loop_amplifies_rounding_noise_at_32_cubed); the CUDA path
+    # landed at 2.4e-6 there.  The bound for that case is the solver's tolerance, not the particle path's.
+    bound = 1e-9 if grid == (8, 6, 8) else 3e-5
+    assert err_e < bound and err_b < bound and err_p < bound, (err_e, err_b, err_p)
     assert st == ra
