@@ -167,7 +167,7 @@ def test_cuda_path_as_drop_in_inside_the_reference_time_cycle(grid, nranks, step
     # eps = 1e-5 (F:4540) and turns 4e-16 of noise on the moments into 2e-7 .. 2e-6 on E within ten steps -- measured with the
     # C oracle in the same loop (tests/test_ref_pin.py::test_closed_loop_amplifies_rounding_noise_at_32_cubed); the CUDA path
     # landed at 2.4e-6 there.  The bound for that case is the solver's tolerance, not the particle path's.
-    bound = 1e-9 if grid == (8, 6, 8) else 3e-5
+    bound = 1e-9 if grid == (8, 6, 8) else 1e-4       # ten solves at eps = 1e-5
     assert err_e < bound and err_b < bound and err_p < bound, (err_e, err_b, err_p)
     if grid == (8, 6, 8):       # at solver-level deviations a particle next to the drive slab's edge may change sides: one more draw
         assert st == ra
